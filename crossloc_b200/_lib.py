@@ -1,0 +1,50 @@
+"""ctypes binding of libcrossloc_b200.so (the C ABI declared in include/crossloc_b200.h).
+
+There is no fallback: if the library is missing or a symbol is absent the import fails loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_C', 'libcrossloc_b200.so')
+
+_c = ctypes
+_f32p = _c.POINTER(_c.c_float)
+_f64p = _c.POINTER(_c.c_double)
+_i32p = _c.POINTER(_c.c_int32)
+
+# name -> (restype, argtypes); mirrors include/crossloc_b200.h one to one
+SIGNATURES = {
+    'cl_version': (_c.c_char_p, []),
+    'cl_last_error': (_c.c_char_p, []),
+    'cl_dsac_forward_rgb': (_c.c_int, [
+        _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_float,
+        _c.c_void_p, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_int,
+        _c.c_uint64, _c.c_uint32, _c.c_uint32, _c.c_int,
+        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and bind every declared entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'crossloc_b200: %s is missing -- build it with `python -m crossloc_b200.build` '
+            '(or __graft_entry__.build()); there is no CPU or PyTorch fallback for this path.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        raise RuntimeError('crossloc_b200: ' + load().cl_last_error().decode())

@@ -1,0 +1,73 @@
+// extern "C" entry points declared in include/crossloc_b200.h -- common part and the DSAC* solver.
+#include "../../include/crossloc_b200.h"
+
+#include "cabi_common.h"
+#include "dsac.h"
+
+namespace cl {
+
+thread_local std::string g_last_error;
+
+Workspace& workspace_for_current_device()
+{
+    static Workspace ws[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return ws[dev & 63];
+}
+
+std::mutex& api_mutex()
+{
+    static std::mutex m;
+    return m;
+}
+
+}  // namespace cl
+
+extern "C" const char* cl_version(void) { return "crossloc_b200 0.1.0 sm_100a"; }
+
+extern "C" const char* cl_last_error(void) { return cl::g_last_error.c_str(); }
+
+extern "C" int cl_dsac_forward_rgb(const float* coords, int B, int Hc, int Wc, float* out_pose, int hyps, float thr,
+                                   const float* focal, float cx, float cy, float alpha, float max_reproj,
+                                   int subsample, uint64_t seed, uint32_t image_base, uint32_t max_tries, int refine,
+                                   const int32_t* forced_samples, int32_t* out_best, double* out_scores,
+                                   double* out_hyps, int32_t* out_tries, int32_t* out_counts, double* out_rt,
+                                   void* cuda_stream)
+{
+    using namespace cl;
+    if (!coords || !out_pose || !focal) return fail(-1, "cl_dsac_forward_rgb: coords, out_pose and focal must not be NULL");
+    if (B < 0 || Hc <= 0 || Wc <= 0 || hyps <= 0 || subsample <= 0)
+        return fail(-1, "cl_dsac_forward_rgb: invalid sizes B=%d Hc=%d Wc=%d hyps=%d subsample=%d", B, Hc, Wc, hyps, subsample);
+    if (B > 65535) return fail(-1, "cl_dsac_forward_rgb: B=%d exceeds the 65535 images one launch takes", B);
+    if (max_tries == 0) return fail(-1, "cl_dsac_forward_rgb: max_tries must be >= 1");
+    if (B == 0) return 0;
+
+    std::lock_guard<std::mutex> lock(api_mutex());
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    Workspace& ws = workspace_for_current_device();
+    Stager st(ws, stream);
+    const size_t n = (size_t)Hc * Wc;
+
+    DsacArgs a{};
+    a.B = B; a.Hc = Hc; a.Wc = Wc; a.hyps = hyps; a.thr = thr; a.cx = cx; a.cy = cy; a.alpha = alpha;
+    a.max_reproj = max_reproj; a.S = subsample; a.seed = seed; a.image_base = image_base; a.max_tries = max_tries;
+    a.refine = refine;
+    CL_CUDA(st.in("dsac.coords", coords, (size_t)B * 3 * n, &a.coords));
+    CL_CUDA(st.in("dsac.focal", focal, (size_t)B, &a.focal));
+    CL_CUDA(st.in("dsac.forced", forced_samples, (size_t)B * hyps * 8, &a.forced));
+    CL_CUDA(st.out("dsac.pose", out_pose, (size_t)B * 16, &a.out_pose));
+    CL_CUDA(st.out("dsac.best", out_best, (size_t)B, &a.out_best));
+    CL_CUDA(st.out("dsac.scores", out_scores, (size_t)B * hyps, &a.scores, /*always=*/true));
+    CL_CUDA(st.out("dsac.hyps", out_hyps, (size_t)B * hyps * 6, &a.hyp_rt, /*always=*/true));
+    CL_CUDA(st.out("dsac.tries", out_tries, (size_t)B * hyps, &a.tries));
+    CL_CUDA(st.out("dsac.counts", out_counts, (size_t)B * 100, &a.out_counts));
+    CL_CUDA(st.out("dsac.rt", out_rt, (size_t)B * 6, &a.out_rt));
+    void* errs;
+    CL_CUDA(ws.get("dsac.errs", (size_t)B * n * sizeof(float), &errs));
+    a.errs = static_cast<float*>(errs);
+
+    CL_CUDA(dsac_forward_launch(a, stream));
+    CL_CUDA(st.finish());
+    return 0;
+}

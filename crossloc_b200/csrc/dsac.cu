@@ -1,0 +1,397 @@
+// DSAC* RGB forward on the GPU (sm_100a): hypothesis sampling + P3P, soft-inlier scoring,
+// selection and iterative refinement, batched over images.
+//
+// Replaces /root/reference/dsacstar/dsacstar.cpp:63-178 (dsacstar_rgb_forward) and the helpers in
+// /root/reference/dsacstar/dsacstar_util.h that it calls:
+//   sampleHypotheses :135-221 -> dsac_sample_kernel   one warp per hypothesis, lane = try index
+//   getReproErrs     :356-446 \  dsac_score_kernel    one block per (image, hypothesis); the [3,Hc*Wc]
+//   getHypScores     :316-343 /                       map is streamed with coalesced fp32 loads
+//   softMax/draw     :684-752 \  dsac_refine_kernel   one block per image
+//   refineHyp        :522-597 |
+//   pose2trans       :759-770 /
+// The per-hypothesis error maps the reference materialises (dsacstar.cpp:121) are never written:
+// only the winner's map is recomputed for the refinement.
+#include <cuda_runtime.h>
+
+#include "dsac.h"
+#include "dsac_common.cuh"
+
+namespace cl {
+
+namespace {
+
+constexpr int kSampleWarps = 4;
+constexpr int kScoreThreads = 256;
+constexpr int kRefineThreads = 512;
+constexpr int kMaxRefSteps = 100;   // dsacstar.cpp:47
+constexpr double kProbEps = 1e-8;   // dsacstar_util.h:45
+
+__device__ __forceinline__ void cell_pixel(int x, int y, int S, int& px, int& py)
+{
+    px = x * S + S / 2;   // dsacstar_util.h:70-72
+    py = y * S + S / 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sampling: lane l of the warp evaluates try (round * 32 + l); the lowest accepted try wins, which is
+// what the reference's sequential retry loop (dsacstar_util.h:159-220) returns for the same draws.
+__global__ void __launch_bounds__(kSampleWarps * 32) dsac_sample_kernel(DsacArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
+    const int b = blockIdx.y;
+    if (h >= a.hyps) return;
+    const int n = a.Hc * a.Wc;
+    const float* X = a.coords + (size_t)b * 3 * n;
+    const double f = a.focal[b], cx = a.cx, cy = a.cy;
+    const double thr = a.thr;
+    const uint32_t image = a.image_base + (uint32_t)b;
+    const bool forced = a.forced != nullptr;
+    const uint32_t max_tries = forced ? 1u : a.max_tries;
+
+    Pose win;
+    uint32_t tries_used = max_tries;
+    for (uint32_t base = 0; base < max_tries; base += 32) {
+        const uint32_t t = base + lane;
+        Pose cand;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { cand.r[j] = 0; cand.t[j] = 0; }
+        bool accept = false;
+        if (t < max_tries) {
+            int cells[8];
+            if (forced) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) cells[j] = a.forced[((size_t)b * a.hyps + h) * 8 + j];
+            } else {
+                sample_cells(a.seed, image, (uint32_t)h, t, a.Wc, a.Hc, cells);
+            }
+            double obj[12], img[8];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = cells[2 * j], y = cells[2 * j + 1], i = y * a.Wc + x;
+                int px, py;
+                cell_pixel(x, y, a.S, px, py);
+                img[2 * j] = px; img[2 * j + 1] = py;
+                obj[3 * j] = X[i]; obj[3 * j + 1] = X[n + i]; obj[3 * j + 2] = X[2 * n + i];
+            }
+            if (p3p_solve(obj, img, f, cx, cy, cand)) {
+                double R[9];
+                rodrigues(cand.r, R);
+                accept = true;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    double u, v;
+                    project_point(R, cand.t, f, cx, cy, obj[3 * j], obj[3 * j + 1], obj[3 * j + 2], u, v);
+                    const float du = (float)img[2 * j] - (float)u, dv = (float)img[2 * j + 1] - (float)v;
+                    if (!(sqrt((double)du * du + (double)dv * dv) < thr)) accept = false;   // strict <, :210
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 3; j++) { cand.r[j] = 0; cand.t[j] = 0; }   // safeSolvePnP, :114-116
+            }
+            if (forced) accept = true;   // replay mode: the injected sample is the hypothesis
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, accept);
+        const bool last_round = base + 32 >= max_tries;
+        if (m || last_round) {
+            // no accepted try within max_tries: the reference is left with its last try's result
+            const int src = m ? __ffs(m) - 1 : (int)(max_tries - 1 - base);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                win.r[j] = __shfl_sync(0xffffffffu, cand.r[j], src);
+                win.t[j] = __shfl_sync(0xffffffffu, cand.t[j], src);
+            }
+            tries_used = base + (uint32_t)src + 1;
+            break;
+        }
+    }
+    if (lane == 0) {
+        double* o = a.hyp_rt + ((size_t)b * a.hyps + h) * 6;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { o[j] = win.r[j]; o[3 + j] = win.t[j]; }
+        if (a.tries) a.tries[(size_t)b * a.hyps + h] = (int32_t)tries_used;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NV, int THREADS>
+__device__ __forceinline__ void block_reduce_sum(double (&v)[NV], double* smem /* [THREADS/32 * NV + NV] */)
+{
+    constexpr int kWarps = THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+    }
+    __syncthreads();   // protects smem reuse across consecutive reductions
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) smem[warp * NV + j] = v[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < kWarps; w++) s += smem[w * NV + threadIdx.x];
+        smem[kWarps * NV + threadIdx.x] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; j++) v[j] = smem[kWarps * NV + j];
+}
+
+// Scoring: block (h, b) streams the image's planar X, Y, Z once (12 B per cell, coalesced), projects
+// in double like cv::projectPoints, and accumulates 1 - sigmoid(beta (err - thr)) in double.
+__global__ void __launch_bounds__(kScoreThreads) dsac_score_kernel(DsacArgs a)
+{
+    __shared__ double red[(kScoreThreads / 32 + 1) * 1];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int n = a.Hc * a.Wc;
+    const float* X = a.coords + (size_t)b * 3 * n;
+    const double* rt = a.hyp_rt + ((size_t)b * a.hyps + h) * 6;
+    const double r[3] = {rt[0], rt[1], rt[2]}, t[3] = {rt[3], rt[4], rt[5]};
+    double R[9];
+    rodrigues(r, R);
+    const float f = a.focal[b];
+    const float beta = 5 / a.thr;   // dsacstar_util.h:324
+    double acc[1] = {0};
+    for (int i = threadIdx.x; i < n; i += kScoreThreads) {
+        const int y = i / a.Wc, x = i - y * a.Wc;
+        int px, py;
+        cell_pixel(x, y, a.S, px, py);
+        const float e = repro_error(R, t, f, a.cx, a.cy, X[i], X[n + i], X[2 * n + i], px, py, a.max_reproj);
+        double soft = beta * (e - a.thr);   // float arithmetic widened to double, :331
+        soft = 1 / (1 + exp(-soft));
+        acc[0] += 1 - soft;
+    }
+    block_reduce_sum<1, kScoreThreads>(acc, red);
+    if (threadIdx.x == 0) a.scores[(size_t)b * a.hyps + h] = acc[0] * (double)(a.alpha / a.Wc / a.Hc);   // :339
+}
+
+// ---------------------------------------------------------------------------------------------
+struct LmSums {
+    double JtJ[36];
+    double Jte[6];
+    double err;
+};
+
+// Residuals (and, if want_j, the normal equations) of the pixel reprojection error over the current
+// inlier set { i : errs[i] < thr }, reduced over the block.  Every thread returns the same sums.
+template <bool WANT_J>
+__device__ void lm_accumulate(const double prm[6], const float* X, const float* errs, int n, int Wc, int S, float thr,
+                              double f, double cx, double cy, double* smem, LmSums& out)
+{
+    double R[9], M[9], RM[9];
+    rodrigues(prm, R);
+    if (WANT_J) {
+        rotation_jacobian_factor(prm, R, M);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) RM[3 * i + j] = R[3 * i] * M[j] + R[3 * i + 1] * M[3 + j] + R[3 * i + 2] * M[6 + j];
+    }
+    constexpr int NV = WANT_J ? 28 : 1;
+    double acc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) acc[j] = 0;
+    for (int i = threadIdx.x; i < n; i += kRefineThreads) {
+        if (!(errs[i] < thr)) continue;   // strict <, dsacstar_util.h:550
+        const int yy = i / Wc, xx = i - yy * Wc;
+        int px, py;
+        cell_pixel(xx, yy, S, px, py);
+        const double Xw = X[i], Yw = X[n + i], Zw = X[2 * n + i];
+        const double qx = R[0] * Xw + R[1] * Yw + R[2] * Zw;
+        const double qy = R[3] * Xw + R[4] * Yw + R[5] * Zw;
+        const double qz = R[6] * Xw + R[7] * Yw + R[8] * Zw;
+        const double x = qx + prm[3], y = qy + prm[4], z = qz + prm[5];
+        const double iz = z ? 1. / z : 1;
+        const double eu = f * x * iz + cx - (double)px, ev = f * y * iz + cy - (double)py;
+        acc[NV - 1] += eu * eu + ev * ev;
+        if (WANT_J) {
+            const double a0 = f * iz, a2 = -f * x * iz * iz, b2 = -f * y * iz * iz;
+            // dp/dr = -[q]x (R M)
+            double dpdr[9];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                dpdr[j] = -(-qz * RM[3 + j] + qy * RM[6 + j]);
+                dpdr[3 + j] = -(qz * RM[j] - qx * RM[6 + j]);
+                dpdr[6 + j] = -(-qy * RM[j] + qx * RM[3 + j]);
+            }
+            double Ju[6], Jv[6];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                Ju[j] = a0 * dpdr[j] + a2 * dpdr[6 + j];
+                Jv[j] = a0 * dpdr[3 + j] + b2 * dpdr[6 + j];
+            }
+            Ju[3] = a0; Ju[4] = 0; Ju[5] = a2;
+            Jv[3] = 0; Jv[4] = a0; Jv[5] = b2;
+            int k = 0;
+#pragma unroll
+            for (int r2 = 0; r2 < 6; r2++)
+#pragma unroll
+                for (int c = r2; c < 6; c++) acc[k++] += Ju[r2] * Ju[c] + Jv[r2] * Jv[c];
+#pragma unroll
+            for (int r2 = 0; r2 < 6; r2++) acc[21 + r2] += Ju[r2] * eu + Jv[r2] * ev;
+        }
+    }
+    block_reduce_sum<NV, kRefineThreads>(acc, smem);
+    out.err = sqrt(acc[NV - 1]);
+    if (WANT_J) {
+        int k = 0;
+#pragma unroll
+        for (int r2 = 0; r2 < 6; r2++)
+#pragma unroll
+            for (int c = r2; c < 6; c++) { out.JtJ[6 * r2 + c] = acc[k]; out.JtJ[6 * c + r2] = acc[k]; k++; }
+#pragma unroll
+        for (int r2 = 0; r2 < 6; r2++) out.Jte[r2] = acc[21 + r2];
+    }
+}
+
+__device__ bool lm_step(const LmSums& s, int lambdaLg10, const double prev[6], double prm[6])
+{
+    double A[36], b[6], x[6];
+    const double lambda = exp(lambdaLg10 * log(10.));
+    for (int i = 0; i < 36; i++) A[i] = s.JtJ[i];
+    for (int i = 0; i < 6; i++) { b[i] = s.Jte[i]; A[7 * i] *= 1. + lambda; }
+    if (!solve6(A, b, x)) return false;
+    for (int i = 0; i < 6; i++) prm[i] = prev[i] - x[i];
+    return true;
+}
+
+// cv::solvePnP(SOLVEPNP_ITERATIVE, useExtrinsicGuess = true): CvLevMarq::update as driven by
+// cvFindExtrinsicCameraParams2 -- at most 20 iterations, eps = FLT_EPSILON on the relative parameter
+// change, lambda = 10^k from k = -3, k+1 on a worse step (at most 16), k-1 on an accepted one.
+__device__ bool lm_solve(double prm[6], const float* X, const float* errs, int n, int Wc, int S, float thr, double f,
+                         double cx, double cy, double* smem)
+{
+    LmSums s;
+    double prev[6];
+    int lambdaLg10 = -3, iters = 0;
+    double prevErr = DBL_MAX, errNorm;
+    for (;;) {
+        lm_accumulate<true>(prm, X, errs, n, Wc, S, thr, f, cx, cy, smem, s);
+        for (int i = 0; i < 6; i++) prev[i] = prm[i];
+        if (!lm_step(s, lambdaLg10, prev, prm)) return false;
+        if (iters == 0) prevErr = s.err;
+        for (;;) {
+            LmSums e;
+            lm_accumulate<false>(prm, X, errs, n, Wc, S, thr, f, cx, cy, smem, e);
+            errNorm = e.err;
+            if (errNorm > prevErr && ++lambdaLg10 <= 16) {
+                if (!lm_step(s, lambdaLg10, prev, prm)) return false;
+                continue;
+            }
+            break;
+        }
+        lambdaLg10 = lambdaLg10 - 1 > -16 ? lambdaLg10 - 1 : -16;
+        double dn = 0, pn = 0;
+        for (int i = 0; i < 6; i++) { dn += (prm[i] - prev[i]) * (prm[i] - prev[i]); pn += prev[i] * prev[i]; }
+        if (++iters >= 20 || sqrt(dn) / (sqrt(pn) + DBL_EPSILON) < FLT_EPSILON) break;
+        prevErr = errNorm;
+    }
+    return true;
+}
+
+// Error map of one pose into errs[] + inlier count (block-uniform return value).
+__device__ int error_map(const double prm[6], const float* X, float* errs, int n, int Wc, int S, float f, float cx,
+                         float cy, float thr, float max_reproj, double* smem)
+{
+    double R[9];
+    rodrigues(prm, R);
+    double cnt[1] = {0};
+    for (int i = threadIdx.x; i < n; i += kRefineThreads) {
+        const int y = i / Wc, x = i - y * Wc;
+        int px, py;
+        cell_pixel(x, y, S, px, py);
+        const float e = repro_error(R, prm + 3, f, cx, cy, X[i], X[n + i], X[2 * n + i], px, py, max_reproj);
+        errs[i] = e;
+        if (e < thr) cnt[0] += 1;
+    }
+    block_reduce_sum<1, kRefineThreads>(cnt, smem);
+    return (int)cnt[0];
+}
+
+__global__ void __launch_bounds__(kRefineThreads) dsac_refine_kernel(DsacArgs a)
+{
+    __shared__ double red[(kRefineThreads / 32 + 1) * 28];
+    __shared__ int s_best;
+    const int b = blockIdx.x;
+    const int n = a.Hc * a.Wc;
+    const float* X = a.coords + (size_t)b * 3 * n;
+    float* errs = a.errs + (size_t)b * n;
+    const double* scores = a.scores + (size_t)b * a.hyps;
+
+    // softMax + draw(probs, false): first maximal probability among those >= 1e-8 (dsacstar_util.h:684-752)
+    if (threadIdx.x == 0) {
+        double mx = scores[0], sum = 0;
+        for (int h = 1; h < a.hyps; h++) if (scores[h] > mx) mx = scores[h];
+        for (int h = 0; h < a.hyps; h++) sum += exp(scores[h] - mx);
+        int best = 0;
+        double bestp = -1;
+        for (int h = 0; h < a.hyps; h++) {
+            const double p = exp(scores[h] - mx) / sum;
+            if (p < kProbEps) continue;
+            if (bestp < 0 || p > bestp) { bestp = p; best = h; }
+        }
+        s_best = best;
+        if (a.out_best) a.out_best[b] = best;
+    }
+    __syncthreads();
+    const int best = s_best;
+
+    double prm[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) prm[j] = a.hyp_rt[((size_t)b * a.hyps + best) * 6 + j];
+    const float f = a.focal[b];
+
+    if (a.refine) {
+        // refineHyp (dsacstar_util.h:522-597): refit to all inliers while the inlier count grows
+        int inliers = error_map(prm, X, errs, n, a.Wc, a.S, f, a.cx, a.cy, a.thr, a.max_reproj, red);
+        int best_inliers = 4;
+        for (int step = 0; step < kMaxRefSteps; step++) {
+            if (a.out_counts && threadIdx.x == 0) a.out_counts[(size_t)b * kMaxRefSteps + step] = inliers;
+            if (inliers <= best_inliers) break;
+            best_inliers = inliers;
+            double upd[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) upd[j] = prm[j];
+            if (!lm_solve(upd, X, errs, n, a.Wc, a.S, a.thr, (double)f, (double)a.cx, (double)a.cy, red)) break;
+#pragma unroll
+            for (int j = 0; j < 6; j++) prm[j] = upd[j];
+            inliers = error_map(prm, X, errs, n, a.Wc, a.S, f, a.cx, a.cy, a.thr, a.max_reproj, red);
+        }
+    }
+
+    if (threadIdx.x == 0) {
+        // pose2trans (dsacstar_util.h:759-770): inverse of [R t; 0 1], row-major float (dsacstar.cpp:174-177)
+        double R[9];
+        rodrigues(prm, R);
+        float* o = a.out_pose + (size_t)b * 16;
+        for (int i = 0; i < 3; i++) {
+            for (int j = 0; j < 3; j++) o[4 * i + j] = (float)R[3 * j + i];
+            o[4 * i + 3] = (float)-(R[i] * prm[3] + R[3 + i] * prm[4] + R[6 + i] * prm[5]);
+        }
+        o[12] = o[13] = o[14] = 0;
+        o[15] = 1;
+        if (a.out_rt)
+            for (int j = 0; j < 6; j++) a.out_rt[(size_t)b * 6 + j] = prm[j];
+    }
+}
+
+}  // namespace
+
+cudaError_t dsac_forward_launch(const DsacArgs& a, cudaStream_t stream)
+{
+    if (a.B <= 0 || a.hyps <= 0) return cudaSuccess;
+    if (a.out_counts) {
+        cudaError_t e = cudaMemsetAsync(a.out_counts, 0xff, sizeof(int32_t) * (size_t)a.B * kMaxRefSteps, stream);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 gs((a.hyps + kSampleWarps - 1) / kSampleWarps, a.B);
+    dsac_sample_kernel<<<gs, kSampleWarps * 32, 0, stream>>>(a);
+    dsac_score_kernel<<<dim3(a.hyps, a.B), kScoreThreads, 0, stream>>>(a);
+    dsac_refine_kernel<<<a.B, kRefineThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace cl
