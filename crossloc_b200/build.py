@@ -22,6 +22,9 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-ccbin', '/u
 UNITS = {
     'cabi.cu': [],
     'dsac.cu': ['--fmad=false'],
+    'cabi_cnn.cu': [],
+    'conv_igemm.cu': [],
+    'cnn_pointwise.cu': [],
 }
 
 

@@ -1,0 +1,315 @@
+"""Host side of the scene-coordinate CNN: weight packing, workspace and the layer plan.
+
+The arithmetic runs in libcrossloc_b200.so (cl_stem_forward, cl_conv_igemm, cl_gn_apply, cl_head_forward);
+this file only lays tensors out in HBM and sequences the launches for the two network families of the
+reference (/root/reference/networks/networks.py): `TransPoseNet` (:363-502, GroupNorm) and the vanilla
+DSAC* `Network` (:43-130, no normalisation).  PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import math
+import os
+
+import torch
+
+from . import _lib
+
+# 'fp16x3' (default): every product as three fp16 tensor-core passes, fp32-grade (4e-6 on the coordinate map).
+# 'fp16x1': one pass, 1.1e-3 relative on the coordinate map -- above the 1e-3 parity bar, offered for speed only.
+PRECISION = os.environ.get('CROSSLOC_B200_CONV_PRECISION', 'fp16x3')
+
+
+def _nterms(precision):
+    if precision == 'fp16x3':
+        return 3
+    if precision == 'fp16x1':
+        return 1
+    raise ValueError('unknown conv precision %r (fp16x3 | fp16x1)' % (precision,))
+
+
+class PackedConv:
+    """Weights of one convolution in the tensor-core layout: fp16 [term][tap][Cout][Cin], scaled by a power of two."""
+
+    def __init__(self, weight, bias, stride, nterms):
+        cout, cin, kh, kw = weight.shape
+        assert kh == kw and kh in (1, 3) and stride in (1, 2)
+        self.cin, self.cout, self.ksize, self.stride, self.nterms = cin, cout, kh, stride, nterms
+        w = weight.detach().to(torch.float32)
+        amax = float(w.abs().max())
+        # power-of-two pre-scale keeps the fp16 low-order term out of the subnormal range; undone in the epilogue
+        exp = 0 if amax == 0.0 else int(math.floor(math.log2(128.0 / amax)))
+        exp = max(-24, min(24, exp))
+        self.out_scale = float(2.0 ** (-exp))
+        w = (w * (2.0 ** exp)).permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)   # [tap][Cout][Cin]
+        hi = w.to(torch.float16)
+        planes = [hi]
+        if nterms == 3:
+            planes.append((w - hi.to(torch.float32)).to(torch.float16))
+        self.weights = torch.stack(planes, 0).contiguous()
+        self.bias = (bias.detach().to(torch.float32) if bias is not None
+                     else torch.zeros(cout, dtype=torch.float32, device=weight.device)).contiguous()
+
+
+class _Geometry:
+    """Padded-flat geometry of one resolution level."""
+
+    def __init__(self, batch, h, w):
+        self.B, self.H, self.W = batch, h, w
+        self.Hp, self.Wp = h + 2, w + 2
+        self.plane = self.Hp * self.Wp
+        self.Mp = batch * self.plane
+
+
+def _taps(pack, geo):
+    """Activation row shift of every filter tap in the padded-flat layout of the OUTPUT resolution."""
+    if pack.ksize == 1:
+        return [0]
+    out = []
+    for kh in range(3):
+        for kw in range(3):
+            if pack.stride == 1:
+                out.append((kh - 1) * geo.Wp + (kw - 1))
+            else:
+                a, dy = (1, -1) if kh == 0 else ((0, 0) if kh == 1 else (1, 0))
+                b, dx = (1, -1) if kw == 0 else ((0, 0) if kw == 1 else (1, 0))
+                out.append((a * 2 + b) * geo.Mp + dy * geo.Wp + dx)
+    return out
+
+
+class CoordNetEngine:
+    """Runs the coordinate network of an nn.Module twin (networks.networks.TransPoseNet / Network)."""
+
+    def __init__(self, precision=None):
+        self.precision = precision or PRECISION
+        self.nterms = _nterms(self.precision)
+        self.terms = 2 if self.nterms == 3 else 1
+        self._packs = {}
+        self._pack_versions = {}
+        self._ws = {}
+        self.launches = 0
+
+    # ------------------------------------------------------------------ parameters
+    def _pack(self, name, conv):
+        ver = (conv.weight._version, conv.weight.data_ptr(), None if conv.bias is None else conv.bias._version)
+        if self._pack_versions.get(name) != ver:
+            self._packs[name] = PackedConv(conv.weight, conv.bias, conv.stride[0], self.nterms)
+            self._pack_versions[name] = ver
+        return self._packs[name]
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, device, batch, h, w, channels):
+        key = (str(device), batch, h, w, self.terms, tuple(sorted(channels.items())))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        ws = {'geo': {}, 'act': {}, 'raw': {}}
+        hh, wwid = h, w
+        for level in range(4):   # level 0 = input resolution, 3 = output resolution
+            ws['geo'][level] = _Geometry(batch, hh, wwid)
+            if level < 3:
+                hh, wwid = (hh + 1) // 2, (wwid + 1) // 2
+        self._ws[key] = ws
+        ws['device'] = device
+        return ws
+
+    def _act(self, ws, tag, level, channels, phases):
+        """Zero-initialised fp16 PF buffer [terms][phases][Mp][C]; borders are never written afterwards."""
+        key = (tag, level, channels, phases)
+        buf = ws['act'].get(key)
+        if buf is None:
+            geo = ws['geo'][level]
+            buf = torch.zeros(self.terms * phases * geo.Mp, channels, dtype=torch.float16, device=ws['device'])
+            ws['act'][key] = buf
+        return buf
+
+    def _raw(self, ws, tag, level, channels):
+        key = (tag, level, channels)
+        buf = ws['raw'].get(key)
+        if buf is None:
+            geo = ws['geo'][level]
+            buf = torch.empty(geo.Mp, channels, dtype=torch.float32, device=ws['device'])
+            ws['raw'][key] = buf
+        return buf
+
+    # ------------------------------------------------------------------ operators
+    def _conv(self, stream, pack, act, in_phases, geo, raw, stats, group_ch):
+        taps = _taps(pack, geo)
+        tap_arr = (ctypes.c_int32 * len(taps))(*taps)
+        lo_rows = in_phases * geo.Mp
+        _lib.check(self._lib.cl_conv_igemm(
+            act.data_ptr(), act.size(0), lo_rows, pack.cin, pack.weights.data_ptr(), pack.cout, len(taps), tap_arr,
+            self.nterms, geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale, raw.data_ptr(), pack.bias.data_ptr(),
+            0 if stats is None else stats.data_ptr(), stream))
+        self.launches += 1
+
+    def _apply(self, stream, raw, geo, channels, norm, stats, out, out_phases, relu_inner=True, res=None,
+               raw2=None, norm2=None, stats2=None, relu_outer=False):
+        group_ch = 0 if norm is None else channels // norm.num_groups
+        add_kind = 1 if res is not None else (2 if raw2 is not None else 0)
+        _lib.check(self._lib.cl_gn_apply(
+            raw.data_ptr(), geo.B, geo.H, geo.W, channels, group_ch,
+            0 if stats is None else stats.data_ptr(),
+            0 if norm is None else norm.weight.data_ptr(), 0 if norm is None else norm.bias.data_ptr(),
+            1e-5 if norm is None else float(norm.eps), 1 if relu_inner else 0, add_kind,
+            0 if res is None else res.data_ptr(), geo.Mp,
+            0 if raw2 is None else raw2.data_ptr(), 0 if stats2 is None else stats2.data_ptr(),
+            0 if norm2 is None else norm2.weight.data_ptr(), 0 if norm2 is None else norm2.bias.data_ptr(),
+            1 if relu_outer else 0, out.data_ptr(), out_phases, self.terms, stream))
+        self.launches += 1
+
+    # ------------------------------------------------------------------ plans
+    def forward(self, spec, image):
+        """spec: dict produced by networks.networks (layer modules + head description). image: NCHW fp32 CUDA."""
+        if not image.is_cuda:
+            raise RuntimeError('crossloc_b200: the coordinate network runs on a CUDA device only (no CPU fallback)')
+        self._lib = _lib.load()
+        image = image.contiguous().to(torch.float32)
+        batch, cin, h, w = image.shape
+        dev = image.device
+        torch.cuda.set_device(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = self._workspace(dev, batch, h, w, {'cin': cin})
+        geo = ws['geo']
+        gn = spec['group_norm']
+        layers = spec['layers']          # ordered list of (name, conv, norm or None)
+        n_stat = len(layers) + 1
+        stats_all = ws.get('stats')
+        if stats_all is None or stats_all.size(0) < n_stat:
+            stats_all = torch.zeros(n_stat, batch, 32, 2, dtype=torch.float64, device=dev)
+            ws['stats'] = stats_all
+        else:
+            stats_all.zero_()
+        self._stat_i = 0
+
+        def next_stats():
+            s = stats_all[self._stat_i]
+            self._stat_i += 1
+            return s
+
+        convs = {name: (conv, norm) for name, conv, norm in layers}
+
+        def groups_of(norm, channels):
+            return 0 if norm is None else channels // norm.num_groups
+
+        # ---- stem: conv1 (+ norm1) + relu, written as the 4-phase input of conv2
+        conv1, norm1 = convs['conv1']
+        if conv1.out_channels != 32 or (norm1 is not None and norm1.num_groups != 32):
+            raise RuntimeError('crossloc_b200: the stem kernel is built for 32 channels / 32 groups')
+        a = self._act(ws, 'stem', 1, 32, 4)
+        st = next_stats() if norm1 is not None else None
+        _lib.check(self._lib.cl_stem_forward(
+            image.data_ptr(), batch, cin, h, w, conv1.weight.detach().contiguous().data_ptr(),
+            conv1.bias.detach().contiguous().data_ptr(), 1 if norm1 is not None else 0,
+            0 if st is None else st.data_ptr(), 0 if norm1 is None else norm1.weight.data_ptr(),
+            0 if norm1 is None else norm1.bias.data_ptr(), 1e-5 if norm1 is None else float(norm1.eps),
+            a.data_ptr(), self.terms, stream))
+        self.launches += 2 if norm1 is not None else 1
+
+        # ---- strided ladder conv2..conv4
+        for level, name in ((1, 'conv2'), (2, 'conv3'), (3, 'conv4')):
+            conv, norm = convs[name]
+            pack = self._pack(name, conv)
+            raw = self._raw(ws, 'ladder', level, pack.cout)
+            st = next_stats() if norm is not None else None
+            self._conv(stream, pack, a, 4, geo[level], raw, st, groups_of(norm, pack.cout))
+            if level < 3:
+                out = self._act(ws, 'ladder', level + 1, pack.cout, 4)
+                self._apply(stream, raw, geo[level], pack.cout, norm, st, out, 4)
+            else:
+                out = self._act(ws, 'res', 3, pack.cout, 1)
+                self._apply(stream, raw, geo[level], pack.cout, norm, st, out, 1)
+            a = out
+        g3 = geo[3]
+        res = a
+
+        rot = {}
+
+        def scratch(channels, avoid):
+            """A PF buffer at the output resolution that is none of `avoid`."""
+            pool = rot.setdefault(channels, [self._act(ws, 'pool%d' % i, 3, channels, 1) for i in range(4)])
+            for buf in pool:
+                if all(buf is not o for o in avoid):
+                    return buf
+            raise AssertionError
+
+        def conv_block(names, x, res_in, outer_relu):
+            """conv -> [GN] -> relu chain; the last layer merges the residual: out = [relu](res + relu(gn(conv)))."""
+            for i, name in enumerate(names):
+                conv, norm = convs[name]
+                pack = self._pack(name, conv)
+                raw = self._raw(ws, 'r%d' % (i % 2), 3, pack.cout)
+                st = next_stats() if norm is not None else None
+                self._conv(stream, pack, x, 1, g3, raw, st, groups_of(norm, pack.cout))
+                out = scratch(pack.cout, (x, res_in))
+                last = i == len(names) - 1
+                self._apply(stream, raw, g3, pack.cout, norm, st, out, 1, relu_inner=True,
+                            res=res_in if last else None, relu_outer=outer_relu and last)
+                x = out
+            return x
+
+        outer = gn   # TransPoseNet applies ReLU after every residual add (networks.py:240-254); Network does not (:105-120)
+        for block in spec['blocks']:
+            kind = block['kind']
+            if kind == 'residual':
+                res = conv_block(block['convs'], res, res, outer)
+            elif kind == 'residual_skip':
+                # x = chain(res); res = skip_norm(skip(res)); res = [relu](res + x)   (networks.py:242-249)
+                names = block['convs']
+                x = res
+                for i, name in enumerate(names[:-1]):
+                    conv, norm = convs[name]
+                    pack = self._pack(name, conv)
+                    raw = self._raw(ws, 'r%d' % (i % 2), 3, pack.cout)
+                    st = next_stats() if norm is not None else None
+                    self._conv(stream, pack, x, 1, g3, raw, st, groups_of(norm, pack.cout))
+                    out = scratch(pack.cout, (x, res))
+                    self._apply(stream, raw, g3, pack.cout, norm, st, out, 1)
+                    x = out
+                conv, norm = convs[names[-1]]
+                pack = self._pack(names[-1], conv)
+                raw_x = self._raw(ws, 'r0', 3, pack.cout)
+                st_x = next_stats() if norm is not None else None
+                self._conv(stream, pack, x, 1, g3, raw_x, st_x, groups_of(norm, pack.cout))
+                sconv, snorm = convs[block['skip']]
+                spack = self._pack(block['skip'], sconv)
+                raw_s = self._raw(ws, 'r1', 3, spack.cout)
+                st_s = next_stats() if snorm is not None else None
+                self._conv(stream, spack, res, 1, g3, raw_s, st_s, groups_of(snorm, spack.cout))
+                out = scratch(pack.cout, (x, res))
+                if gn:
+                    self._apply(stream, raw_x, g3, pack.cout, norm, st_x, out, 1, relu_inner=True,
+                                raw2=raw_s, norm2=snorm, stats2=st_s, relu_outer=outer)
+                else:
+                    # vanilla Network: res = skip(res) + relu(conv(x)), no normalisation anywhere
+                    tmp = scratch(pack.cout, (x, res, out))
+                    self._apply(stream, raw_s, g3, spack.cout, None, None, tmp, 1, relu_inner=False)
+                    self._apply(stream, raw_x, g3, pack.cout, None, None, out, 1, relu_inner=True, res=tmp)
+                res = out
+            elif kind == 'plain':
+                # conv -> [GN] -> relu without a residual (fc1, fc2)
+                for name in block['convs']:
+                    conv, norm = convs[name]
+                    pack = self._pack(name, conv)
+                    raw = self._raw(ws, 'r0', 3, pack.cout)
+                    st = next_stats() if norm is not None else None
+                    self._conv(stream, pack, res, 1, g3, raw, st, groups_of(norm, pack.cout))
+                    out = scratch(pack.cout, (res,))
+                    self._apply(stream, raw, g3, pack.cout, norm, st, out, 1)
+                    res = out
+            else:
+                raise AssertionError(kind)
+
+        # ---- head
+        head = spec['head']
+        hconv = head['conv']
+        co = hconv.out_channels
+        out = torch.empty(batch, co, g3.H, g3.W, dtype=torch.float32, device=dev)
+        mean = head['mean'].to(device=dev, dtype=torch.float32).contiguous()
+        _lib.check(self._lib.cl_head_forward(
+            res.data_ptr(), g3.Mp, self.terms, batch, g3.H, g3.W, hconv.in_channels, co,
+            hconv.weight.detach().reshape(co, -1).contiguous().data_ptr(),
+            hconv.bias.detach().contiguous().data_ptr(), mean.data_ptr(), head['num_task'],
+            head['clamp'][0], head['clamp'][1], out.data_ptr(), stream))
+        self.launches += 1
+        # keep parameter temporaries alive until the stream has consumed them
+        self._keepalive = (mean,)
+        return out

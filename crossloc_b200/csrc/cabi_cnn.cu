@@ -1,0 +1,101 @@
+// extern "C" entry points of the CNN operators declared in include/crossloc_b200.h.
+#include "../../include/crossloc_b200.h"
+
+#include "cabi_common.h"
+#include "conv.h"
+
+namespace {
+
+int need_device(const char* fn, const char* name, const void* p, bool nullable = false)
+{
+    if (!p) return nullable ? 0 : cl::fail(-1, "%s: %s must not be NULL", fn, name);
+    if (!cl::is_device_ptr(p)) return cl::fail(-1, "%s: %s must be a device pointer", fn, name);
+    return 0;
+}
+
+int finish(const char* fn, const char* err)
+{
+    if (err) return cl::fail(-2, "%s: %s", fn, err);
+    return 0;
+}
+
+}  // namespace
+
+#define NEED_DEV(name, ...)                                                \
+    do {                                                                   \
+        if (int _rc = need_device(kFn, #name, name, ##__VA_ARGS__)) return _rc; \
+    } while (0)
+
+extern "C" int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int Cin, const void* weights,
+                             int Cout, int num_taps, const int32_t* tap_a_row, int nterms, int Mp, int Hp, int Wp,
+                             int group_ch, float out_scale, float* raw, const float* bias, double* stats,
+                             void* cuda_stream)
+{
+    static const char* kFn = "cl_conv_igemm";
+    NEED_DEV(act); NEED_DEV(weights); NEED_DEV(raw); NEED_DEV(bias);
+    if (group_ch) NEED_DEV(stats);
+    if (!tap_a_row) return cl::fail(-1, "%s: tap_a_row must not be NULL", kFn);
+    if (num_taps < 1 || num_taps > 9) return cl::fail(-1, "%s: num_taps=%d out of range", kFn, num_taps);
+    if (Mp <= 0 || Hp < 3 || Wp < 3 || Mp % (Hp * Wp) != 0)
+        return cl::fail(-1, "%s: Mp=%d is not a whole number of %dx%d planes", kFn, Mp, Hp, Wp);
+    cl::ConvIgemmDesc d{};
+    d.act = act; d.a_total_rows = a_total_rows; d.a_lo_rows = a_lo_rows; d.Cin = Cin; d.weights = weights;
+    d.Cout = Cout; d.num_taps = num_taps;
+    for (int i = 0; i < num_taps; i++) d.tap_a_row[i] = tap_a_row[i];
+    d.nterms = nterms; d.Mp = Mp; d.Hp = Hp; d.Wp = Wp; d.group_ch = group_ch; d.out_scale = out_scale;
+    d.raw = raw; d.bias = bias; d.stats = stats;
+    return finish(kFn, cl::conv_igemm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}
+
+extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int group_ch, const double* stats,
+                           const float* gamma, const float* beta, float eps, int relu_inner, int add_kind,
+                           const void* res, int64_t res_lo_rows, const float* raw2, const double* stats2,
+                           const float* gamma2, const float* beta2, int relu_outer, void* out, int out_phases,
+                           int out_terms, void* cuda_stream)
+{
+    static const char* kFn = "cl_gn_apply";
+    NEED_DEV(raw); NEED_DEV(out);
+    if (group_ch) { NEED_DEV(stats); NEED_DEV(gamma); NEED_DEV(beta); }
+    if (add_kind == 1) NEED_DEV(res);
+    if (add_kind == 2) { NEED_DEV(raw2); NEED_DEV(stats2); NEED_DEV(gamma2); NEED_DEV(beta2); }
+    if (add_kind < 0 || add_kind > 2) return cl::fail(-1, "%s: add_kind=%d", kFn, add_kind);
+    if (group_ch && C % group_ch != 0) return cl::fail(-1, "%s: C=%d not divisible by group_ch=%d", kFn, C, group_ch);
+    cl::GnApplyDesc d{};
+    d.raw = raw; d.B = B; d.H = H; d.W = W; d.C = C; d.group_ch = group_ch; d.stats = stats; d.gamma = gamma;
+    d.beta = beta; d.eps = eps; d.relu_inner = relu_inner; d.add_kind = add_kind;
+    d.res = static_cast<const __half*>(res); d.res_lo_rows = res_lo_rows; d.raw2 = raw2; d.stats2 = stats2;
+    d.gamma2 = gamma2; d.beta2 = beta2; d.relu_outer = relu_outer; d.out = static_cast<__half*>(out);
+    d.out_phases = out_phases; d.out_terms = out_terms;
+    return finish(kFn, cl::gn_apply_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}
+
+extern "C" int cl_stem_forward(const float* image, int B, int Cin, int H, int W, const float* weight,
+                               const float* bias, int has_gn, double* stats, const float* gamma, const float* beta,
+                               float eps, void* out, int out_terms, void* cuda_stream)
+{
+    static const char* kFn = "cl_stem_forward";
+    NEED_DEV(image); NEED_DEV(weight); NEED_DEV(bias); NEED_DEV(out);
+    if (has_gn) { NEED_DEV(stats); NEED_DEV(gamma); NEED_DEV(beta); }
+    cl::StemDesc d{};
+    d.image = image; d.B = B; d.Cin = Cin; d.H = H; d.W = W; d.weight = weight; d.bias = bias; d.has_gn = has_gn;
+    d.stats = stats; d.gamma = gamma; d.beta = beta; d.eps = eps; d.out = static_cast<__half*>(out);
+    d.out_terms = out_terms;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    if (has_gn)
+        if (int rc = finish(kFn, cl::stem_stats_launch(d, s))) return rc;
+    return finish(kFn, cl::stem_apply_launch(d, s));
+}
+
+extern "C" int cl_head_forward(const void* act, int64_t act_lo_rows, int in_terms, int B, int H, int W, int C,
+                               int Co, const float* weight, const float* bias, const float* mean, int num_task,
+                               float clamp_lo, float clamp_hi, float* out, void* cuda_stream)
+{
+    static const char* kFn = "cl_head_forward";
+    NEED_DEV(act); NEED_DEV(weight); NEED_DEV(bias); NEED_DEV(out);
+    if (num_task > 0) NEED_DEV(mean);
+    cl::HeadDesc d{};
+    d.act = static_cast<const __half*>(act); d.act_lo_rows = act_lo_rows; d.in_terms = in_terms; d.B = B; d.H = H;
+    d.W = W; d.C = C; d.Co = Co; d.weight = weight; d.bias = bias; d.mean = mean; d.num_task = num_task;
+    d.clamp_lo = clamp_lo; d.clamp_hi = clamp_hi; d.out = out;
+    return finish(kFn, cl::head_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}

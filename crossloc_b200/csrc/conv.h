@@ -1,0 +1,106 @@
+// Launch interfaces of the CNN kernels (device pointers only).
+//
+// Activation layout ("padded-flat", PF): fp16 matrix [rows][C], row(t, ph, b, y, x) =
+//   ((t * P + ph) * B + b) * (H + 2) * (W + 2) + (y + 1) * (W + 2) + (x + 1)
+// with t = 0 (hi) / 1 (lo) fp16 split term, ph = parity phase (P = 1, or 4 when the consumer is a
+// stride-2 convolution: ph = (y_in & 1) * 2 + (x_in & 1), (y, x) = (y_in / 2, x_in / 2)), zero borders.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace cl {
+
+// ---------------------------------------------------------------- tcgen05 implicit GEMM
+struct ConvIgemmDesc {
+    const void* act;        // fp16 PF matrix, all planes
+    int64_t a_total_rows;   // rows of the whole activation matrix (bounds of the TMA map)
+    int64_t a_lo_rows;      // row distance between the hi and the lo plane
+    int Cin;
+    const void* weights;    // fp16 [term][tap][Cout][Cin]
+    int Cout;
+    int num_taps;
+    int tap_a_row[9];       // activation row shift of every tap (phase offset included)
+    int nterms;             // 1 (single fp16 pass) or 3 (fp16x3 split)
+    int Mp, Hp, Wp;         // output rows (B * Hp * Wp) and padded plane size
+    int group_ch;           // GroupNorm channels per group (0: no statistics)
+    float out_scale;        // undoes the power-of-two weight pre-scale
+    float* raw;             // fp32 [Mp][Cout] (interior rows only are written)
+    const float* bias;      // fp32 [Cout]
+    double* stats;          // fp64 [B][groups][2] sum, sum of squares (accumulated, caller zeroes)
+};
+
+struct ConvIgemmParams {
+    int num_taps;
+    int tap_a_row[9];
+    int kblocks_per_tap, nterms, a_lo_rows, w_tap_rows, w_lo_rows;
+    int Mp, Cout, BN, tiles_m, tiles_n, Hp, Wp, group_ch, groups;
+    float out_scale;
+    float* raw;
+    const float* bias;
+    double* stats;
+    int num_stages, accum_stages;
+    uint32_t a_bytes, w_bytes, stage_bytes;
+};
+
+// returns nullptr on success, else a static error string
+const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream);
+
+// ---------------------------------------------------------------- GroupNorm apply / residual merge
+struct GnApplyDesc {
+    const float* raw;       // fp32 PF [B*(H+2)*(W+2)][C]
+    int B, H, W, C;
+    int group_ch;           // 0: no normalisation
+    const double* stats;    // [B][C/group_ch][2]
+    const float* gamma;
+    const float* beta;
+    float eps;
+    int relu_inner;         // ReLU right after the normalisation
+    int add_kind;           // 0 none | 1 fp16 hi/lo residual (same geometry, P = 1) | 2 second raw tensor with its own GroupNorm
+    const __half* res;      // add_kind 1: PF matrix, lo plane res_lo_rows rows further
+    int64_t res_lo_rows;
+    const float* raw2;      // add_kind 2
+    const double* stats2;
+    const float* gamma2;
+    const float* beta2;
+    int relu_outer;         // ReLU after the add
+    __half* out;            // PF matrix at (H, W) for out_phases == 1, at (ceil(H/2), ceil(W/2)) x 4 phases otherwise
+    int out_phases;
+    int out_terms;          // 2: write hi and lo, 1: hi only
+};
+const char* gn_apply_launch(const GnApplyDesc& d, cudaStream_t stream);
+
+// ---------------------------------------------------------------- stem convolution (3x3, stride 1, Cin in {1, 3}, Cout = 32)
+struct StemDesc {
+    const float* image;     // NCHW fp32 [B][Cin][H][W]
+    int B, Cin, H, W;
+    const float* weight;    // OIHW fp32 [32][Cin][3][3]
+    const float* bias;      // [32]
+    int has_gn;             // per-channel GroupNorm(32, 32)
+    double* stats;          // [B][32][2]
+    const float* gamma;
+    const float* beta;
+    float eps;
+    __half* out;            // PF, 4 phases at (ceil(H/2), ceil(W/2)), C = 32
+    int out_terms;
+};
+const char* stem_stats_launch(const StemDesc& d, cudaStream_t stream);   // pass 1: statistics only
+const char* stem_apply_launch(const StemDesc& d, cudaStream_t stream);   // pass 2: recompute, normalise, ReLU, store
+
+// ---------------------------------------------------------------- 1x1 head (C -> Co <= 8) with the decoder's output maps
+struct HeadDesc {
+    const __half* act;      // PF P = 1 at (H, W), C channels, lo plane act_lo_rows further
+    int64_t act_lo_rows;
+    int in_terms;
+    int B, H, W, C, Co;
+    const float* weight;    // fp32 [Co][C]
+    const float* bias;      // [Co]
+    const float* mean;      // [num_task] added to the task channels
+    int num_task;           // channels >= num_task get exp(clamp(x, lo, hi))
+    float clamp_lo, clamp_hi;
+    float* out;             // NCHW fp32 [B][Co][H][W]
+};
+const char* head_launch(const HeadDesc& d, cudaStream_t stream);
+
+}  // namespace cl

@@ -1,0 +1,397 @@
+// Implicit-GEMM convolution for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> fused epilogue.
+//
+// Replaces the cuDNN kernels behind every nn.Conv2d of the coordinate network except the 3-channel stem
+// (/root/reference/networks/networks.py:191-213, 133-146, 297-306: conv3x3 s1/s2 and conv1x1).
+//
+// Formulation.  Activations live in HBM as fp16 "padded-flat" matrices [rows][C]: one row per pixel of a
+// zero-bordered (H+2) x (W+2) image, images back to back.  In that layout the input of filter tap
+// (kh, kw) is the same matrix shifted by a constant number of rows, so a convolution is a sum over taps
+// of plain GEMMs  D[m, n] += A[m + shift(tap), k] * W[tap][n, k]  and every operand tile is one 2-D TMA
+// box (out-of-range rows are zero-filled by the TMA unit).  Stride-2 layers read an input that was
+// written as four parity phases at the output resolution, which again makes every tap a pure row shift.
+// Rows that correspond to border pixels produce garbage that is never stored.
+//
+// Precision.  fp32 parity with the reference (1e-3 relative on the coordinate map) needs more than one
+// fp16/TF32 pass (measured 1.07e-3), so by default each product is evaluated as three fp16
+// MMAs  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  with fp32 accumulation in TMEM ("fp16x3", ~2^-22 relative).
+//
+// Warp roles (256 threads, one CTA per SM, persistent over output tiles):
+//   warp 0   TMA producer          warp 1   tcgen05.mma issuer       warp 2   TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld -> scale + bias -> fp32 store + GroupNorm partial sums (fp64 atomics)
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "conv.h"
+#include "ptx_sm100.cuh"
+
+namespace cl {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kTmemCols = 512;
+
+// Sums NV per-lane values across the warp with a recursive-halving butterfly (NV - 1 + log2(32 / NV)
+// shuffles per value set).  On return v[0] of lane l holds the total of value index
+// scatter_index<NV>(l); lanes sharing that index hold copies.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[NV], int lane)
+{
+    int cur = NV;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (cur > 1) {
+            const int half = cur >> 1;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; i++) {
+                if (i < half) {
+                    const float send = upper ? v[i] : v[i + half];
+                    const float keep = upper ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            cur = half;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ int scatter_index(int lane)
+{
+    int idx = 0, cur = NV;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (cur > 1) {
+            cur >>= 1;
+            if (lane & off) idx += cur;
+        }
+    }
+    return idx;
+}
+
+template <int NV>
+__device__ __forceinline__ bool scatter_owner(int lane)
+{
+    // lanes whose low bits (those reduced by plain butterfly steps) are zero publish the value
+    int cur = NV, mask = 0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (cur > 1) cur >>= 1;
+        else mask |= off;
+    }
+    return (lane & mask) == 0;
+}
+
+// GroupNorm partial sums of one 32-column chunk held by the warp (one row per lane).
+// GC = channels per group; the chunk covers 32 / GC whole groups.
+template <int GC>
+__device__ __forceinline__ void stats_chunk(const float (&f)[32], bool valid, int image, int lane, double* stats,
+                                            int groups, int first_group)
+{
+    constexpr int NG = 32 / GC, NV = 2 * NG;
+    float v[NV];
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < GC; j++) {
+            const float x = valid ? f[g * GC + j] : 0.f;
+            s += x;
+            ss += x * x;
+        }
+        v[2 * g] = s;
+        v[2 * g + 1] = ss;
+    }
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (vmask == 0) return;
+    const int ref_image = __shfl_sync(0xffffffffu, image, __ffs(vmask) - 1);
+    const bool uniform = __all_sync(0xffffffffu, !valid || image == ref_image);
+    if (uniform) {
+        warp_reduce_scatter<NV>(v, lane);
+        if (scatter_owner<NV>(lane)) {
+            const int idx = scatter_index<NV>(lane);
+            atomicAdd(stats + ((size_t)ref_image * groups + first_group + (idx >> 1)) * 2 + (idx & 1), (double)v[0]);
+        }
+    } else if (valid) {
+        // the warp's rows straddle two images (once per image boundary): every lane publishes its own sums
+#pragma unroll
+        for (int i = 0; i < NV; i++)
+            atomicAdd(stats + ((size_t)image * groups + first_group + (i >> 1)) * 2 + (i & 1), (double)v[i]);
+    }
+}
+
+template <int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const ConvIgemmParams p)
+{
+    constexpr int kSwizzle = BK * 2;   // bytes per operand row = swizzle span (128 B or 64 B)
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms need 1 KB alignment
+    const int nA = p.nterms == 3 ? 2 : 1;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int kblocks = p.num_taps * p.kblocks_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmW);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.num_stages; s++) {
+            ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 4);   // one arrival per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(ptx::smem_u32(&tmem_base_s), kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (uint32_t)nA * (p.a_bytes + p.w_bytes);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / p.tiles_n) * kBlockM;
+                const int n0 = (tile % p.tiles_n) * p.BN;
+                for (int tap = 0; tap < p.num_taps; tap++) {
+                    const int a_row = p.tap_a_row[tap] + m0;
+                    const int w_row = tap * p.w_tap_rows + n0;
+                    for (int kb = 0; kb < p.kblocks_per_tap; kb++) {
+                        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                        const uint32_t bar = ptx::smem_u32(&full_bar[stage]);
+                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
+                        ptx::mbar_expect_tx(bar, tx_bytes);
+                        ptx::tma_load_2d(sa, &tmA, bar, kb * BK, a_row);
+                        ptx::tma_load_2d(sw, &tmW, bar, kb * BK, w_row);
+                        if (nA == 2) {
+                            ptx::tma_load_2d(sa + p.a_bytes, &tmA, bar, kb * BK, p.a_lo_rows + a_row);
+                            ptx::tma_load_2d(sw + p.w_bytes, &tmW, bar, kb * BK, p.w_lo_rows + w_row);
+                        }
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = ptx::make_idesc_f16(kBlockM, p.BN);
+        int stage = 0, local = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+            const int as = local % p.accum_stages;
+            const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
+            ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aphase ^ 1u);   // epilogue has drained this accumulator
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.BN);
+            for (int kbi = 0; kbi < kblocks; kbi++) {
+                ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                    const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
+                    // term 0: a_hi * w_hi, term 1: a_lo * w_hi, term 2: a_hi * w_lo
+                    for (int term = 0; term < p.nterms; term++) {
+                        const uint32_t a_addr = sa + (term == 1 ? p.a_bytes : 0u);
+                        const uint32_t w_addr = sw + (term == 2 ? p.w_bytes : 0u);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++) {
+                            const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(a_addr + k * 32);
+                            const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(w_addr + k * 32);
+                            ptx::mma_f16_ss(tmem_d, da, db, idesc, (kbi | term | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));          // frees the smem stage
+                    if (kbi == kblocks - 1) ptx::mma_commit(ptx::smem_u32(&tfull_bar[as]));   // accumulator ready
+                }
+                __syncwarp();
+                if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3;   // TMEM lane quarter this warp may read
+        const int plane = p.Hp * p.Wp;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+            const int as = local % p.accum_stages;
+            const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
+            const int m0 = (tile / p.tiles_n) * kBlockM;
+            const int n0 = (tile % p.tiles_n) * p.BN;
+            const int m = m0 + q * 32 + lane;
+            int image = 0;
+            bool valid = false;
+            if (m < p.Mp) {
+                image = m / plane;
+                const int r = m - image * plane;
+                const int y = r / p.Wp, x = r - y * p.Wp;
+                valid = y >= 1 && y <= p.Hp - 2 && x >= 1 && x <= p.Wp - 2;
+            }
+            ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                uint32_t u[32];
+                ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
+                ptx::tmem_ld_wait();
+                float f[32];
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 bb = __ldg(b4 + j);
+                    f[4 * j + 0] = __uint_as_float(u[4 * j + 0]) * p.out_scale + bb.x;
+                    f[4 * j + 1] = __uint_as_float(u[4 * j + 1]) * p.out_scale + bb.y;
+                    f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) * p.out_scale + bb.z;
+                    f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) * p.out_scale + bb.w;
+                }
+                if (valid) {
+                    float4* o = reinterpret_cast<float4*>(p.raw + (size_t)m * p.Cout + n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                }
+                if (p.group_ch) {
+                    const int first_group = (n0 + c0) / p.group_ch;
+                    switch (p.group_ch) {
+                        case 2: stats_chunk<2>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 4: stats_chunk<4>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 8: stats_chunk<8>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 16: stats_chunk<16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        default: break;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// fp16 row-major [rows][cols] matrix, box = box_rows x box_cols elements, rows zero-filled out of range
+bool make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                     uint32_t box_cols)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
+{
+    if (d.Cin % 32 != 0) return "conv_igemm: Cin must be a multiple of 32";
+    if (d.Cout % 64 != 0) return "conv_igemm: Cout must be a multiple of 64";
+    if (d.num_taps < 1 || d.num_taps > 9) return "conv_igemm: 1..9 taps";
+    if (d.nterms != 1 && d.nterms != 3) return "conv_igemm: nterms must be 1 or 3";
+    if (d.group_ch != 0 && d.group_ch != 2 && d.group_ch != 4 && d.group_ch != 8 && d.group_ch != 16)
+        return "conv_igemm: GroupNorm group size must be 2, 4, 8 or 16 channels";
+    const int BK = d.Cin % 64 == 0 ? 64 : 32;
+    const int BN = d.Cout % 256 == 0 ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
+    const int nA = d.nterms == 3 ? 2 : 1;
+
+    ConvIgemmParams p{};
+    p.num_taps = d.num_taps;
+    for (int i = 0; i < d.num_taps; i++) p.tap_a_row[i] = d.tap_a_row[i];
+    p.kblocks_per_tap = d.Cin / BK;
+    p.nterms = d.nterms;
+    p.a_lo_rows = (int)d.a_lo_rows;
+    p.w_tap_rows = d.Cout;
+    p.w_lo_rows = d.num_taps * d.Cout;
+    p.Mp = d.Mp; p.Cout = d.Cout; p.BN = BN;
+    p.tiles_m = (d.Mp + kBlockM - 1) / kBlockM;
+    p.tiles_n = d.Cout / BN;
+    p.Hp = d.Hp; p.Wp = d.Wp;
+    p.group_ch = d.group_ch;
+    p.groups = d.group_ch ? d.Cout / d.group_ch : 0;
+    p.out_scale = d.out_scale;
+    p.raw = d.raw; p.bias = d.bias; p.stats = d.stats;
+    p.a_bytes = (uint32_t)(kBlockM * BK * 2);
+    p.w_bytes = (uint32_t)(BN * BK * 2);
+    p.stage_bytes = (uint32_t)nA * (p.a_bytes + p.w_bytes);
+    const int smem_budget = 227 * 1024 - 2048;
+    p.num_stages = smem_budget / (int)p.stage_bytes;
+    if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+    if (p.num_stages < 2) return "conv_igemm: tile does not fit two pipeline stages";
+    p.accum_stages = 2 * BN <= (int)kTmemCols ? 2 : 1;
+    const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024;
+
+    CUtensorMap tmA, tmW;
+    if (!make_tensor_map(&tmA, d.act, (uint64_t)d.a_total_rows, (uint64_t)d.Cin, kBlockM, BK))
+        return "conv_igemm: cuTensorMapEncodeTiled failed for the activation matrix";
+    if (!make_tensor_map(&tmW, d.weights, (uint64_t)(d.nterms == 3 ? 2 : 1) * d.num_taps * d.Cout, (uint64_t)d.Cin, BN, BK))
+        return "conv_igemm: cuTensorMapEncodeTiled failed for the weight matrix";
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int grid = num_tiles < sms ? num_tiles : sms;
+
+    cudaError_t e;
+    if (BK == 64) {
+        e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        conv_igemm_kernel<64><<<grid, kThreads, smem, stream>>>(tmA, tmW, p);
+    } else {
+        e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        conv_igemm_kernel<32><<<grid, kThreads, smem, stream>>>(tmA, tmW, p);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace cl

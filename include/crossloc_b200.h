@@ -61,6 +61,68 @@ int cl_dsac_forward_rgb(const float* coords, int B, int Hc, int Wc, float* out_p
                         const int32_t* forced_samples, int32_t* out_best, double* out_scores, double* out_hyps,
                         int32_t* out_tries, int32_t* out_counts, double* out_rt, void* cuda_stream);
 
+/*
+ * ---- Scene-coordinate CNN operators ---------------------------------------------------------------
+ * These replace the cuDNN / ATen kernels stock PyTorch launches for the reference network
+ * (/root/reference/networks/networks.py:175-256 encoder, :276-360 decoder, :43-130 vanilla Network).
+ * All tensor arguments of this group must be DEVICE pointers (activations never leave HBM); small
+ * parameter tables (`tap_a_row`) are host pointers.
+ *
+ * Activation layout ("padded-flat", PF): fp16 matrix [rows][C],
+ *   row(t, ph, b, y, x) = ((t * P + ph) * B + b) * (H + 2) * (W + 2) + (y + 1) * (W + 2) + (x + 1)
+ * t = fp16 split term (0 hi, 1 lo), ph = parity phase (P = 1; P = 4 for the input of a stride-2
+ * convolution, stored at the OUTPUT resolution), borders zero.  In this layout every filter tap is a
+ * constant row shift, so a convolution is a sum of shifted GEMMs fed by plain 2-D TMA boxes.
+ */
+
+/*
+ * Implicit-GEMM convolution on the tcgen05 tensor cores (+ bias, + GroupNorm partial sums).
+ * Replaces nn.Conv2d 3x3 s1 / 3x3 s2 / 1x1 (networks.py:191-213, 133-146, 297-306).
+ *   act           fp16 PF activation matrix (all planes), a_total_rows rows of Cin channels
+ *   a_lo_rows     row distance between the hi and the lo plane (ignored when nterms == 1)
+ *   weights       fp16 [nterms == 3 ? 2 : 1][num_taps][Cout][Cin], pre-scaled by 1 / out_scale
+ *   tap_a_row     HOST int32 [num_taps]: activation row shift of each tap (phase offset included)
+ *   nterms        1 = one fp16 pass; 3 = fp16x3 split (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo), fp32-grade
+ *   Mp, Hp, Wp    output rows B * Hp * Wp and padded plane size (Hp = H + 2, Wp = W + 2)
+ *   group_ch      channels per GroupNorm group for the statistics (0 = none; 2, 4, 8 or 16)
+ *   raw           fp32 [Mp][Cout] output (interior rows written), bias fp32 [Cout]
+ *   stats         fp64 [B][Cout / group_ch][2] (sum, sum of squares), accumulated: caller zeroes it
+ */
+int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int Cin, const void* weights, int Cout,
+                  int num_taps, const int32_t* tap_a_row, int nterms, int Mp, int Hp, int Wp, int group_ch,
+                  float out_scale, float* raw, const float* bias, double* stats, void* cuda_stream);
+
+/*
+ * GroupNorm apply + ReLU + residual merge, fp32 raw -> fp16 hi/lo PF input of the next convolution.
+ * Replaces nn.GroupNorm + F.relu (+ `res + x`) (networks.py:231-254, 332-343).
+ *   out = relu_outer( add + relu_inner( gn(raw) ) ),  add = 0 | res_hi + res_lo | gn2(raw2)
+ *   out_phases 1: same geometry;  4: the four parity phases at (ceil(H/2), ceil(W/2)).
+ */
+int cl_gn_apply(const float* raw, int B, int H, int W, int C, int group_ch, const double* stats, const float* gamma,
+                const float* beta, float eps, int relu_inner, int add_kind, const void* res, int64_t res_lo_rows,
+                const float* raw2, const double* stats2, const float* gamma2, const float* beta2, int relu_outer,
+                void* out, int out_phases, int out_terms, void* cuda_stream);
+
+/*
+ * Stem: conv3x3 s1 (Cin = 1 or 3 -> 32) + per-channel GroupNorm(32, 32) + ReLU, written as the
+ * four-phase fp16 PF input of conv2.  Two passes over the image (statistics, then recompute + store):
+ * the 32-channel full-resolution fp32 tensor the reference materialises is never written.
+ * Replaces encoder.conv1 / norm1 (networks.py:186-190, 231) and Network.conv1 (:59, 96; has_gn = 0).
+ *   image NCHW fp32 [B][Cin][H][W]; weight OIHW fp32 [32][Cin][3][3]; stats fp64 [B][32][2] zeroed by caller.
+ */
+int cl_stem_forward(const float* image, int B, int Cin, int H, int W, const float* weight, const float* bias,
+                    int has_gn, double* stats, const float* gamma, const float* beta, float eps, void* out,
+                    int out_terms, void* cuda_stream);
+
+/*
+ * Output head: 1x1 convolution C -> Co (Co <= 8) + mean offset on the task channels +
+ * exp(clamp(x, clamp_lo, clamp_hi)) on the remaining (uncertainty) channels; NCHW fp32 output.
+ * Replaces decoder.fc3 and the output maps (networks.py:349-358; Network.fc3 :124-128).
+ */
+int cl_head_forward(const void* act, int64_t act_lo_rows, int in_terms, int B, int H, int W, int C, int Co,
+                    const float* weight, const float* bias, const float* mean, int num_task, float clamp_lo,
+                    float clamp_hi, float* out, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,407 @@
+"""Drop-in twin of the reference's `networks.networks` for the localization hot path.
+
+Same classes, constructor signatures, attributes and state-dict keys as
+/root/reference/networks/networks.py (`Network` :43-130, `TransPoseNetEncoder` :175-256,
+`TransPoseNetDecoder` :276-360, `TransPoseNet` :363-502), so `load_state_dict(strict=True)` of reference
+checkpoints and the unchanged callers (utils/evaluation.py:106-116, test_single_task.py:347-366) keep working.
+What differs is what `forward` launches: on a CUDA tensor without autograd it runs the hand-written sm_100a
+kernels of crossloc_b200 (TMA + tcgen05 implicit-GEMM convolutions, fused GroupNorm statistics) instead of
+cuDNN/ATen.  `forward_reference` is the same network spelled with stock torch ops in fp32: it is the
+definition the parity tests compare against and the autograd path of `train_single_task.py` until the
+backward kernels exist.  There is no CPU execution of the native path.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from crossloc_b200.cnn import CoordNetEngine
+
+try:   # the reference logs through utils.io.safe_printout (networks.py:40); optional here
+    from utils.io import safe_printout
+except Exception:   # pragma: no cover - reference utils not on the path
+    def safe_printout(words):
+        pass
+
+_POS_CLAMP = (-16.10, 13.82)   # exp() range limiter of the uncertainty channel, networks.py:355-356
+
+
+def _width(tiny, full=512):
+    return 128 if tiny else full
+
+
+def _res_block(tiny, num_gn_channel, in_ch=None):
+    """conv3x3-GN-ReLU, conv1x1-GN-ReLU, conv3x3-GN-ReLU (networks.py:133-146; :149-163 for in_ch != width)."""
+    ch = _width(tiny)
+    in_ch = ch if in_ch is None else in_ch
+    groups = min(num_gn_channel, ch)
+    return nn.Sequential(
+        nn.Conv2d(in_ch, ch, 3, 1, 1), nn.GroupNorm(groups, ch), nn.ReLU(),
+        nn.Conv2d(ch, ch, 1, 1, 0), nn.GroupNorm(groups, ch), nn.ReLU(),
+        nn.Conv2d(ch, ch, 3, 1, 1), nn.GroupNorm(groups, ch), nn.ReLU())
+
+
+def _native_ok(module, x):
+    if not x.is_cuda:
+        raise RuntimeError('crossloc_b200: forward() needs a CUDA tensor -- the native path has no CPU fallback '
+                           '(use forward_reference() for the plain-torch definition)')
+    return not (torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()))
+
+
+class Network(nn.Module):
+    """Vanilla DSAC* FCN (networks.py:43-130): grayscale in, 3-channel scene coordinates out, no normalisation."""
+
+    OUTPUT_SUBSAMPLE = 8
+
+    def __init__(self, mean, tiny):
+        super(Network, self).__init__()
+        c4, c5 = _width(tiny, 256), _width(tiny, 512)
+        self.conv1 = nn.Conv2d(1, 32, 3, 1, 1)
+        self.conv2 = nn.Conv2d(32, 64, 3, 2, 1)
+        self.conv3 = nn.Conv2d(64, 128, 3, 2, 1)
+        self.conv4 = nn.Conv2d(128, c4, 3, 2, 1)
+        self.res1_conv1 = nn.Conv2d(c4, c4, 3, 1, 1)
+        self.res1_conv2 = nn.Conv2d(c4, c4, 1, 1, 0)
+        self.res1_conv3 = nn.Conv2d(c4, c4, 3, 1, 1)
+        self.res2_conv1 = nn.Conv2d(c4, c5, 3, 1, 1)
+        self.res2_conv2 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.res2_conv3 = nn.Conv2d(c5, c5, 3, 1, 1)
+        if not tiny:
+            self.res2_skip = nn.Conv2d(256, 512, 1, 1, 0)
+        self.res3_conv1 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.res3_conv2 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.res3_conv3 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.fc1 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.fc2 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.fc3 = nn.Conv2d(c5, 3, 1, 1, 0)
+        self.register_buffer('mean', mean.clone())
+        self.tiny = tiny
+        self._engine = None
+
+    def _spec(self):
+        names = ['conv1', 'conv2', 'conv3', 'conv4', 'res1_conv1', 'res1_conv2', 'res1_conv3', 'res2_conv1',
+                 'res2_conv2', 'res2_conv3', 'res3_conv1', 'res3_conv2', 'res3_conv3', 'fc1', 'fc2']
+        if not self.tiny:
+            names.append('res2_skip')
+        res2 = {'kind': 'residual', 'convs': ['res2_conv1', 'res2_conv2', 'res2_conv3']}
+        if not self.tiny:
+            res2 = {'kind': 'residual_skip', 'convs': res2['convs'], 'skip': 'res2_skip'}
+        return {
+            'group_norm': False,
+            'layers': [(n, getattr(self, n), None) for n in names],
+            'blocks': [{'kind': 'residual', 'convs': ['res1_conv1', 'res1_conv2', 'res1_conv3']}, res2,
+                       {'kind': 'residual', 'convs': ['res3_conv1', 'res3_conv2', 'res3_conv3']},
+                       {'kind': 'plain', 'convs': ['fc1', 'fc2']}],
+            'head': {'conv': self.fc3, 'mean': self.mean, 'num_task': 3, 'clamp': _POS_CLAMP},
+        }
+
+    def forward_reference(self, inputs):
+        x = F.relu(self.conv1(inputs))
+        x = F.relu(self.conv2(x))
+        x = F.relu(self.conv3(x))
+        res = F.relu(self.conv4(x))
+        x = F.relu(self.res1_conv1(res))
+        x = F.relu(self.res1_conv2(x))
+        x = F.relu(self.res1_conv3(x))
+        res = res + x
+        x = F.relu(self.res2_conv1(res))
+        x = F.relu(self.res2_conv2(x))
+        x = F.relu(self.res2_conv3(x))
+        if not self.tiny:
+            res = self.res2_skip(res)
+        res = res + x
+        x = F.relu(self.res3_conv1(res))
+        x = F.relu(self.res3_conv2(x))
+        x = F.relu(self.res3_conv3(x))
+        res = res + x
+        sc = F.relu(self.fc1(res))
+        sc = F.relu(self.fc2(sc))
+        sc = self.fc3(sc)
+        return sc + self.mean.to(sc.device)[None, :, None, None]
+
+    def forward(self, inputs):
+        if not _native_ok(self, inputs):
+            return self.forward_reference(inputs)
+        if self._engine is None:
+            self._engine = CoordNetEngine()
+        return self._engine.forward(self._spec(), inputs)
+
+
+class TransPoseNetEncoder(nn.Module):
+    """Encoder (networks.py:175-256): strided conv ladder + two residual stages + optional extra blocks."""
+
+    def __init__(self, tiny, grayscale, enc_add_res_block=0, num_gn_channel=32):
+        super(TransPoseNetEncoder, self).__init__()
+        self.tiny = tiny
+        self.grayscale = grayscale
+        self.enc_add_res_block = enc_add_res_block
+        self.num_gn_channel = num_gn_channel
+        c4, c5, g = _width(tiny, 256), _width(tiny, 512), num_gn_channel
+        self.conv1 = nn.Conv2d(1 if grayscale else 3, g, 3, 1, 1)
+        self.norm1 = nn.GroupNorm(g, g)
+        self.conv2 = nn.Conv2d(g, 64, 3, 2, 1)
+        self.norm2 = nn.GroupNorm(g, 64)
+        self.conv3 = nn.Conv2d(64, 128, 3, 2, 1)
+        self.norm3 = nn.GroupNorm(g, 128)
+        self.conv4 = nn.Conv2d(128, c4, 3, 2, 1)
+        self.norm4 = nn.GroupNorm(g, c4)
+        self.res1_conv1 = nn.Conv2d(c4, c4, 3, 1, 1)
+        self.res1_norm1 = nn.GroupNorm(g, c4)
+        self.res1_conv2 = nn.Conv2d(c4, c4, 1, 1, 0)
+        self.res1_norm2 = nn.GroupNorm(g, c4)
+        self.res1_conv3 = nn.Conv2d(c4, c4, 3, 1, 1)
+        self.res1_norm3 = nn.GroupNorm(g, c4)
+        self.res2_conv1 = nn.Conv2d(c4, c5, 3, 1, 1)
+        self.res2_norm1 = nn.GroupNorm(g, c5)
+        self.res2_conv2 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.res2_norm2 = nn.GroupNorm(g, c5)
+        self.res2_conv3 = nn.Conv2d(c5, c5, 3, 1, 1)
+        self.res2_norm3 = nn.GroupNorm(g, c5)
+        if not tiny:
+            self.res2_skip = nn.Conv2d(256, 512, 1, 1, 0)
+            self.res2_skip_norm = nn.GroupNorm(g, 512)
+        self.enc_add_res_block_ls = [_res_block(tiny, g) for _ in range(enc_add_res_block)]
+        for i, block in enumerate(self.enc_add_res_block_ls):
+            self.add_module('enc_add_res_block{:d}'.format(i + 1), block)
+
+    def plan(self, prefix):
+        """(layers, blocks) of this encoder for the native engine; names are state-dict prefixes."""
+        pairs = [('conv1', 'norm1'), ('conv2', 'norm2'), ('conv3', 'norm3'), ('conv4', 'norm4'),
+                 ('res1_conv1', 'res1_norm1'), ('res1_conv2', 'res1_norm2'), ('res1_conv3', 'res1_norm3'),
+                 ('res2_conv1', 'res2_norm1'), ('res2_conv2', 'res2_norm2'), ('res2_conv3', 'res2_norm3')]
+        layers = [(c if c.startswith('conv') else prefix + c, getattr(self, c), getattr(self, n)) for c, n in pairs]
+        res2 = {'kind': 'residual', 'convs': [prefix + 'res2_conv%d' % i for i in (1, 2, 3)]}
+        if not self.tiny:
+            layers.append((prefix + 'res2_skip', self.res2_skip, self.res2_skip_norm))
+            res2 = {'kind': 'residual_skip', 'convs': res2['convs'], 'skip': prefix + 'res2_skip'}
+        blocks = [{'kind': 'residual', 'convs': [prefix + 'res1_conv%d' % i for i in (1, 2, 3)]}, res2]
+        for i, block in enumerate(self.enc_add_res_block_ls):
+            names = [prefix + 'enc_add_res_block%d.%d' % (i + 1, j) for j in (0, 3, 6)]
+            layers += [(names[k], block[3 * k], block[3 * k + 1]) for k in range(3)]
+            blocks.append({'kind': 'residual', 'convs': names})
+        return layers, blocks
+
+    def forward_reference(self, inputs):
+        x = F.relu(self.norm1(self.conv1(inputs)))
+        x = F.relu(self.norm2(self.conv2(x)))
+        x = F.relu(self.norm3(self.conv3(x)))
+        res = F.relu(self.norm4(self.conv4(x)))
+        x = F.relu(self.res1_norm1(self.res1_conv1(res)))
+        x = F.relu(self.res1_norm2(self.res1_conv2(x)))
+        x = F.relu(self.res1_norm3(self.res1_conv3(x)))
+        res = F.relu(res + x)
+        x = F.relu(self.res2_norm1(self.res2_conv1(res)))
+        x = F.relu(self.res2_norm2(self.res2_conv2(x)))
+        x = F.relu(self.res2_norm3(self.res2_conv3(x)))
+        if not self.tiny:
+            res = self.res2_skip_norm(self.res2_skip(res))
+        res = F.relu(res + x)
+        for block in self.enc_add_res_block_ls:
+            res = F.relu(res + block(res))
+        return res
+
+    def forward(self, inputs):
+        # the encoder alone (used by the reference's MLR variants) has no native plan yet: plain torch
+        return self.forward_reference(inputs)
+
+
+class DenseUpsamplingConvolution(nn.Module):
+    """DUC up-sampling head of the full-size variant (networks.py:259-273); semantics task only."""
+
+    def __init__(self, down_sampling_rate, in_channel, num_classes, num_gn_channel=32):
+        super(DenseUpsamplingConvolution, self).__init__()
+        up = (down_sampling_rate ** 2) * num_classes
+        self.conv = nn.Conv2d(in_channel, up, 3, 1, 1)
+        self.norm = nn.GroupNorm(num_gn_channel, up)
+        self.relu = nn.ReLU(inplace=True)
+        self.pixel_shuffle = nn.PixelShuffle(down_sampling_rate)
+
+    def forward(self, x):
+        return self.pixel_shuffle(self.relu(self.norm(self.conv(x))))
+
+
+class TransPoseNetDecoder(nn.Module):
+    """Decoder (networks.py:276-360): optional extra blocks, a 1x1 residual stage, fc1/fc2 and the output head."""
+
+    def __init__(self, mean, tiny, dec_add_res_block=0, num_task_channel=3, num_pos_channel=1, num_gn_channel=32,
+                 full_size_output=False):
+        super(TransPoseNetDecoder, self).__init__()
+        self.register_buffer('mean', mean.clone())
+        self.tiny = tiny
+        self.dec_add_res_block = dec_add_res_block
+        self.num_task_channel = num_task_channel
+        self.num_pos_channel = num_pos_channel
+        self.num_gn_channel = num_gn_channel
+        self.full_size_output = full_size_output
+        c5, g = _width(tiny), num_gn_channel
+        self.dec_add_res_block_ls = [_res_block(tiny, g) for _ in range(dec_add_res_block)]
+        for i, block in enumerate(self.dec_add_res_block_ls):
+            self.add_module('dec_add_res_block{:d}'.format(i + 1), block)
+        self.res3_conv1 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.res3_norm1 = nn.GroupNorm(g, c5)
+        self.res3_conv2 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.res3_norm2 = nn.GroupNorm(g, c5)
+        self.res3_conv3 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.res3_norm3 = nn.GroupNorm(g, c5)
+        self.fc1 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.fc1_norm = nn.GroupNorm(min(c5, g), c5)
+        self.fc2 = nn.Conv2d(c5, c5, 1, 1, 0)
+        self.fc2_norm = nn.GroupNorm(min(c5, g), c5)
+        assert num_task_channel > 0 and num_pos_channel >= 0
+        assert num_task_channel == len(mean)
+        co = num_task_channel + num_pos_channel
+        if full_size_output:
+            self.duc_upsample = DenseUpsamplingConvolution(down_sampling_rate=8, in_channel=c5, num_classes=co)
+            self.fc3 = nn.Conv2d(co, co, 1, 1, 0)
+        else:
+            self.fc3 = nn.Conv2d(c5, co, 1, 1, 0)
+
+    def plan(self, prefix):
+        layers, blocks = [], []
+        for i, block in enumerate(self.dec_add_res_block_ls):
+            names = [prefix + 'dec_add_res_block%d.%d' % (i + 1, j) for j in (0, 3, 6)]
+            layers += [(names[k], block[3 * k], block[3 * k + 1]) for k in range(3)]
+            blocks.append({'kind': 'residual', 'convs': names})
+        names = [prefix + 'res3_conv%d' % i for i in (1, 2, 3)]
+        layers += [(names[i], getattr(self, 'res3_conv%d' % (i + 1)), getattr(self, 'res3_norm%d' % (i + 1)))
+                   for i in range(3)]
+        blocks.append({'kind': 'residual', 'convs': names})
+        layers += [(prefix + 'fc1', self.fc1, self.fc1_norm), (prefix + 'fc2', self.fc2, self.fc2_norm)]
+        blocks.append({'kind': 'plain', 'convs': [prefix + 'fc1', prefix + 'fc2']})
+        head = {'conv': self.fc3, 'mean': self.mean, 'num_task': self.num_task_channel, 'clamp': _POS_CLAMP}
+        return layers, blocks, head
+
+    def forward_reference(self, inputs, up_height=None, up_width=None):
+        res = inputs
+        for block in self.dec_add_res_block_ls:
+            res = F.relu(res + block(res))
+        x = F.relu(self.res3_norm1(self.res3_conv1(res)))
+        x = F.relu(self.res3_norm2(self.res3_conv2(x)))
+        x = F.relu(self.res3_norm3(self.res3_conv3(x)))
+        res = F.relu(res + x)
+        sc = F.relu(self.fc1_norm(self.fc1(res)))
+        sc = F.relu(self.fc2_norm(self.fc2(sc)))
+        if self.full_size_output:
+            sc = self.duc_upsample(sc)
+            sc = F.interpolate(sc, (up_height, up_width), mode='bilinear', align_corners=False)
+        sc = self.fc3(sc)
+        k = self.num_task_channel
+        task = sc[:, :k] + self.mean.to(sc.device)[None, :, None, None]
+        if not self.num_pos_channel:
+            return task
+        pos = torch.exp(F.hardtanh(sc[:, k:], min_val=_POS_CLAMP[0], max_val=_POS_CLAMP[1]))
+        return torch.cat([task, pos], dim=1)
+
+    def forward(self, inputs, up_height=None, up_width=None):
+        return self.forward_reference(inputs, up_height, up_width)
+
+
+class TransPoseNet(nn.Module):
+    """Encoder-decoder regression network with GroupNorm (networks.py:363-502)."""
+
+    def __init__(self, mean, tiny, grayscale, enc_add_res_block=0, dec_add_res_block=0, num_task_channel=3,
+                 num_pos_channel=1, num_gn_channel=32, num_mlr=0, num_unfrozen_encoder=0, full_size_output=False):
+        super(TransPoseNet, self).__init__()
+        self.register_buffer('mean', mean.clone())
+        self.tiny = tiny
+        self.grayscale = grayscale
+        self.enc_add_res_block = enc_add_res_block
+        self.dec_add_res_block = dec_add_res_block
+        self.num_task_channel = num_task_channel
+        self.num_pos_channel = num_pos_channel
+        self.num_gn_channel = num_gn_channel
+        self.num_mlr = num_mlr
+        self.full_size_output = full_size_output
+        self.OUTPUT_SUBSAMPLE = 1 if full_size_output else 8
+
+        if num_mlr == 0:
+            self.encoder = TransPoseNetEncoder(tiny, grayscale, enc_add_res_block, num_gn_channel)
+        else:
+            self.encoder = nn.Identity()
+        self.encoder_ls = [self.encoder]
+
+        if num_mlr > 0 and isinstance(num_mlr, int):
+            assert 0 <= num_unfrozen_encoder <= num_mlr
+            self.mlr_encoder_ls = [TransPoseNetEncoder(tiny, grayscale, enc_add_res_block, num_gn_channel)
+                                   for _ in range(num_mlr)]
+            for i, block in enumerate(self.mlr_encoder_ls):
+                if i >= num_unfrozen_encoder:
+                    for param in block.parameters():
+                        param.requires_grad = False
+                self.add_module('mlr_encoder_{:d}'.format(i + 1), block)
+            width = _width(tiny)
+            self.mlr_norm = nn.GroupNorm(num_gn_channel, width * num_mlr)
+            self.mlr_forward = _res_block(tiny, num_gn_channel, in_ch=width * num_mlr)
+            self.mlr_skip = nn.Sequential(nn.Conv2d(width * num_mlr, width, 1, 1, 0),
+                                          nn.GroupNorm(num_gn_channel, width))
+        else:
+            self.mlr_encoder_ls = [nn.Identity()]
+            self.mlr_norm = nn.Identity()
+            self.mlr_forward = nn.Identity()
+            self.mlr_skip = nn.Identity()
+        self.mlr_ls = self.mlr_encoder_ls + [self.mlr_norm, self.mlr_forward, self.mlr_skip]
+
+        self.decoder = TransPoseNetDecoder(mean, tiny, dec_add_res_block, num_task_channel, num_pos_channel,
+                                           num_gn_channel, full_size_output)
+        self.decoder_ls = [self.decoder]
+        self._engine = None
+
+        count = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        safe_printout('Initialized TransPoseNet (crossloc_b200): tiny {}, grayscale {}, fullsize {}, #MLR {:d}, '
+                      'extra blocks enc {:d} / dec {:d}, trainable parameters {:,d}.'.format(
+                          tiny, grayscale, full_size_output, num_mlr, enc_add_res_block, dec_add_res_block, count))
+
+    def _spec(self):
+        enc_layers, enc_blocks = self.encoder.plan('encoder.')
+        dec_layers, dec_blocks, head = self.decoder.plan('decoder.')
+        return {'group_norm': True, 'layers': enc_layers + dec_layers, 'blocks': enc_blocks + dec_blocks, 'head': head}
+
+    def forward_reference(self, inputs):
+        up_height, up_width = inputs.size()[2:4]
+        if self.num_mlr == 0:
+            res = self.encoder.forward_reference(inputs)
+        else:
+            mlr = torch.cat([enc.forward_reference(inputs) for enc in self.mlr_encoder_ls], dim=1)
+            res = self.mlr_skip(mlr)
+            mlr = self.mlr_forward(self.mlr_norm(mlr))
+            res = F.relu(res + mlr)
+        if self.full_size_output:
+            return self.decoder.forward_reference(res, up_height, up_width)
+        return self.decoder.forward_reference(res)
+
+    def forward(self, inputs):
+        if not _native_ok(self, inputs):
+            return self.forward_reference(inputs)
+        if self.num_mlr != 0 or self.full_size_output:
+            raise NotImplementedError('crossloc_b200: the native path covers the single-encoder, sub-sampled '
+                                      'coordinate network; MLR / full-size variants are SURVEY.md section 8f rows 1-2 '
+                                      '(forward_reference() runs them with stock torch ops)')
+        if self._engine is None:
+            self._engine = CoordNetEngine()
+        return self._engine.forward(self._spec(), inputs)
+
+
+class ProjHead(nn.Module):
+    """Projection head (networks.py:505-541); unused by every reference script, kept for import compatibility."""
+
+    def __init__(self, in_channel, out_length=2048, tiny=False, num_gn_channel=32):
+        super(ProjHead, self).__init__()
+        ch = _width(tiny)
+        self.conv1 = nn.Conv2d(in_channel, ch, 3, 2, 1)
+        self.norm1 = nn.GroupNorm(num_gn_channel, ch)
+        self.conv2 = nn.Conv2d(ch, ch, 3, 2, 1)
+        self.norm2 = nn.GroupNorm(num_gn_channel, ch)
+        self.conv3 = nn.Conv2d(ch, ch, 3, 2, 1)
+        self.norm3 = nn.GroupNorm(num_gn_channel, ch)
+        self.conv4 = nn.Conv2d(ch, out_length, 1, 1, 0)
+        self.norm4 = nn.GroupNorm(num_gn_channel, out_length)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.in_channel = in_channel
+        self.out_length = out_length
+        self.num_gn_channel = num_gn_channel
+
+    def forward(self, inputs):
+        x = F.relu(self.norm1(self.conv1(inputs)))
+        x = F.relu(self.norm2(self.conv2(x)))
+        x = F.relu(self.norm3(self.conv3(x)))
+        x = F.relu(self.norm4(self.conv4(x)))
+        return torch.flatten(self.avgpool(x), 1)

@@ -1,0 +1,225 @@
+"""GPU parity of the CNN operators and of the whole coordinate network against plain fp32 torch."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from crossloc_b200 import _lib, layout
+from crossloc_b200.cnn import CoordNetEngine, PackedConv, _Geometry, _taps
+from tests.test_cnn_cpu import CASES, GOLD, build_case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def run_conv(x, conv, nterms, groups):
+    """x NCHW fp32 -> (raw NCHW, stats [B, groups, 2]) through cl_conv_igemm."""
+    lib = _lib.load()
+    b, cin, h, w = x.shape
+    stride = conv.stride[0]
+    pack = PackedConv(conv.weight, conv.bias, stride, nterms)
+    terms = 2 if nterms == 3 else 1
+    ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
+    geo = _Geometry(b, ho, wo)
+    phases = 4 if stride == 2 else 1
+    act = layout.to_pf(x, phases=phases, terms=terms)
+    raw = torch.zeros(geo.Mp, pack.cout, dtype=torch.float32, device=DEV)
+    group_ch = pack.cout // groups if groups else 0
+    stats = torch.zeros(b, max(groups, 1), 2, dtype=torch.float64, device=DEV)
+    taps = _taps(pack, geo)
+    arr = (ctypes.c_int32 * len(taps))(*taps)
+    _lib.check(lib.cl_conv_igemm(act.data_ptr(), act.size(0), phases * geo.Mp, cin, pack.weights.data_ptr(), pack.cout,
+                                 len(taps), arr, nterms, geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale,
+                                 raw.data_ptr(), pack.bias.data_ptr(), stats.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return layout.raw_to_nchw(raw, b, ho, wo), stats
+
+
+CONV_SHAPES = [
+    # cin, cout, k, stride, B, H, W
+    (512, 512, 1, 1, 2, 9, 14),
+    (256, 256, 3, 1, 2, 9, 14),
+    (512, 512, 3, 1, 1, 60, 90),
+    (256, 512, 3, 1, 3, 7, 5),
+    (32, 64, 3, 2, 2, 20, 28),
+    (64, 128, 3, 2, 2, 21, 27),     # odd input size: ragged parity phases
+    (128, 256, 3, 2, 1, 120, 180),
+    (128, 128, 3, 1, 2, 6, 8),      # tiny-network widths
+]
+
+
+@pytest.mark.parametrize('shape', CONV_SHAPES)
+@pytest.mark.parametrize('nterms', [3, 1])
+def test_conv_igemm_matches_torch(shape, nterms):
+    cin, cout, k, stride, b, h, w = shape
+    torch.manual_seed(cin + cout + k + stride)
+    conv = torch.nn.Conv2d(cin, cout, k, stride, k // 2).to(DEV)
+    x = torch.randn(b, cin, h, w, device=DEV).relu()
+    with torch.no_grad():
+        ref = conv(x)
+    out, stats = run_conv(x, conv, nterms, 32)
+    tol = 2e-5 if nterms == 3 else 2e-3
+    assert rel_l2(out, ref) < tol
+    # GroupNorm partial sums accumulated in the epilogue
+    g = ref.double().reshape(b, 32, -1)
+    assert torch.allclose(stats[:, :, 0], g.sum(-1), rtol=1e-3, atol=1e-2 * float(g.abs().sum(-1).max()) * (1e-3 if nterms == 3 else 1))
+    assert torch.allclose(stats[:, :, 1], (g * g).sum(-1), rtol=5e-3 if nterms == 1 else 1e-4)
+
+
+def test_gn_apply_variants():
+    lib = _lib.load()
+    b, c, h, w = 2, 256, 9, 13
+    torch.manual_seed(0)
+    gn = torch.nn.GroupNorm(32, c).to(DEV)
+    gn2 = torch.nn.GroupNorm(32, c).to(DEV)
+    with torch.no_grad():
+        for m in (gn, gn2):
+            m.weight.uniform_(0.5, 1.5)
+            m.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(b, c, h, w, device=DEV) * 3 + 1
+    x2 = torch.randn(b, c, h, w, device=DEV)
+    res = torch.randn(b, c, h, w, device=DEV).relu()
+    geo = _Geometry(b, h, w)
+
+    def raw_of(t):
+        r = torch.zeros(b, h + 2, w + 2, c, device=DEV)
+        r[:, 1:-1, 1:-1] = t.permute(0, 2, 3, 1)
+        r[:, 0] = 7.0    # border garbage must be ignored
+        return r.reshape(-1, c).contiguous()
+
+    def stats_of(t):
+        g = t.double().reshape(b, 32, -1)
+        return torch.stack([g.sum(-1), (g * g).sum(-1)], -1).contiguous()
+
+    def run(phases, add_kind, relu_outer):
+        ho, wo = ((h + 1) // 2, (w + 1) // 2) if phases == 4 else (h, w)
+        out = torch.zeros(2 * phases * b * (ho + 2) * (wo + 2), c, dtype=torch.float16, device=DEV)
+        res_pf = layout.to_pf(res)
+        r1, r2, s1, s2 = raw_of(x), raw_of(x2), stats_of(x), stats_of(x2)
+        _lib.check(lib.cl_gn_apply(r1.data_ptr(), b, h, w, c, c // 32, s1.data_ptr(), gn.weight.data_ptr(),
+                                   gn.bias.data_ptr(), 1e-5, 1, add_kind, res_pf.data_ptr(), geo.Mp, r2.data_ptr(),
+                                   s2.data_ptr(), gn2.weight.data_ptr(), gn2.bias.data_ptr(), relu_outer,
+                                   out.data_ptr(), phases, 2, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return layout.from_pf(out, b, h, w) if phases == 1 else layout.from_pf_phases(out, b, h, w)
+
+    with torch.no_grad():
+        base = F.relu(gn(x))
+        assert rel_l2(run(1, 0, 0), base) < 1e-5
+        assert rel_l2(run(4, 0, 0), base) < 1e-5
+        assert rel_l2(run(1, 1, 1), F.relu(res + base)) < 1e-5
+        assert rel_l2(run(1, 1, 0), res + base) < 1e-5
+        assert rel_l2(run(1, 2, 1), F.relu(gn2(x2) + base)) < 1e-5
+
+
+@pytest.mark.parametrize('cin,has_gn', [(3, 1), (1, 0), (1, 1)])
+def test_stem_matches_torch(cin, has_gn):
+    lib = _lib.load()
+    b, h, w = 2, 37, 70
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(cin, 32, 3, 1, 1).to(DEV)
+    gn = torch.nn.GroupNorm(32, 32).to(DEV)
+    with torch.no_grad():
+        gn.weight.uniform_(0.5, 1.5)
+        gn.bias.uniform_(-0.5, 0.5)
+    x = torch.rand(b, cin, h, w, device=DEV)
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    out = torch.zeros(2 * 4 * b * (ho + 2) * (wo + 2), 32, dtype=torch.float16, device=DEV)
+    stats = torch.zeros(b, 32, 2, dtype=torch.float64, device=DEV)
+    _lib.check(lib.cl_stem_forward(x.data_ptr(), b, cin, h, w, conv.weight.data_ptr(), conv.bias.data_ptr(), has_gn,
+                                   stats.data_ptr(), gn.weight.data_ptr(), gn.bias.data_ptr(), 1e-5, out.data_ptr(), 2,
+                                   torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = conv(x)
+        ref = F.relu(gn(ref)) if has_gn else F.relu(ref)
+    assert rel_l2(layout.from_pf_phases(out, b, h, w), ref) < 1e-5
+
+
+def test_head_matches_torch():
+    lib = _lib.load()
+    b, c, h, w, co = 2, 512, 9, 13, 4
+    torch.manual_seed(2)
+    conv = torch.nn.Conv2d(c, co, 1).to(DEV)
+    with torch.no_grad():
+        conv.bias[3] = 20.0   # exercises the upper clamp of the uncertainty channel
+    x = torch.randn(b, c, h, w, device=DEV).relu()
+    mean = torch.tensor([10., -20., 30.], device=DEV)
+    act = layout.to_pf(x)
+    out = torch.empty(b, co, h, w, device=DEV)
+    _lib.check(lib.cl_head_forward(act.data_ptr(), b * (h + 2) * (w + 2), 2, b, h, w, c, co,
+                                   conv.weight.reshape(co, c).contiguous().data_ptr(), conv.bias.data_ptr(),
+                                   mean.data_ptr(), 3, -16.10, 13.82, out.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        sc = conv(x)
+        ref = torch.cat([sc[:, :3] + mean[None, :, None, None], torch.exp(F.hardtanh(sc[:, 3:], -16.10, 13.82))], 1)
+    assert rel_l2(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_network_matches_reference_fixture_and_torch(name):
+    """Native forward vs the fixture produced by the reference module and vs forward_reference on the GPU."""
+    net, x = build_case(name, DEV)
+    with torch.no_grad():
+        out = net(x)
+        ref = net.forward_reference(x)
+    torch.cuda.synchronize()
+    gold = torch.from_numpy(GOLD[name + '_out']).to(DEV)
+    k = 3
+    assert rel_l2(out[:, :k], ref[:, :k]) < 1e-3          # north-star tolerance: 1e-3 relative fp32
+    assert rel_l2(out[:, :k], gold[:, :k]) < 1e-3
+    assert rel_l2(out, gold) < 1e-3
+    assert rel_l2(out[:, :k], gold[:, :k]) < 5e-5          # what fp16x3 actually delivers
+    assert float((out[:, :k] - gold[:, :k]).abs().max() / gold[:, :k].abs().max()) < 1e-3
+
+
+def test_network_full_resolution_parity_and_determinism():
+    """BASELINE config 1 shape: 480x720 RGB, TransPoseNet(2+2 extra blocks), seed 2021 weights."""
+    import networks.networks as nets
+    torch.manual_seed(2021)
+    net = nets.TransPoseNet(torch.zeros(3), False, False, 2, 2, 3, 1).eval().to(DEV)
+    x = torch.rand(2, 3, 480, 720, generator=torch.Generator().manual_seed(0)).to(DEV)
+    with torch.no_grad():
+        out = net(x)
+        out2 = net(x)
+        ref = net.forward_reference(x)
+    assert tuple(out.shape) == (2, 4, 60, 90)
+    assert rel_l2(out[:, :3], ref[:, :3]) < 1e-3
+    assert float((out[:, :3] - ref[:, :3]).abs().max() / ref[:, :3].abs().max()) < 1e-3
+    assert rel_l2(out[:, 3:], ref[:, 3:]) < 1e-3
+    assert rel_l2(out, out2) < 1e-6   # fp64 atomics make the statistics order-independent up to round-off
+    # batch entries are independent: image 1 alone gives the same map
+    with torch.no_grad():
+        single = net(x[1:2])
+    assert rel_l2(single, out[1:2]) < 1e-6
+
+
+def test_single_pass_precision_is_reported_not_hidden():
+    """fp16x1 is a speed mode that misses the 1e-3 bar by design; make sure the knob does what it says."""
+    import networks.networks as nets
+    torch.manual_seed(2021)
+    net = nets.TransPoseNet(torch.zeros(3), False, False, 2, 2, 3, 1).eval().to(DEV)
+    x = torch.rand(1, 3, 96, 128, generator=torch.Generator().manual_seed(0)).to(DEV)
+    eng = CoordNetEngine(precision='fp16x1')
+    with torch.no_grad():
+        fast = eng.forward(net._spec(), x)
+        ref = net.forward_reference(x)
+    err = rel_l2(fast[:, :3], ref[:, :3])
+    assert 1e-5 < err < 1e-2
