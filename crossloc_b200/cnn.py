@@ -86,6 +86,7 @@ class CoordNetEngine:
         self._pack_versions = {}
         self._ws = {}
         self.launches = 0
+        self.events = None   # set to a list to record (layer, flops, start, end) CUDA events around every conv launch
 
     # ------------------------------------------------------------------ parameters
     def _pack(self, name, conv):
@@ -131,14 +132,22 @@ class CoordNetEngine:
         return buf
 
     # ------------------------------------------------------------------ operators
-    def _conv(self, stream, pack, act, in_phases, geo, raw, stats, group_ch):
+    def _conv(self, stream, pack, act, in_phases, geo, raw, stats, group_ch, name=None):
         taps = _taps(pack, geo)
         tap_arr = (ctypes.c_int32 * len(taps))(*taps)
         lo_rows = in_phases * geo.Mp
+        if self.events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(self._lib.cl_conv_igemm(
             act.data_ptr(), act.size(0), lo_rows, pack.cin, pack.weights.data_ptr(), pack.cout, len(taps), tap_arr,
             self.nterms, geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale, raw.data_ptr(), pack.bias.data_ptr(),
             0 if stats is None else stats.data_ptr(), stream))
+        if self.events is not None:
+            e1.record()
+            # algorithmic FLOPs: 2 * (real output pixels) * Cout * Cin * taps (borders and split terms excluded)
+            flops = 2.0 * geo.B * geo.H * geo.W * pack.cout * pack.cin * len(taps)
+            self.events.append((name, (pack.cin, pack.cout, pack.ksize, pack.stride), flops, e0, e1))
         self.launches += 1
 
     def _apply(self, stream, raw, geo, channels, norm, stats, out, out_phases, relu_inner=True, res=None,
@@ -150,7 +159,7 @@ class CoordNetEngine:
             0 if stats is None else stats.data_ptr(),
             0 if norm is None else norm.weight.data_ptr(), 0 if norm is None else norm.bias.data_ptr(),
             1e-5 if norm is None else float(norm.eps), 1 if relu_inner else 0, add_kind,
-            0 if res is None else res.data_ptr(), geo.Mp,
+            0 if res is None else res.data_ptr(), geo.Mp if self.terms == 2 else 0,
             0 if raw2 is None else raw2.data_ptr(), 0 if stats2 is None else stats2.data_ptr(),
             0 if norm2 is None else norm2.weight.data_ptr(), 0 if norm2 is None else norm2.bias.data_ptr(),
             1 if relu_outer else 0, out.data_ptr(), out_phases, self.terms, stream))
@@ -210,7 +219,7 @@ class CoordNetEngine:
             pack = self._pack(name, conv)
             raw = self._raw(ws, 'ladder', level, pack.cout)
             st = next_stats() if norm is not None else None
-            self._conv(stream, pack, a, 4, geo[level], raw, st, groups_of(norm, pack.cout))
+            self._conv(stream, pack, a, 4, geo[level], raw, st, groups_of(norm, pack.cout), name)
             if level < 3:
                 out = self._act(ws, 'ladder', level + 1, pack.cout, 4)
                 self._apply(stream, raw, geo[level], pack.cout, norm, st, out, 4)
@@ -238,7 +247,7 @@ class CoordNetEngine:
                 pack = self._pack(name, conv)
                 raw = self._raw(ws, 'r%d' % (i % 2), 3, pack.cout)
                 st = next_stats() if norm is not None else None
-                self._conv(stream, pack, x, 1, g3, raw, st, groups_of(norm, pack.cout))
+                self._conv(stream, pack, x, 1, g3, raw, st, groups_of(norm, pack.cout), name)
                 out = scratch(pack.cout, (x, res_in))
                 last = i == len(names) - 1
                 self._apply(stream, raw, g3, pack.cout, norm, st, out, 1, relu_inner=True,
@@ -260,7 +269,7 @@ class CoordNetEngine:
                     pack = self._pack(name, conv)
                     raw = self._raw(ws, 'r%d' % (i % 2), 3, pack.cout)
                     st = next_stats() if norm is not None else None
-                    self._conv(stream, pack, x, 1, g3, raw, st, groups_of(norm, pack.cout))
+                    self._conv(stream, pack, x, 1, g3, raw, st, groups_of(norm, pack.cout), name)
                     out = scratch(pack.cout, (x, res))
                     self._apply(stream, raw, g3, pack.cout, norm, st, out, 1)
                     x = out
@@ -268,12 +277,12 @@ class CoordNetEngine:
                 pack = self._pack(names[-1], conv)
                 raw_x = self._raw(ws, 'r0', 3, pack.cout)
                 st_x = next_stats() if norm is not None else None
-                self._conv(stream, pack, x, 1, g3, raw_x, st_x, groups_of(norm, pack.cout))
+                self._conv(stream, pack, x, 1, g3, raw_x, st_x, groups_of(norm, pack.cout), names[-1])
                 sconv, snorm = convs[block['skip']]
                 spack = self._pack(block['skip'], sconv)
                 raw_s = self._raw(ws, 'r1', 3, spack.cout)
                 st_s = next_stats() if snorm is not None else None
-                self._conv(stream, spack, res, 1, g3, raw_s, st_s, groups_of(snorm, spack.cout))
+                self._conv(stream, spack, res, 1, g3, raw_s, st_s, groups_of(snorm, spack.cout), block['skip'])
                 out = scratch(pack.cout, (x, res))
                 if gn:
                     self._apply(stream, raw_x, g3, pack.cout, norm, st_x, out, 1, relu_inner=True,
@@ -291,7 +300,7 @@ class CoordNetEngine:
                     pack = self._pack(name, conv)
                     raw = self._raw(ws, 'r0', 3, pack.cout)
                     st = next_stats() if norm is not None else None
-                    self._conv(stream, pack, res, 1, g3, raw, st, groups_of(norm, pack.cout))
+                    self._conv(stream, pack, res, 1, g3, raw, st, groups_of(norm, pack.cout), name)
                     out = scratch(pack.cout, (res,))
                     self._apply(stream, raw, g3, pack.cout, norm, st, out, 1)
                     res = out

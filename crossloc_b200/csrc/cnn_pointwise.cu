@@ -80,11 +80,15 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyDesc d)
         }
         if (d.add_kind == 1) {
             const uint4 hq = __ldg(reinterpret_cast<const uint4*>(d.res + row * d.C + c));
-            const uint4 lq = __ldg(reinterpret_cast<const uint4*>(d.res + (row + (size_t)d.res_lo_rows) * d.C + c));
             const __half* hh = reinterpret_cast<const __half*>(&hq);
-            const __half* ll = reinterpret_cast<const __half*>(&lq);
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] += __half2float(hh[j]) + __half2float(ll[j]);
+            for (int j = 0; j < 8; j++) v[j] += __half2float(hh[j]);
+            if (d.res_lo_rows > 0) {   // the residual carries a low-order plane
+                const uint4 lq = __ldg(reinterpret_cast<const uint4*>(d.res + (row + (size_t)d.res_lo_rows) * d.C + c));
+                const __half* ll = reinterpret_cast<const __half*>(&lq);
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] += __half2float(ll[j]);
+            }
         } else if (d.add_kind == 2) {
             const float4* r4 = reinterpret_cast<const float4*>(d.raw2 + row * d.C + c);
             const float4 a = __ldg(r4), bq = __ldg(r4 + 1);

@@ -58,7 +58,7 @@ struct GnApplyDesc {
     float eps;
     int relu_inner;         // ReLU right after the normalisation
     int add_kind;           // 0 none | 1 fp16 hi/lo residual (same geometry, P = 1) | 2 second raw tensor with its own GroupNorm
-    const __half* res;      // add_kind 1: PF matrix, lo plane res_lo_rows rows further
+    const __half* res;      // add_kind 1: PF matrix, lo plane res_lo_rows rows further (0: no lo plane)
     int64_t res_lo_rows;
     const float* raw2;      // add_kind 2
     const double* stats2;

@@ -1,0 +1,95 @@
+"""Public end-to-end API of the localization hot path: RGB frames in, camera poses out.
+
+This is the body of the reference's evaluation loop (/root/reference/test_single_task.py:328-370:
+`network(image.cuda())` -> `torch.split` -> `scene_coords_eval` -> `dsacstar.forward_rgb`) for a batch of
+frames, with the coordinate map kept in HBM between the network and the solver (the reference's
+`.cpu()` round trip, utils/evaluation.py:161, is gone).
+
+`Localizer.localize(images_host)` takes pinned host images and returns host poses; `submit()` /
+`result()` expose the same thing as a two-deep software pipeline so that the host-to-device copy of
+the next batch overlaps the kernels of the current one.
+"""
+import torch
+
+from . import dsac
+
+
+class Localizer:
+    def __init__(self, network, hyps=64, threshold=10.0, alpha=100.0, max_reproj=100.0, seed=1305, device=None):
+        self.net = network
+        self.hyps, self.threshold, self.alpha, self.max_reproj, self.seed = hyps, threshold, alpha, max_reproj, seed
+        self.device = torch.device(device if device is not None else 'cuda')
+        self.subsample = int(getattr(network, 'OUTPUT_SUBSAMPLE', 8))
+        self.num_task = int(getattr(network, 'num_task_channel', 3))
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._slots = [None, None]
+        self._turn = 0
+        self._pending = []
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ device-resident entry
+    def localize_device(self, images, focal, coord_offset=None, image_base=0, out_pose=None, debug=False):
+        """images [B,C,H,W] fp32 CUDA, focal float or [B]; returns poses [B,4,4] fp32 CUDA (camera-to-world).
+
+        `coord_offset` ([B,3,Hc,Wc], optional) is added to the regressed coordinates before the solve: with
+        random-initialised weights the raw map is geometrically meaningless, so the synthetic benchmark turns
+        it into a consistent scene the same way the decoder's `mean` buffer offsets it.
+        """
+        b, _, h, w = images.shape
+        with torch.no_grad():
+            pred = self.net(images)
+            coords = pred[:, :self.num_task]
+            if coord_offset is not None:
+                coords = coords + coord_offset
+            coords = coords.contiguous()
+            if out_pose is None:
+                out_pose = torch.empty(b, 4, 4, dtype=torch.float32, device=images.device)
+            dbg = dsac.forward_rgb_batch(coords, out_pose, self.hyps, self.threshold, focal, w / 2, h / 2, self.alpha,
+                                         self.max_reproj, self.subsample, seed=self.seed, image_base=image_base,
+                                         debug=debug)
+        engine = getattr(self.net, '_engine', None)
+        self.kernel_launches = (engine.launches if engine is not None else 0)
+        return (out_pose, dbg) if debug else out_pose
+
+    # ------------------------------------------------------------------ host entry, pipelined
+    def submit(self, images_host, focal, coord_offset=None, image_base=0):
+        """Queue one batch: async H2D on the copy stream, compute on the current stream, async D2H of the poses."""
+        slot = self._turn
+        self._turn ^= 1
+        b = images_host.size(0)
+        st = self._slots[slot]
+        if st is None or st['images'].shape != images_host.shape:
+            st = {
+                'images': torch.empty(images_host.shape, dtype=torch.float32, device=self.device),
+                'pose_dev': torch.empty(b, 4, 4, dtype=torch.float32, device=self.device),
+                'pose_host': torch.empty(b, 4, 4, dtype=torch.float32).pin_memory(),
+                'done': torch.cuda.Event(),
+                'copied': torch.cuda.Event(),
+                'free': None,
+            }
+            self._slots[slot] = st
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            if st['free'] is not None:
+                self._copy_stream.wait_event(st['free'])   # previous use of this slot's device image has been consumed
+            st['images'].copy_(images_host, non_blocking=True)
+            st['copied'].record(self._copy_stream)
+        compute.wait_event(st['copied'])
+        self.localize_device(st['images'], focal, coord_offset, image_base, out_pose=st['pose_dev'])
+        st['free'] = torch.cuda.Event()
+        st['free'].record(compute)
+        st['pose_host'].copy_(st['pose_dev'], non_blocking=True)
+        st['done'].record(compute)
+        self._pending.append(st)
+        return st
+
+    def result(self):
+        """Poses of the oldest submitted batch (host tensor, valid until its slot is reused two submits later)."""
+        st = self._pending.pop(0)
+        st['done'].synchronize()
+        return st['pose_host']
+
+    def localize(self, images_host, focal, coord_offset=None, image_base=0):
+        """Synchronous form: one batch of pinned host images -> host poses."""
+        self.submit(images_host, focal, coord_offset, image_base)
+        return self.result()

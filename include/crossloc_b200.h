@@ -96,6 +96,7 @@ int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int 
  * GroupNorm apply + ReLU + residual merge, fp32 raw -> fp16 hi/lo PF input of the next convolution.
  * Replaces nn.GroupNorm + F.relu (+ `res + x`) (networks.py:231-254, 332-343).
  *   out = relu_outer( add + relu_inner( gn(raw) ) ),  add = 0 | res_hi + res_lo | gn2(raw2)
+ *   res_lo_rows: row distance of the residual's lo plane, 0 when it has none (single-pass mode)
  *   out_phases 1: same geometry;  4: the four parity phases at (ceil(H/2), ceil(W/2)).
  */
 int cl_gn_apply(const float* raw, int B, int H, int W, int C, int group_ch, const double* stats, const float* gamma,
