@@ -119,31 +119,37 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_rate(sample_images, hyps, threads):
-    """images/s of the all-CPU path (stock torch network on the host + C/OpenMP DSAC*) over a bounded sample."""
-    from oracle import dsac_oracle_c as tier2
-    torch.set_num_threads(threads)
-    net = build_network('cpu')
-    images, offsets, poses, focal = synthetic_batch(5000, sample_images)
-    # one warm-up image (thread pools, oneDNN primitive caches)
-    with torch.no_grad():
-        net.forward_reference(images[:1])
-    t0 = time.perf_counter()
-    t_net = t_solve = 0.0
-    for i in range(sample_images):   # batch size 1, as the reference evaluates (utils/evaluation.py:69)
-        t1 = time.perf_counter()
-        with torch.no_grad():
-            pred = net.forward_reference(images[i:i + 1])
-        coords = (pred[:, :3] + offsets[i:i + 1]).contiguous().numpy()
-        t2 = time.perf_counter()
-        tier2.forward_rgb(coords[0], hyps, 10.0, float(focal[i]), WIDTH / 2, HEIGHT / 2, 100.0, 100.0, 8,
-                          seed=1305, image=5000 + i)
-        t3 = time.perf_counter()
-        t_net += t2 - t1
-        t_solve += t3 - t2
-    total = time.perf_counter() - t0
-    return sample_images / total, {'network_s_per_image': t_net / sample_images,
-                                   'solver_s_per_image': t_solve / sample_images}
+class CpuPath:
+    """The all-CPU path: stock torch network on the host cores + C/OpenMP DSAC* (batch size 1, as the reference)."""
+
+    def __init__(self, hyps, threads, frames):
+        from oracle import dsac_oracle_c as tier2
+        self.tier2 = tier2
+        self.hyps = hyps
+        torch.set_num_threads(threads)
+        self.net = build_network('cpu')
+        self.images, self.offsets, _, self.focal = synthetic_batch(5000, frames)
+        with torch.no_grad():   # warm-up: thread pools, oneDNN primitive caches
+            self.net.forward_reference(self.images[:1])
+
+    def rate(self, frames):
+        """images/s over `frames` frames, plus the split between network and solver."""
+        t0 = time.perf_counter()
+        t_net = t_solve = 0.0
+        for i in range(frames):   # utils/evaluation.py:69 evaluates with batch size 1
+            j = i % self.images.size(0)
+            t1 = time.perf_counter()
+            with torch.no_grad():
+                pred = self.net.forward_reference(self.images[j:j + 1])
+            coords = (pred[:, :3] + self.offsets[j:j + 1]).contiguous().numpy()
+            t2 = time.perf_counter()
+            self.tier2.forward_rgb(coords[0], self.hyps, 10.0, float(self.focal[j]), WIDTH / 2, HEIGHT / 2, 100.0,
+                                   100.0, 8, seed=1305, image=5000 + j)
+            t3 = time.perf_counter()
+            t_net += t2 - t1
+            t_solve += t3 - t2
+        total = time.perf_counter() - t0
+        return frames / total, {'network_s_per_image': t_net / frames, 'solver_s_per_image': t_solve / frames}
 
 
 def run_reference(args):
@@ -153,13 +159,14 @@ def run_reference(args):
     threads = len(os.sched_getaffinity(0))
     os.environ.setdefault('OMP_NUM_THREADS', str(threads))
     per_step = 2   # bounded sample: two frames per step keeps --steps 10 --warmup 3 within a few minutes
+    path = CpuPath(args.hyps, threads, per_step)
     rates = []
     detail = {}
     for step in range(args.warmup + args.steps):
-        rate, detail = cpu_reference_rate(per_step, args.hyps, threads)
+        rate, detail = path.rate(per_step)
         if step >= args.warmup:
             rates.append(rate)
-    value = float(statistics.median(rates))
+    value = per_step * len(rates) / sum(per_step / r for r in rates)   # frames / total time of the timed steps
     sample = '%d frames per step, batch size 1, %d hypotheses' % (per_step, args.hyps)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
@@ -296,7 +303,7 @@ def run_native(args):
             threads = len(os.sched_getaffinity(0))
             os.environ.setdefault('OMP_NUM_THREADS', str(threads))
             sample = 6
-            rate, detail = cpu_reference_rate(sample, args.hyps, threads)
+            rate, detail = CpuPath(args.hyps, threads, sample).rate(sample)
             cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                             'sample': '%d frames, batch size 1, %d hypotheses: stock torch network on the host cores + '
                                       'oracle/dsac_oracle.c (OpenMP)' % (sample, args.hyps), **detail}
