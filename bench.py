@@ -261,7 +261,16 @@ def run_native(args):
     peak_tf, peak_src = (peaks.get('bf16_tflops_sustained'), 'MEASURED_PEAKS.json bf16_tflops_sustained') \
         if peaks.get('bf16_tflops_sustained') else (1400.0, 'B200_PROFILING.md fallback (sustained)')
     dom = [(fl, e0.elapsed_time(e1)) for (name, shape, fl, e0, e1) in conv_events if shape == (512, 512, 3, 1)]
-    conv_total_ms = sum(e0.elapsed_time(e1) for (_, _, _, e0, e1) in conv_events) / args.steps
+    by_shape = {}
+    for (name, shape, fl, e0, e1) in conv_events:
+        key = '/'.join(str(x) for x in shape)
+        ent = by_shape.setdefault(key, [0, 0.0, fl])
+        ent[0] += 1
+        ent[1] += e0.elapsed_time(e1)
+    kernel_ms = {k: {'launches_per_step': v[0] / args.steps, 'ms_per_step': v[1] / args.steps,
+                     'avg_ms': v[1] / v[0], 'tflops_useful': (v[2] / (v[1] / v[0] * 1e-3) / 1e12) if v[2] else None}
+                 for k, v in by_shape.items()}
+    conv_total_ms = sum(e0.elapsed_time(e1) for (_, shape, _, e0, e1) in conv_events if len(shape) == 4 and shape[0] != 'gn_apply') / args.steps
     roofline = None
     if dom:
         avg_ms = sum(ms for _, ms in dom) / len(dom)
@@ -324,6 +333,7 @@ def run_native(args):
             'cpu_baseline': cpu_baseline,
             'conv_tflops_useful': B * CONV_GFLOP_PER_IMAGE / conv_total_ms if conv_total_ms else None,
             'pose_error_median': {'t_m': float(np.median(errs[:, 0])), 'r_deg': float(np.median(errs[:, 1]))},
+            'kernel_ms': kernel_ms,
         }
         print(json.dumps(line))
     if world > 1:

@@ -132,6 +132,19 @@ class CoordNetEngine:
         return buf
 
     # ------------------------------------------------------------------ operators
+    def _tick(self):
+        if self.events is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _tock(self, e0, name, shape, flops):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.events.append((name, shape, flops, e0, e1))
+
     def _conv(self, stream, pack, act, in_phases, geo, raw, stats, group_ch, name=None):
         taps = _taps(pack, geo)
         tap_arr = (ctypes.c_int32 * len(taps))(*taps)
@@ -154,6 +167,7 @@ class CoordNetEngine:
                raw2=None, norm2=None, stats2=None, relu_outer=False):
         group_ch = 0 if norm is None else channels // norm.num_groups
         add_kind = 1 if res is not None else (2 if raw2 is not None else 0)
+        e0 = self._tick()
         _lib.check(self._lib.cl_gn_apply(
             raw.data_ptr(), geo.B, geo.H, geo.W, channels, group_ch,
             0 if stats is None else stats.data_ptr(),
@@ -163,6 +177,7 @@ class CoordNetEngine:
             0 if raw2 is None else raw2.data_ptr(), 0 if stats2 is None else stats2.data_ptr(),
             0 if norm2 is None else norm2.weight.data_ptr(), 0 if norm2 is None else norm2.bias.data_ptr(),
             1 if relu_outer else 0, out.data_ptr(), out_phases, self.terms, stream))
+        self._tock(e0, 'gn_apply', ('gn_apply', channels, out_phases, add_kind), 0.0)
         self.launches += 1
 
     # ------------------------------------------------------------------ plans
@@ -205,12 +220,14 @@ class CoordNetEngine:
             raise RuntimeError('crossloc_b200: the stem kernel is built for 32 channels / 32 groups')
         a = self._act(ws, 'stem', 1, 32, 4)
         st = next_stats() if norm1 is not None else None
+        e0 = self._tick()
         _lib.check(self._lib.cl_stem_forward(
             image.data_ptr(), batch, cin, h, w, conv1.weight.detach().contiguous().data_ptr(),
             conv1.bias.detach().contiguous().data_ptr(), 1 if norm1 is not None else 0,
             0 if st is None else st.data_ptr(), 0 if norm1 is None else norm1.weight.data_ptr(),
             0 if norm1 is None else norm1.bias.data_ptr(), 1e-5 if norm1 is None else float(norm1.eps),
             a.data_ptr(), self.terms, stream))
+        self._tock(e0, 'stem', ('stem',), 2.0 * batch * h * w * 32 * cin * 9)
         self.launches += 2 if norm1 is not None else 1
 
         # ---- strided ladder conv2..conv4
@@ -313,11 +330,13 @@ class CoordNetEngine:
         co = hconv.out_channels
         out = torch.empty(batch, co, g3.H, g3.W, dtype=torch.float32, device=dev)
         mean = head['mean'].to(device=dev, dtype=torch.float32).contiguous()
+        e0 = self._tick()
         _lib.check(self._lib.cl_head_forward(
             res.data_ptr(), g3.Mp, self.terms, batch, g3.H, g3.W, hconv.in_channels, co,
             hconv.weight.detach().reshape(co, -1).contiguous().data_ptr(),
             hconv.bias.detach().contiguous().data_ptr(), mean.data_ptr(), head['num_task'],
             head['clamp'][0], head['clamp'][1], out.data_ptr(), stream))
+        self._tock(e0, 'head', ('head',), 0.0)
         self.launches += 1
         # keep parameter temporaries alive until the stream has consumed them
         self._keepalive = (mean,)

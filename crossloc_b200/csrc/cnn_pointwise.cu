@@ -40,196 +40,310 @@ __device__ __forceinline__ void split_store8(__half* hi_ptr, __half* lo_ptr, con
     if (write_lo) *reinterpret_cast<uint4*>(lo_ptr) = *reinterpret_cast<const uint4*>(l);
 }
 
-// One thread = 8 consecutive channels of one interior pixel.
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyDesc d)
+// One work item = 8 consecutive channels of one interior pixel; every thread handles kGnUnroll items per
+// grid-stride step so that several independent 16-byte loads are in flight.  The per-(image, group) mean and
+// 1/sigma are derived once per block from the fp64 sums into shared memory.
+constexpr int kGnThreads = 256;
+constexpr int kGnUnroll = 4;
+
+struct GnLane {
+    int c;              // first of the 8 channels this thread owns (constant over the grid-stride loop)
+    int gshift;         // log2(channels per group)
+    float ga[8], be[8];
+};
+
+struct GnItem {
+    size_t row;         // PF row of the pixel in the input geometry
+    unsigned b;
+    int y, x;
+    float4 r0, r1;      // raw conv output
+    uint4 a0, a1;       // ADD_KIND 1: residual hi / lo halves;  ADD_KIND 2: second raw tensor (as bits)
+    bool live;
+};
+
+// phase 1: address arithmetic + all global loads of one item (no stores in between items: the loads of the
+// kGnUnroll items of a thread are in flight together)
+template <int ADD_KIND>
+__device__ __forceinline__ void gn_load(const GnApplyDesc& d, int c, unsigned pix, unsigned total_pix, int Wp, int plane,
+                                        GnItem& it)
 {
-    const int c8n = d.C / 8;
-    const long long total = (long long)d.B * d.H * d.W * c8n;
+    it.live = pix < total_pix;
+    if (!it.live) return;
+    const unsigned hw = (unsigned)(d.H * d.W);
+    it.b = pix / hw;
+    const unsigned rem = pix - it.b * hw;
+    it.y = (int)(rem / (unsigned)d.W);
+    it.x = (int)(rem - (unsigned)it.y * (unsigned)d.W);
+    it.row = (size_t)it.b * plane + (size_t)(it.y + 1) * Wp + (it.x + 1);
+    const float4* r4 = reinterpret_cast<const float4*>(d.raw + it.row * d.C + c);
+    it.r0 = __ldg(r4);
+    it.r1 = __ldg(r4 + 1);
+    if (ADD_KIND == 1) {
+        it.a0 = __ldg(reinterpret_cast<const uint4*>(d.res + it.row * d.C + c));
+        it.a1 = d.res_lo_rows > 0 ? __ldg(reinterpret_cast<const uint4*>(d.res + (it.row + (size_t)d.res_lo_rows) * d.C + c))
+                                  : make_uint4(0, 0, 0, 0);
+    } else if (ADD_KIND == 2) {
+        const uint4* q4 = reinterpret_cast<const uint4*>(d.raw2 + it.row * d.C + c);
+        it.a0 = __ldg(q4);
+        it.a1 = __ldg(q4 + 1);
+    }
+}
+
+// phase 2: normalise, merge, split into fp16 hi / lo and store
+template <int ADD_KIND>
+__device__ __forceinline__ void gn_finish(const GnApplyDesc& d, const GnLane& t, const GnItem& it, int plane, int Wop,
+                                          int oplane, int groups, const float2* tab1, const float2* tab2)
+{
+    if (!it.live) return;
+    const int c = t.c;
+    float v[8] = {it.r0.x, it.r0.y, it.r0.z, it.r0.w, it.r1.x, it.r1.y, it.r1.z, it.r1.w};
+    if (d.group_ch) {
+        const float2* tb = tab1 + it.b * groups;
+        if (t.gshift >= 3) {   // the 8 channels share one group
+            const float2 mr = tb[c >> t.gshift];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = (v[j] - mr.x) * (mr.y * t.ga[j]) + t.be[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float2 mr = tb[(c + j) >> t.gshift];
+                v[j] = (v[j] - mr.x) * (mr.y * t.ga[j]) + t.be[j];
+            }
+        }
+    }
+    if (d.relu_inner) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (ADD_KIND == 1) {
+        const __half2* hh = reinterpret_cast<const __half2*>(&it.a0);
+        const __half2* ll = reinterpret_cast<const __half2*>(&it.a1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 a = __half22float2(hh[j]), bq = __half22float2(ll[j]);
+            v[2 * j] += a.x + bq.x;
+            v[2 * j + 1] += a.y + bq.y;
+        }
+    } else if (ADD_KIND == 2) {
+        const float w[8] = {__uint_as_float(it.a0.x), __uint_as_float(it.a0.y), __uint_as_float(it.a0.z), __uint_as_float(it.a0.w),
+                            __uint_as_float(it.a1.x), __uint_as_float(it.a1.y), __uint_as_float(it.a1.z), __uint_as_float(it.a1.w)};
+        const float2* tb = tab2 + it.b * groups;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float2 mr = tb[(c + j) >> t.gshift];
+            v[j] += (w[j] - mr.x) * (mr.y * __ldg(d.gamma2 + c + j)) + __ldg(d.beta2 + c + j);
+        }
+    }
+    if (d.relu_outer) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
+    }
+    size_t orow, olo;
+    if (d.out_phases == 1) {
+        orow = it.row;
+        olo = (size_t)d.B * plane;
+    } else {
+        const int ph = (it.y & 1) * 2 + (it.x & 1);
+        orow = ((size_t)ph * d.B + it.b) * oplane + (size_t)(it.y / 2 + 1) * Wop + (it.x / 2 + 1);
+        olo = (size_t)4 * d.B * oplane;
+    }
+    split_store8(d.out + orow * d.C + c, d.out + (orow + olo) * d.C + c, v, d.out_terms == 2);
+}
+
+template <int ADD_KIND>
+__global__ void __launch_bounds__(kGnThreads, 2) gn_apply_kernel(GnApplyDesc d)
+{
+    extern __shared__ float2 gn_tab[];   // [B * groups] (mean, 1/sigma), twice when a second GroupNorm is merged
+    const int groups = d.group_ch ? d.C / d.group_ch : 1;
+    const float2* tab1 = gn_tab;
+    const float2* tab2 = gn_tab + d.B * groups;
+    if (d.group_ch) {
+        const double count = (double)d.group_ch * d.H * d.W;
+        for (int i = threadIdx.x; i < d.B * groups; i += kGnThreads) {
+            float m, r;
+            mean_rstd(d.stats, i / groups, groups, i % groups, count, d.eps, m, r);
+            gn_tab[i] = make_float2(m, r);
+            if (ADD_KIND == 2) {
+                mean_rstd(d.stats2, i / groups, groups, i % groups, count, d.eps, m, r);
+                gn_tab[d.B * groups + i] = make_float2(m, r);
+            }
+        }
+        __syncthreads();
+    }
+    // C / 8 divides the block size, so a thread keeps the same 8 channels for every pixel it visits:
+    // the affine parameters live in registers and only the pixel index advances.
+    const unsigned c8n = (unsigned)(d.C / 8);
+    const unsigned pix_per_block = kGnThreads / c8n;
+    GnLane t;
+    t.c = (int)(threadIdx.x % c8n) * 8;
+    t.gshift = d.group_ch ? 31 - __clz(d.group_ch) : 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        t.ga[j] = d.group_ch ? __ldg(d.gamma + t.c + j) : 1.f;
+        t.be[j] = d.group_ch ? __ldg(d.beta + t.c + j) : 0.f;
+    }
+    const unsigned total_pix = (unsigned)d.B * (unsigned)(d.H * d.W);
     const int Wp = d.W + 2, plane = (d.H + 2) * Wp;
     const int Ho = (d.H + 1) / 2, Wo = (d.W + 1) / 2, Wop = Wo + 2, oplane = (Ho + 2) * Wop;
-    const int groups = d.group_ch ? d.C / d.group_ch : 1;
-    const double count = (double)d.group_ch * d.H * d.W;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % c8n) * 8;
-        const long long pix = idx / c8n;
-        const int x = (int)(pix % d.W);
-        const int y = (int)((pix / d.W) % d.H);
-        const int b = (int)(pix / ((long long)d.W * d.H));
-        const size_t row = (size_t)b * plane + (size_t)(y + 1) * Wp + (x + 1);
-
-        float v[8];
-        {
-            const float4* r4 = reinterpret_cast<const float4*>(d.raw + row * d.C + c);
-            const float4 a = __ldg(r4), bq = __ldg(r4 + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
-        }
-        if (d.group_ch) {
-            int gprev = -1;
-            float mean = 0.f, rstd = 1.f;
+    const unsigned stride = gridDim.x * pix_per_block;
+    for (unsigned base = blockIdx.x * pix_per_block + threadIdx.x / c8n; base < total_pix; base += stride * kGnUnroll) {
+        GnItem items[kGnUnroll];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int g = (c + j) / d.group_ch;
-                if (g != gprev) { mean_rstd(d.stats, b, groups, g, count, d.eps, mean, rstd); gprev = g; }
-                v[j] = (v[j] - mean) * rstd * __ldg(d.gamma + c + j) + __ldg(d.beta + c + j);
-            }
-        }
-        if (d.relu_inner) {
+        for (int u = 0; u < kGnUnroll; u++) gn_load<ADD_KIND>(d, t.c, base + (unsigned)u * stride, total_pix, Wp, plane, items[u]);
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (d.add_kind == 1) {
-            const uint4 hq = __ldg(reinterpret_cast<const uint4*>(d.res + row * d.C + c));
-            const __half* hh = reinterpret_cast<const __half*>(&hq);
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[j] += __half2float(hh[j]);
-            if (d.res_lo_rows > 0) {   // the residual carries a low-order plane
-                const uint4 lq = __ldg(reinterpret_cast<const uint4*>(d.res + (row + (size_t)d.res_lo_rows) * d.C + c));
-                const __half* ll = reinterpret_cast<const __half*>(&lq);
-#pragma unroll
-                for (int j = 0; j < 8; j++) v[j] += __half2float(ll[j]);
-            }
-        } else if (d.add_kind == 2) {
-            const float4* r4 = reinterpret_cast<const float4*>(d.raw2 + row * d.C + c);
-            const float4 a = __ldg(r4), bq = __ldg(r4 + 1);
-            float w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
-            int gprev = -1;
-            float mean = 0.f, rstd = 1.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int g = (c + j) / d.group_ch;
-                if (g != gprev) { mean_rstd(d.stats2, b, groups, g, count, d.eps, mean, rstd); gprev = g; }
-                v[j] += (w[j] - mean) * rstd * __ldg(d.gamma2 + c + j) + __ldg(d.beta2 + c + j);
-            }
-        }
-        if (d.relu_outer) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
-        }
-
-        size_t orow, olo;
-        if (d.out_phases == 1) {
-            orow = row;
-            olo = (size_t)d.B * plane;
-        } else {
-            const int ph = (y & 1) * 2 + (x & 1);
-            orow = ((size_t)ph * d.B + b) * oplane + (size_t)(y / 2 + 1) * Wop + (x / 2 + 1);
-            olo = (size_t)4 * d.B * oplane;
-        }
-        split_store8(d.out + orow * d.C + c, d.out + (orow + olo) * d.C + c, v, d.out_terms == 2);
+        for (int u = 0; u < kGnUnroll; u++) gn_finish<ADD_KIND>(d, t, items[u], plane, Wop, oplane, groups, tab1, tab2);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stem: direct 3x3 convolution, one output pixel (32 channels) per thread, weights broadcast from smem.
-// STATS pass accumulates per-(image, channel) sums; APPLY pass recomputes the convolution, normalises,
-// applies ReLU and writes the fp16 hi/lo planes straight into the four-phase input of the next layer.
+// Stem: direct 3x3 convolution on the CUDA cores (K = 27 is too thin for the tensor pipe), weights broadcast
+// from shared memory.  One thread = two vertically adjacent output pixels x 32 channels, so every weight
+// vector fetched feeds 64 FMAs and the 4x3 input patch is shared.  STATS pass: per-(image, channel) sum and sum
+// of squares (reduce-scatter over the warp after every segment, two running registers per lane, one fp64
+// atomic per block and moment).  APPLY pass: recomputes the convolution, normalises, applies ReLU and writes
+// the fp16 hi/lo planes straight into the four-phase input of conv2 -- the 32-channel full-resolution fp32
+// tensor (1.4 GB at 32 frames) is never materialised.
 constexpr int kStemThreads = 256;
 constexpr int kStemCo = 32;
 
-template <bool STATS>
-__global__ void __launch_bounds__(kStemThreads) stem_kernel(StemDesc d)
+// recursive-halving butterfly over 64 interleaved (sum, sum of squares) values: on return lane l holds the
+// totals of channel stem_channel_of(l) in v[0], v[1]
+__device__ __forceinline__ void stem_reduce_scatter(float (&v)[2 * kStemCo], int lane)
 {
-    __shared__ float w_s[27 * kStemCo];   // [ci*9 + kh*3 + kw][co]
+    int cur = 2 * kStemCo;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const int half = cur >> 1;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < kStemCo; i++) {
+            if (i < half) {
+                const float send = upper ? v[i] : v[i + half];
+                const float keep = upper ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        cur = half;
+    }
+}
+__device__ __forceinline__ int stem_channel_of(int lane)
+{
+    return ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(StemDesc d)
+{
+    __shared__ __align__(16) float w_s[27 * kStemCo];   // [ci*9 + kh*3 + kw][co]
     __shared__ float b_s[kStemCo];
+    __shared__ float2 affine_s[kStemCo];                // APPLY: y = max(x * scale + shift, 0)
     __shared__ float red_s[kStemThreads / 32][2 * kStemCo];
     const int taps = d.Cin * 9;
+    const int b = blockIdx.y;
     for (int i = threadIdx.x; i < taps * kStemCo; i += kStemThreads) {
         const int co = i % kStemCo, t = i / kStemCo;
         w_s[i] = d.weight[co * taps + t];
     }
-    if (threadIdx.x < kStemCo) b_s[threadIdx.x] = d.bias[threadIdx.x];
-    __syncthreads();
-
-    const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int segs_x = (d.W + 31) / 32;
-    const int segs = d.H * segs_x;
-    const float* img = d.image + (size_t)b * d.Cin * d.H * d.W;
-    const int Ho = (d.H + 1) / 2, Wo = (d.W + 1) / 2, Wop = Wo + 2, oplane = (Ho + 2) * Wop;
-
-    float scale[kStemCo], shift[kStemCo];
-    if (!STATS) {
-        const double count = (double)d.H * d.W;
-#pragma unroll
-        for (int co = 0; co < kStemCo; co++) {
+    if (threadIdx.x < kStemCo) {
+        b_s[threadIdx.x] = d.bias[threadIdx.x];
+        if (!STATS) {
+            float scale = 1.f, shift = 0.f;
             if (d.has_gn) {
                 float mean, rstd;
-                mean_rstd(d.stats, b, kStemCo, co, count, d.eps, mean, rstd);
-                scale[co] = rstd * d.gamma[co];
-                shift[co] = d.beta[co] - mean * scale[co];
-            } else {
-                scale[co] = 1.f;
-                shift[co] = 0.f;
+                mean_rstd(d.stats, b, kStemCo, threadIdx.x, (double)d.H * d.W, d.eps, mean, rstd);
+                scale = rstd * d.gamma[threadIdx.x];
+                shift = d.beta[threadIdx.x] - mean * scale;
             }
+            affine_s[threadIdx.x] = make_float2(scale, shift);
         }
     }
-    float s1[kStemCo], s2[kStemCo];
-    if (STATS) {
-#pragma unroll
-        for (int co = 0; co < kStemCo; co++) { s1[co] = 0.f; s2[co] = 0.f; }
-    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int segs_x = (d.W + 31) / 32;
+    const int pairs_y = (d.H + 1) / 2;
+    const int segs = pairs_y * segs_x;
+    const float* img = d.image + (size_t)b * d.Cin * d.H * d.W;
+    const int Ho = (d.H + 1) / 2, Wo = (d.W + 1) / 2, Wop = Wo + 2, oplane = (Ho + 2) * Wop;
+    float tot1 = 0.f, tot2 = 0.f;   // STATS: running totals of channel stem_channel_of(lane)
 
     for (int seg = blockIdx.x * (kStemThreads / 32) + warp; seg < segs; seg += gridDim.x * (kStemThreads / 32)) {
-        const int y = seg / segs_x, x = (seg % segs_x) * 32 + lane;
+        const int yp = seg / segs_x, y0 = 2 * yp, x = (seg % segs_x) * 32 + lane;
         const bool inside = x < d.W;
-        float acc[kStemCo];
+        const bool row1 = y0 + 1 < d.H;
+        float acc0[kStemCo], acc1[kStemCo];
 #pragma unroll
-        for (int co = 0; co < kStemCo; co++) acc[co] = b_s[co];
+        for (int co = 0; co < kStemCo; co++) { acc0[co] = b_s[co]; acc1[co] = b_s[co]; }
         for (int ci = 0; ci < d.Cin; ci++) {
+            float in[4][3];
 #pragma unroll
-            for (int kh = 0; kh < 3; kh++) {
-                const int yy = y + kh - 1;
+            for (int r = 0; r < 4; r++) {
+                const int yy = y0 + r - 1;
 #pragma unroll
                 for (int kw = 0; kw < 3; kw++) {
                     const int xx = x + kw - 1;
-                    float xv = 0.f;
-                    if (inside && yy >= 0 && yy < d.H && xx >= 0 && xx < d.W) xv = __ldg(img + ((size_t)ci * d.H + yy) * d.W + xx);
+                    in[r][kw] = (inside && yy >= 0 && yy < d.H && xx >= 0 && xx < d.W)
+                                    ? __ldg(img + ((size_t)ci * d.H + yy) * d.W + xx) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int kh = 0; kh < 3; kh++) {
+#pragma unroll
+                for (int kw = 0; kw < 3; kw++) {
+                    const float xv0 = in[kh][kw], xv1 = in[kh + 1][kw];
                     const float4* w4 = reinterpret_cast<const float4*>(w_s + (ci * 9 + kh * 3 + kw) * kStemCo);
 #pragma unroll
                     for (int j = 0; j < kStemCo / 4; j++) {
                         const float4 w = w4[j];
-                        acc[4 * j + 0] = fmaf(xv, w.x, acc[4 * j + 0]);
-                        acc[4 * j + 1] = fmaf(xv, w.y, acc[4 * j + 1]);
-                        acc[4 * j + 2] = fmaf(xv, w.z, acc[4 * j + 2]);
-                        acc[4 * j + 3] = fmaf(xv, w.w, acc[4 * j + 3]);
+                        acc0[4 * j + 0] = fmaf(xv0, w.x, acc0[4 * j + 0]);
+                        acc0[4 * j + 1] = fmaf(xv0, w.y, acc0[4 * j + 1]);
+                        acc0[4 * j + 2] = fmaf(xv0, w.z, acc0[4 * j + 2]);
+                        acc0[4 * j + 3] = fmaf(xv0, w.w, acc0[4 * j + 3]);
+                        acc1[4 * j + 0] = fmaf(xv1, w.x, acc1[4 * j + 0]);
+                        acc1[4 * j + 1] = fmaf(xv1, w.y, acc1[4 * j + 1]);
+                        acc1[4 * j + 2] = fmaf(xv1, w.z, acc1[4 * j + 2]);
+                        acc1[4 * j + 3] = fmaf(xv1, w.w, acc1[4 * j + 3]);
                     }
                 }
             }
         }
         if (STATS) {
-            if (inside) {
+            float v[2 * kStemCo];
+            const float m0 = inside ? 1.f : 0.f, m1 = (inside && row1) ? 1.f : 0.f;
 #pragma unroll
-                for (int co = 0; co < kStemCo; co++) { s1[co] += acc[co]; s2[co] += acc[co] * acc[co]; }
+            for (int co = 0; co < kStemCo; co++) {
+                const float a0 = acc0[co] * m0, a1 = acc1[co] * m1;
+                v[2 * co] = a0 + a1;
+                v[2 * co + 1] = a0 * a0 + a1 * a1;
             }
+            stem_reduce_scatter(v, lane);
+            tot1 += v[0];
+            tot2 += v[1];
         } else if (inside) {
-            const int ph = (y & 1) * 2 + (x & 1);
-            const size_t orow = ((size_t)ph * d.B + b) * oplane + (size_t)(y / 2 + 1) * Wop + (x / 2 + 1);
             const size_t olo = (size_t)4 * d.B * oplane;
 #pragma unroll
-            for (int c0 = 0; c0 < kStemCo; c0 += 8) {
-                float v[8];
+            for (int r = 0; r < 2; r++) {
+                if (r == 1 && !row1) break;
+                const int ph = r * 2 + (x & 1);
+                const size_t orow = ((size_t)ph * d.B + b) * oplane + (size_t)(yp + 1) * Wop + (x / 2 + 1);
 #pragma unroll
-                for (int j = 0; j < 8; j++) v[j] = fmaxf(fmaf(acc[c0 + j], scale[c0 + j], shift[c0 + j]), 0.f);
-                split_store8(d.out + orow * kStemCo + c0, d.out + (orow + olo) * kStemCo + c0, v, d.out_terms == 2);
+                for (int c0 = 0; c0 < kStemCo; c0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float2 af = affine_s[c0 + j];
+                        v[j] = fmaxf(fmaf(r == 0 ? acc0[c0 + j] : acc1[c0 + j], af.x, af.y), 0.f);
+                    }
+                    split_store8(d.out + orow * kStemCo + c0, d.out + (orow + olo) * kStemCo + c0, v, d.out_terms == 2);
+                }
             }
         }
     }
 
     if (STATS) {
-        // warp totals -> shared -> one fp64 atomic per (block, channel, moment)
-#pragma unroll
-        for (int co = 0; co < kStemCo; co++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s1[co] += __shfl_xor_sync(0xffffffffu, s1[co], o);
-                s2[co] += __shfl_xor_sync(0xffffffffu, s2[co], o);
-            }
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int co = 0; co < kStemCo; co++) { red_s[warp][2 * co] = s1[co]; red_s[warp][2 * co + 1] = s2[co]; }
-        }
+        const int ch = stem_channel_of(lane);
+        red_s[warp][2 * ch] = tot1;
+        red_s[warp][2 * ch + 1] = tot2;
         __syncthreads();
         if (threadIdx.x < 2 * kStemCo) {
             double t = 0;
@@ -240,56 +354,68 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(StemDesc d)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Head: one warp per pixel, fp32 weights in shared memory, fp16 hi+lo activations.
+// Head: one warp per pixel; every lane owns 8 (x2 for C > 256) fixed input channels and keeps their fp32 weights
+// for all output channels in registers, so the per-pixel work is two 16-byte loads per plane, Co x 8 FMAs per
+// slice and a shuffle reduction.
 constexpr int kHeadThreads = 256;
 constexpr int kHeadMaxCo = 8;
+constexpr int kHeadMaxC = 512;
 
+template <int CO>
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadDesc d)
 {
-    extern __shared__ float hw_s[];   // [Co][C]
-    for (int i = threadIdx.x; i < d.Co * d.C; i += kHeadThreads) hw_s[i] = d.weight[i];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Wp = d.W + 2, plane = (d.H + 2) * Wp;
     const long long total = (long long)d.B * d.H * d.W;
+    const int slices = (d.C + 255) / 256;   // 1 or 2
+    float w[2][CO][8];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int c = s * 256 + lane * 8;
+#pragma unroll
+        for (int o = 0; o < CO; o++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) w[s][o][j] = (s < slices && c + j < d.C && o < d.Co) ? d.weight[o * d.C + c + j] : 0.f;
+    }
     for (long long pix = blockIdx.x * (long long)(kHeadThreads / 32) + warp; pix < total;
          pix += (long long)gridDim.x * (kHeadThreads / 32)) {
         const int x = (int)(pix % d.W);
         const int y = (int)((pix / d.W) % d.H);
         const int b = (int)(pix / ((long long)d.W * d.H));
         const size_t row = (size_t)b * plane + (size_t)(y + 1) * Wp + (x + 1);
-        float acc[kHeadMaxCo];
+        float acc[CO];
 #pragma unroll
-        for (int o = 0; o < kHeadMaxCo; o++) acc[o] = 0.f;
-        for (int c = lane * 8; c < d.C; c += 256) {
-            const uint4 hq = __ldg(reinterpret_cast<const uint4*>(d.act + row * d.C + c));
-            const __half* hh = reinterpret_cast<const __half*>(&hq);
-            float v[8];
+        for (int o = 0; o < CO; o++) acc[o] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = __half2float(hh[j]);
-            if (d.in_terms == 2) {
-                const uint4 lq = __ldg(reinterpret_cast<const uint4*>(d.act + (row + (size_t)d.act_lo_rows) * d.C + c));
-                const __half* ll = reinterpret_cast<const __half*>(&lq);
+        for (int s = 0; s < 2; s++) {
+            const int c = s * 256 + lane * 8;
+            if (s < slices && c < d.C) {
+                const uint4 hq = __ldg(reinterpret_cast<const uint4*>(d.act + row * d.C + c));
+                const __half* hh = reinterpret_cast<const __half*>(&hq);
+                float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) v[j] += __half2float(ll[j]);
-            }
+                for (int j = 0; j < 8; j++) v[j] = __half2float(hh[j]);
+                if (d.in_terms == 2) {
+                    const uint4 lq = __ldg(reinterpret_cast<const uint4*>(d.act + (row + (size_t)d.act_lo_rows) * d.C + c));
+                    const __half* ll = reinterpret_cast<const __half*>(&lq);
 #pragma unroll
-            for (int o = 0; o < kHeadMaxCo; o++) {
-                if (o < d.Co) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) acc[o] = fmaf(v[j], hw_s[o * d.C + c + j], acc[o]);
+                    for (int j = 0; j < 8; j++) v[j] += __half2float(ll[j]);
                 }
+#pragma unroll
+                for (int o = 0; o < CO; o++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[o] = fmaf(v[j], w[s][o][j], acc[o]);
             }
         }
 #pragma unroll
-        for (int o = 0; o < kHeadMaxCo; o++) {
+        for (int o = 0; o < CO; o++) {
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+            for (int sft = 16; sft > 0; sft >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
         }
         if (lane < d.Co) {
             float r = 0.f;
 #pragma unroll
-            for (int o = 0; o < kHeadMaxCo; o++)
+            for (int o = 0; o < CO; o++)
                 if (o == lane) r = acc[o];
             r += d.bias[lane];
             if (lane < d.num_task) r += d.mean[lane];
@@ -319,13 +445,21 @@ const char* gn_apply_launch(const GnApplyDesc& d, cudaStream_t stream)
 {
     if (d.C % 8 != 0) return "gn_apply: C must be a multiple of 8";
     if (d.out_phases != 1 && d.out_phases != 4) return "gn_apply: out_phases must be 1 or 4";
-    if (d.add_kind != 0 && d.out_phases != 1 && d.add_kind != 2) return "gn_apply: residual add needs a same-resolution output";
+    if (d.add_kind == 1 && d.out_phases != 1) return "gn_apply: residual add needs a same-resolution output";
     const long long total = (long long)d.B * d.H * d.W * (d.C / 8);
     if (total == 0) return nullptr;
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)sm_count() * 16;
+    if (total >= (1ll << 31)) return "gn_apply: tensor too large for 32-bit item indices";
+    if (kGnThreads % (d.C / 8) != 0) return "gn_apply: C / 8 must divide 256 (C in {8, 16, ..., 2048} powers of two)";
+    if (d.group_ch & (d.group_ch - 1)) return "gn_apply: channels per group must be a power of two";
+    const int groups = d.group_ch ? d.C / d.group_ch : 0;
+    const size_t smem = (size_t)d.B * groups * sizeof(float2) * (d.add_kind == 2 ? 2 : 1);
+    if (smem > 48 * 1024) return "gn_apply: batch * groups exceeds the 48 KB statistics table";
+    long long blocks = (total + kGnThreads * kGnUnroll - 1) / (kGnThreads * kGnUnroll);
+    const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    gn_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d);
+    if (d.add_kind == 0) gn_apply_kernel<0><<<(unsigned)blocks, kGnThreads, smem, stream>>>(d);
+    else if (d.add_kind == 1) gn_apply_kernel<1><<<(unsigned)blocks, kGnThreads, smem, stream>>>(d);
+    else gn_apply_kernel<2><<<(unsigned)blocks, kGnThreads, smem, stream>>>(d);
     return last_error();
 }
 
@@ -339,7 +473,7 @@ static const char* stem_check(const StemDesc& d)
 const char* stem_stats_launch(const StemDesc& d, cudaStream_t stream)
 {
     if (const char* e = stem_check(d)) return e;
-    int bx = sm_count() * 4 / d.B;
+    int bx = sm_count() * 8 / d.B;
     if (bx < 1) bx = 1;
     stem_kernel<true><<<dim3(bx, d.B), kStemThreads, 0, stream>>>(d);
     return last_error();
@@ -348,7 +482,7 @@ const char* stem_stats_launch(const StemDesc& d, cudaStream_t stream)
 const char* stem_apply_launch(const StemDesc& d, cudaStream_t stream)
 {
     if (const char* e = stem_check(d)) return e;
-    const int segs = d.H * ((d.W + 31) / 32);
+    const int segs = ((d.H + 1) / 2) * ((d.W + 31) / 32);
     int bx = (segs + 7) / 8;
     const int cap = sm_count() * 8 / d.B > 0 ? sm_count() * 8 / d.B : 1;
     if (bx > cap) bx = cap;
@@ -359,15 +493,14 @@ const char* stem_apply_launch(const StemDesc& d, cudaStream_t stream)
 const char* head_launch(const HeadDesc& d, cudaStream_t stream)
 {
     if (d.Co < 1 || d.Co > kHeadMaxCo) return "head: 1..8 output channels";
-    if (d.C % 8 != 0) return "head: C must be a multiple of 8";
-    const size_t smem = (size_t)d.Co * d.C * sizeof(float);
-    if (smem > 48 * 1024) return "head: weights exceed 48 KB of shared memory";
+    if (d.C % 8 != 0 || d.C > kHeadMaxC) return "head: C must be a multiple of 8 and at most 512";
     const long long total = (long long)d.B * d.H * d.W;
     if (total == 0) return nullptr;
     long long blocks = (total + 7) / 8;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    head_kernel<<<(unsigned)blocks, kHeadThreads, smem, stream>>>(d);
+    if (d.Co <= 4) head_kernel<4><<<(unsigned)blocks, kHeadThreads, 0, stream>>>(d);
+    else head_kernel<8><<<(unsigned)blocks, kHeadThreads, 0, stream>>>(d);
     return last_error();
 }
 

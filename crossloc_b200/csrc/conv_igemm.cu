@@ -17,7 +17,8 @@
 //
 // Warp roles (256 threads, one CTA per SM, persistent over output tiles):
 //   warp 0   TMA producer          warp 1   tcgen05.mma issuer       warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld -> scale + bias -> fp32 store + GroupNorm partial sums (fp64 atomics)
+//   warps 4-7 epilogue: tcgen05.ld -> scale + bias -> swizzled smem staging -> TMA store (fp32) + GroupNorm
+//             partial sums (shuffle reduction, fp64 atomics)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -32,6 +33,8 @@ constexpr int kBlockM = 128;
 constexpr int kThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kStageChunkBytes = 32 * 32 * 4;   // one epilogue staging chunk: 32 rows x 32 fp32
+constexpr uint32_t kEpilogueStagingBytes = 4 * 2 * kStageChunkBytes;
 
 // Sums NV per-lane values across the warp with a recursive-halving butterfly (NV - 1 + log2(32 / NV)
 // shuffles per value set).  On return v[0] of lane l holds the total of value index
@@ -128,7 +131,7 @@ __device__ __forceinline__ void stats_chunk(const float (&f)[32], bool valid, in
 template <int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                  const ConvIgemmParams p)
+                  const __grid_constant__ CUtensorMap tmO, const ConvIgemmParams p)
 {
     constexpr int kSwizzle = BK * 2;   // bytes per operand row = swizzle span (128 B or 64 B)
     extern __shared__ uint8_t smem_raw[];
@@ -147,6 +150,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmW);
+        ptx::prefetch_tensormap(&tmO);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.num_stages; s++) {
@@ -236,6 +240,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ------------------------------------------------------------------ epilogue
         const int q = warp & 3;   // TMEM lane quarter this warp may read
         const int plane = p.Hp * p.Wp;
+        // per-warp staging: two 32 x 32 fp32 chunks (4 KB each, 128-byte rows, SWIZZLE_128B) feeding TMA stores
+        const uint32_t stage_base = smem_base + (uint32_t)p.num_stages * p.stage_bytes + (uint32_t)q * 2u * kStageChunkBytes;
+        uint32_t chunk_no = 0;
         int local = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
             const int as = local % p.accum_stages;
@@ -254,7 +261,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            for (int c0 = 0; c0 < p.BN; c0 += 32, chunk_no++) {
                 uint32_t u[32];
                 ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
                 ptx::tmem_ld_wait();
@@ -268,10 +275,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) * p.out_scale + bb.z;
                     f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) * p.out_scale + bb.w;
                 }
-                if (valid) {
-                    float4* o = reinterpret_cast<float4*>(p.raw + (size_t)m * p.Cout + n0 + c0);
+                // the staging buffer used two chunks ago must have been read by its TMA store
+                if (lane == 0) ptx::tma_store_wait_read<1>();
+                __syncwarp();
+                const uint32_t sbuf = stage_base + (chunk_no & 1u) * kStageChunkBytes;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t dst = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                                 "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                                 : "memory");
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    // border rows carry garbage that nothing reads; rows >= Mp are clipped by the TMA unit
+                    ptx::tma_store_2d(&tmO, sbuf, n0 + c0, m0 + q * 32);
+                    ptx::tma_store_commit();
                 }
                 if (p.group_ch) {
                     const int first_group = (n0 + c0) / p.group_ch;
@@ -288,6 +308,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
         }
+        if (lane == 0) ptx::tma_store_wait<0>();   // all output tiles are in global memory before the CTA retires
     }
 
     ptx::tc_fence_before();
@@ -312,20 +333,21 @@ EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-// fp16 row-major [rows][cols] matrix, box = box_rows x box_cols elements, rows zero-filled out of range
+// row-major [rows][cols] matrix of fp16 (elem_bytes 2) or fp32 (4), box = box_rows x box_cols elements whose
+// byte width is the swizzle span; rows out of range are zero-filled on loads and clipped on stores
 bool make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                     uint32_t box_cols)
+                     uint32_t box_cols, uint32_t elem_bytes)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint64_t strides[1] = {cols * elem_bytes};
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    const CUtensorMapSwizzle sw = box_cols * elem_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -361,18 +383,20 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     p.a_bytes = (uint32_t)(kBlockM * BK * 2);
     p.w_bytes = (uint32_t)(BN * BK * 2);
     p.stage_bytes = (uint32_t)nA * (p.a_bytes + p.w_bytes);
-    const int smem_budget = 227 * 1024 - 2048;
+    const int smem_budget = 227 * 1024 - 2048 - (int)kEpilogueStagingBytes;
     p.num_stages = smem_budget / (int)p.stage_bytes;
     if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
     if (p.num_stages < 2) return "conv_igemm: tile does not fit two pipeline stages";
     p.accum_stages = 2 * BN <= (int)kTmemCols ? 2 : 1;
-    const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024;
+    const size_t smem = (size_t)p.num_stages * p.stage_bytes + kEpilogueStagingBytes + 1024;
 
-    CUtensorMap tmA, tmW;
-    if (!make_tensor_map(&tmA, d.act, (uint64_t)d.a_total_rows, (uint64_t)d.Cin, kBlockM, BK))
+    CUtensorMap tmA, tmW, tmO;
+    if (!make_tensor_map(&tmA, d.act, (uint64_t)d.a_total_rows, (uint64_t)d.Cin, kBlockM, BK, 2))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the activation matrix";
-    if (!make_tensor_map(&tmW, d.weights, (uint64_t)(d.nterms == 3 ? 2 : 1) * d.num_taps * d.Cout, (uint64_t)d.Cin, BN, BK))
+    if (!make_tensor_map(&tmW, d.weights, (uint64_t)(d.nterms == 3 ? 2 : 1) * d.num_taps * d.Cout, (uint64_t)d.Cin, BN, BK, 2))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the weight matrix";
+    if (!make_tensor_map(&tmO, d.raw, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 4))
+        return "conv_igemm: cuTensorMapEncodeTiled failed for the output matrix";
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -384,11 +408,11 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     if (BK == 64) {
         e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        conv_igemm_kernel<64><<<grid, kThreads, smem, stream>>>(tmA, tmW, p);
+        conv_igemm_kernel<64><<<grid, kThreads, smem, stream>>>(tmA, tmW, tmO, p);
     } else {
         e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        conv_igemm_kernel<32><<<grid, kThreads, smem, stream>>>(tmA, tmW, p);
+        conv_igemm_kernel<32><<<grid, kThreads, smem, stream>>>(tmA, tmW, tmO, p);
     }
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

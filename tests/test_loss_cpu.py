@@ -1,0 +1,64 @@
+"""CPU suite for loss.coord: the twin vs fixtures produced by the reference implementation."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from crossloc_b200 import synth
+from tests.util import ROOT
+
+CASES = {
+    # name: (batch, uncertainty, reduction, noise, seed)
+    'mle_mean': (3, 'MLE', 'mean', 2.0, 0),
+    'mle_none': (2, 'MLE', None, 30.0, 1),
+    'plain_mean': (2, None, 'mean', 5.0, 2),
+    'far_off': (2, 'MLE', 'mean', 400.0, 3),     # most predictions violate the constraints
+}
+
+
+def pixel_grid(subsample=8):
+    """utils/learning.py:20-35 (vectorised)."""
+    n = -(-1080 // subsample)
+    g = torch.zeros(2, n, n)
+    g[0] = (torch.arange(n) * subsample + subsample / 2)[None, :]
+    g[1] = (torch.arange(n) * subsample + subsample / 2)[:, None]
+    return g
+
+
+def make_inputs(case):
+    batch, uncertainty, reduction, noise, seed = case
+    gen = torch.Generator().manual_seed(seed)
+    coords_l, gt_l, pose_l = [], [], []
+    for i in range(batch):
+        s = synth.make_scene(50 + seed * 10 + i, height=96, width=144, focal=120.0)
+        gt_l.append(torch.from_numpy(s['gt']))
+        pose_l.append(torch.from_numpy(s['pose']).float())
+        coords_l.append(torch.from_numpy(s['coords']) + noise * torch.randn(3, 12, 18, generator=gen))
+    coords = torch.stack(coords_l).requires_grad_(True)
+    unc = (torch.rand(batch, 1, 12, 18, generator=gen) * 20 + 0.5)
+    cam = torch.eye(3)
+    cam[0, 0] = cam[1, 1] = 120.0
+    cam[0, 2], cam[1, 2] = 72.0, 48.0
+    args = (0.1, 100.0, 1000.0, 50.0, uncertainty, pixel_grid(), -1, cam, coords, unc, torch.stack(pose_l),
+            torch.stack(gt_l))
+    return args, {'reduction': reduction}, coords
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_loss_matches_reference_fixture(name):
+    from loss.coord import scene_coords_regression_loss
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'loss_golden.npz'))
+    args, kwargs, coords = make_inputs(CASES[name])
+    loss, rate = scene_coords_regression_loss(*args, **kwargs)
+    loss.sum().backward()
+    assert np.allclose(loss.detach().numpy(), gold[name + '_loss'], rtol=1e-5, atol=1e-6)
+    assert abs(float(rate) - float(gold[name + '_rate'])) < 1e-12
+    assert abs(coords.grad.abs().sum().item() - float(gold[name + '_grad_abs_sum'])) <= 1e-4 * float(gold[name + '_grad_abs_sum']) + 1e-6
+    assert np.allclose(coords.grad.reshape(-1)[::97].numpy(), gold[name + '_grad_sample'], rtol=1e-4, atol=1e-6)
+
+
+def test_get_cam_mat():
+    from loss.coord import get_cam_mat
+    k = get_cam_mat(720, 480, 480.0).cpu()
+    assert k[0, 0] == 480.0 and k[1, 1] == 480.0 and k[0, 2] == 360.0 and k[1, 2] == 240.0 and k[2, 2] == 1.0
