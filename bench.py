@@ -280,8 +280,8 @@ def run_native(args):
                     'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                     'traffic': None, 'peak_source': peak_src, 'avg_launch_ms': avg_ms, 'launches_timed': len(dom),
                     'issued_tflops': achieved * nterms, 'issued_frac': achieved * nterms / peak_tf,
-                    'note': 'achieved counts algorithmic FLOPs (2*pixels*Cout*Cin*9); %s issues %d fp16 MMAs per product' % (
-                        engine.precision, nterms),
+                    'note': 'achieved counts algorithmic FLOPs (2*pixels*Cout*Cin*9); %s issues %d fp16-MMA equivalents per '
+                            'product (fp16+fp8: one fp16 MMA + two e4m3 MMAs at twice the rate)' % (engine.precision, nterms),
                     'all_conv_ms_per_step': conv_total_ms}
 
     # ---- end to end through the public API with host buffers ("e2e")
@@ -319,7 +319,7 @@ def run_native(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f16x3->f32 (conv, fp32-grade split) + f64 (pose solve)', 'data': 'synthetic',
+            'dtype': 'f16+f8 split products -> f32 accumulate (conv) + f64 (pose solve)', 'data': 'synthetic',
             'config': {'workload': 'batch32_480x720_forward+dsac256', 'batch_per_gpu': B, 'hypotheses': args.hyps,
                        'network': 'TransPoseNet enc+2/dec+2, random init seed 2021', 'conv_precision': engine.precision,
                        'parallelism': 'dp%d (images sharded, NCCL all-gather of poses)' % world,

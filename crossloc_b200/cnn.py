@@ -13,21 +13,27 @@ import torch
 
 from . import _lib
 
-# 'fp16x3' (default): every product as three fp16 tensor-core passes, fp32-grade (4e-6 on the coordinate map).
-# 'fp16x1': one pass, 1.1e-3 relative on the coordinate map -- above the 1e-3 parity bar, offered for speed only.
-PRECISION = os.environ.get('CROSSLOC_B200_CONV_PRECISION', 'fp16x3')
+# Convolution arithmetic (CROSSLOC_B200_CONV_PRECISION):
+#   'fp16+fp8' (default)  a_hi*w_hi on the fp16 tensor pipe + the two 2^-11 correction products as e4m3 MMAs for the
+#                         large 3x3 layers (85 % of the FLOPs), fp16x3 elsewhere: 2e-5 relative on the coordinate map
+#   'fp16x3'              every product as three fp16 MMAs: 1e-5 relative
+#   'fp16x1'              one pass: 1.1e-3 relative -- misses the 1e-3 parity bar, offered for speed comparisons only
+PRECISION = os.environ.get('CROSSLOC_B200_CONV_PRECISION', 'fp16+fp8')
+_PRECISIONS = ('fp16+fp8', 'fp16x3', 'fp16x1')
+_W8_LO_SCALE = 4096.0   # csrc/conv.h kW8LoScale
 
 
-def _nterms(precision):
-    if precision == 'fp16x3':
-        return 3
+def _nterms_for(precision, cin, ksize, stride):
+    """MMA scheme of one convolution: 1 = fp16, 2 = fp16 + e4m3 corrections, 3 = fp16x3."""
     if precision == 'fp16x1':
         return 1
-    raise ValueError('unknown conv precision %r (fp16x3 | fp16x1)' % (precision,))
+    if precision == 'fp16+fp8' and ksize == 3 and stride == 1 and cin % 64 == 0 and cin >= 256:
+        return 2
+    return 3
 
 
 class PackedConv:
-    """Weights of one convolution in the tensor-core layout: fp16 [term][tap][Cout][Cin], scaled by a power of two."""
+    """Weights of one convolution in the tensor-core layout: fp16 [term][tap][Cout][Cin] (+ e4m3 planes), scaled by 2^k."""
 
     def __init__(self, weight, bias, stride, nterms):
         cout, cin, kh, kw = weight.shape
@@ -35,16 +41,21 @@ class PackedConv:
         self.cin, self.cout, self.ksize, self.stride, self.nterms = cin, cout, kh, stride, nterms
         w = weight.detach().to(torch.float32)
         amax = float(w.abs().max())
-        # power-of-two pre-scale keeps the fp16 low-order term out of the subnormal range; undone in the epilogue
+        # power-of-two pre-scale keeps the low-order terms inside the fp16 / e4m3 normal ranges; undone in the epilogue
         exp = 0 if amax == 0.0 else int(math.floor(math.log2(128.0 / amax)))
         exp = max(-24, min(24, exp))
         self.out_scale = float(2.0 ** (-exp))
         w = (w * (2.0 ** exp)).permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)   # [tap][Cout][Cin]
         hi = w.to(torch.float16)
+        lo = w - hi.to(torch.float32)
         planes = [hi]
         if nterms == 3:
-            planes.append((w - hi.to(torch.float32)).to(torch.float16))
+            planes.append(lo.to(torch.float16))
         self.weights = torch.stack(planes, 0).contiguous()
+        self.weights8 = None
+        if nterms == 2:
+            self.weights8 = torch.stack([hi.to(torch.float32).to(torch.float8_e4m3fn),
+                                         (lo * _W8_LO_SCALE).to(torch.float8_e4m3fn)], 0).contiguous()
         self.bias = (bias.detach().to(torch.float32) if bias is not None
                      else torch.zeros(cout, dtype=torch.float32, device=weight.device)).contiguous()
 
@@ -57,6 +68,23 @@ class _Geometry:
         self.Hp, self.Wp = h + 2, w + 2
         self.plane = self.Hp * self.Wp
         self.Mp = batch * self.plane
+
+
+class _PF:
+    """One padded-flat activation: fp16 hi/lo planes and, on demand, the e4m3 planes of the fp16 + fp8 mode."""
+
+    def __init__(self, geo, channels, phases, terms, device):
+        self.geo, self.channels, self.phases, self.terms = geo, channels, phases, terms
+        # zero-initialised once: kernels only ever write interior pixels, so the borders stay zero
+        self.h16 = torch.zeros(terms * phases * geo.Mp, channels, dtype=torch.float16, device=device)
+        self._f8 = None
+        self._device = device
+
+    @property
+    def f8(self):
+        if self._f8 is None:
+            self._f8 = torch.zeros(2 * self.phases * self.geo.Mp, self.channels, dtype=torch.uint8, device=self._device)
+        return self._f8
 
 
 def _taps(pack, geo):
@@ -80,19 +108,22 @@ class CoordNetEngine:
 
     def __init__(self, precision=None):
         self.precision = precision or PRECISION
-        self.nterms = _nterms(self.precision)
-        self.terms = 2 if self.nterms == 3 else 1
+        if self.precision not in _PRECISIONS:
+            raise ValueError('unknown conv precision %r (%s)' % (self.precision, ' | '.join(_PRECISIONS)))
+        self.terms = 1 if self.precision == 'fp16x1' else 2
+        self.nterms = {'fp16x1': 1, 'fp16x3': 3, 'fp16+fp8': 2}[self.precision]   # scheme of the dominant 3x3 layers
         self._packs = {}
         self._pack_versions = {}
         self._ws = {}
         self.launches = 0
-        self.events = None   # set to a list to record (layer, flops, start, end) CUDA events around every conv launch
+        self.events = None   # set to a list to record (layer, shape, flops, start, end) CUDA events around every launch
 
     # ------------------------------------------------------------------ parameters
     def _pack(self, name, conv):
         ver = (conv.weight._version, conv.weight.data_ptr(), None if conv.bias is None else conv.bias._version)
         if self._pack_versions.get(name) != ver:
-            self._packs[name] = PackedConv(conv.weight, conv.bias, conv.stride[0], self.nterms)
+            nterms = _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0])
+            self._packs[name] = PackedConv(conv.weight, conv.bias, conv.stride[0], nterms)
             self._pack_versions[name] = ver
         return self._packs[name]
 
@@ -113,12 +144,10 @@ class CoordNetEngine:
         return ws
 
     def _act(self, ws, tag, level, channels, phases):
-        """Zero-initialised fp16 PF buffer [terms][phases][Mp][C]; borders are never written afterwards."""
         key = (tag, level, channels, phases)
         buf = ws['act'].get(key)
         if buf is None:
-            geo = ws['geo'][level]
-            buf = torch.zeros(self.terms * phases * geo.Mp, channels, dtype=torch.float16, device=ws['device'])
+            buf = _PF(ws['geo'][level], channels, phases, self.terms, ws['device'])
             ws['act'][key] = buf
         return buf
 
@@ -145,26 +174,25 @@ class CoordNetEngine:
             e1.record()
             self.events.append((name, shape, flops, e0, e1))
 
-    def _conv(self, stream, pack, act, in_phases, geo, raw, stats, group_ch, name=None):
+    def _conv(self, stream, pack, act, geo, raw, stats, group_ch, name=None):
         taps = _taps(pack, geo)
         tap_arr = (ctypes.c_int32 * len(taps))(*taps)
-        lo_rows = in_phases * geo.Mp
-        if self.events is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+        lo_rows = act.phases * geo.Mp
+        use8 = pack.nterms == 2
+        e0 = self._tick()
         _lib.check(self._lib.cl_conv_igemm(
-            act.data_ptr(), act.size(0), lo_rows, pack.cin, pack.weights.data_ptr(), pack.cout, len(taps), tap_arr,
-            self.nterms, geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale, raw.data_ptr(), pack.bias.data_ptr(),
-            0 if stats is None else stats.data_ptr(), stream))
-        if self.events is not None:
-            e1.record()
-            # algorithmic FLOPs: 2 * (real output pixels) * Cout * Cin * taps (borders and split terms excluded)
-            flops = 2.0 * geo.B * geo.H * geo.W * pack.cout * pack.cin * len(taps)
-            self.events.append((name, (pack.cin, pack.cout, pack.ksize, pack.stride), flops, e0, e1))
+            act.h16.data_ptr(), act.h16.size(0), lo_rows, pack.cin, pack.weights.data_ptr(), pack.cout, len(taps),
+            tap_arr, pack.nterms, geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale, raw.data_ptr(),
+            pack.bias.data_ptr(), 0 if stats is None else stats.data_ptr(),
+            act.f8.data_ptr() if use8 else 0, act.f8.size(0) if use8 else 0, lo_rows if use8 else 0,
+            pack.weights8.data_ptr() if use8 else 0, stream))
+        # algorithmic FLOPs: 2 * (real output pixels) * Cout * Cin * taps (borders and split terms excluded)
+        self._tock(e0, name, (pack.cin, pack.cout, pack.ksize, pack.stride),
+                   2.0 * geo.B * geo.H * geo.W * pack.cout * pack.cin * len(taps))
         self.launches += 1
 
-    def _apply(self, stream, raw, geo, channels, norm, stats, out, out_phases, relu_inner=True, res=None,
-               raw2=None, norm2=None, stats2=None, relu_outer=False):
+    def _apply(self, stream, raw, geo, channels, norm, stats, out, relu_inner=True, res=None, raw2=None, norm2=None,
+               stats2=None, relu_outer=False, want_lo=True, want8=False):
         group_ch = 0 if norm is None else channels // norm.num_groups
         add_kind = 1 if res is not None else (2 if raw2 is not None else 0)
         e0 = self._tick()
@@ -173,11 +201,12 @@ class CoordNetEngine:
             0 if stats is None else stats.data_ptr(),
             0 if norm is None else norm.weight.data_ptr(), 0 if norm is None else norm.bias.data_ptr(),
             1e-5 if norm is None else float(norm.eps), 1 if relu_inner else 0, add_kind,
-            0 if res is None else res.data_ptr(), geo.Mp if self.terms == 2 else 0,
+            0 if res is None else res.h16.data_ptr(), geo.Mp if self.terms == 2 else 0,
             0 if raw2 is None else raw2.data_ptr(), 0 if stats2 is None else stats2.data_ptr(),
             0 if norm2 is None else norm2.weight.data_ptr(), 0 if norm2 is None else norm2.bias.data_ptr(),
-            1 if relu_outer else 0, out.data_ptr(), out_phases, self.terms, stream))
-        self._tock(e0, 'gn_apply', ('gn_apply', channels, out_phases, add_kind), 0.0)
+            1 if relu_outer else 0, out.h16.data_ptr(), out.phases, 2 if (want_lo and self.terms == 2) else 1,
+            out.f8.data_ptr() if want8 else 0, stream))
+        self._tock(e0, 'gn_apply', ('gn_apply', channels, out.phases, add_kind), 0.0)
         self.launches += 1
 
     # ------------------------------------------------------------------ plans
@@ -210,9 +239,25 @@ class CoordNetEngine:
             return s
 
         convs = {name: (conv, norm) for name, conv, norm in layers}
+        packs = {name: self._pack(name, conv) for name, conv, _ in layers if name != 'conv1'}
 
         def groups_of(norm, channels):
             return 0 if norm is None else channels // norm.num_groups
+
+        def planes_for(consumers, also_lo=False):
+            """Which operand planes the consumers of an activation need: (fp16 lo plane, e4m3 planes)."""
+            want8 = any(packs[c].nterms == 2 for c in consumers)
+            want_lo = also_lo or any(packs[c].nterms == 3 for c in consumers)
+            return want_lo, want8
+
+        blocks = spec['blocks']
+
+        def first_conv_of(block_index):
+            """Name(s) of the convolution(s) that read the residual stream entering block `block_index`."""
+            if block_index >= len(blocks):
+                return []
+            blk = blocks[block_index]
+            return [blk['convs'][0]] + ([blk['skip']] if blk['kind'] == 'residual_skip' else [])
 
         # ---- stem: conv1 (+ norm1) + relu, written as the 4-phase input of conv2
         conv1, norm1 = convs['conv1']
@@ -226,23 +271,24 @@ class CoordNetEngine:
             conv1.bias.detach().contiguous().data_ptr(), 1 if norm1 is not None else 0,
             0 if st is None else st.data_ptr(), 0 if norm1 is None else norm1.weight.data_ptr(),
             0 if norm1 is None else norm1.bias.data_ptr(), 1e-5 if norm1 is None else float(norm1.eps),
-            a.data_ptr(), self.terms, stream))
+            a.h16.data_ptr(), self.terms, stream))
         self._tock(e0, 'stem', ('stem',), 2.0 * batch * h * w * 32 * cin * 9)
         self.launches += 2 if norm1 is not None else 1
 
         # ---- strided ladder conv2..conv4
         for level, name in ((1, 'conv2'), (2, 'conv3'), (3, 'conv4')):
             conv, norm = convs[name]
-            pack = self._pack(name, conv)
+            pack = packs[name]
             raw = self._raw(ws, 'ladder', level, pack.cout)
             st = next_stats() if norm is not None else None
-            self._conv(stream, pack, a, 4, geo[level], raw, st, groups_of(norm, pack.cout), name)
+            self._conv(stream, pack, a, geo[level], raw, st, groups_of(norm, pack.cout), name)
             if level < 3:
                 out = self._act(ws, 'ladder', level + 1, pack.cout, 4)
-                self._apply(stream, raw, geo[level], pack.cout, norm, st, out, 4)
+                self._apply(stream, raw, geo[level], pack.cout, norm, st, out)
             else:
                 out = self._act(ws, 'res', 3, pack.cout, 1)
-                self._apply(stream, raw, geo[level], pack.cout, norm, st, out, 1)
+                want_lo, want8 = planes_for(first_conv_of(0), also_lo=True)   # residual stream: always hi + lo
+                self._apply(stream, raw, geo[level], pack.cout, norm, st, out, want_lo=want_lo, want8=want8)
             a = out
         g3 = geo[3]
         res = a
@@ -257,69 +303,65 @@ class CoordNetEngine:
                     return buf
             raise AssertionError
 
-        def conv_block(names, x, res_in, outer_relu):
-            """conv -> [GN] -> relu chain; the last layer merges the residual: out = [relu](res + relu(gn(conv)))."""
+        def chain(names, x, res_in, outer_relu, next_readers, merge_raw2=None):
+            """conv -> [GN] -> relu per layer; the last layer merges the residual stream:
+            out = [relu](res + relu(gn(conv)))  or, with merge_raw2 = (raw, norm, stats), the GroupNorm'ed skip path."""
             for i, name in enumerate(names):
                 conv, norm = convs[name]
-                pack = self._pack(name, conv)
+                pack = packs[name]
                 raw = self._raw(ws, 'r%d' % (i % 2), 3, pack.cout)
                 st = next_stats() if norm is not None else None
-                self._conv(stream, pack, x, 1, g3, raw, st, groups_of(norm, pack.cout), name)
+                self._conv(stream, pack, x, g3, raw, st, groups_of(norm, pack.cout), name)
                 out = scratch(pack.cout, (x, res_in))
                 last = i == len(names) - 1
-                self._apply(stream, raw, g3, pack.cout, norm, st, out, 1, relu_inner=True,
-                            res=res_in if last else None, relu_outer=outer_relu and last)
+                if not last:
+                    want_lo, want8 = planes_for([names[i + 1]])
+                    self._apply(stream, raw, g3, pack.cout, norm, st, out, want_lo=want_lo, want8=want8)
+                else:
+                    want_lo, want8 = planes_for(next_readers, also_lo=True)
+                    if merge_raw2 is None:
+                        self._apply(stream, raw, g3, pack.cout, norm, st, out, res=res_in, relu_outer=outer_relu,
+                                    want_lo=want_lo, want8=want8)
+                    else:
+                        raw_s, snorm, st_s = merge_raw2
+                        self._apply(stream, raw, g3, pack.cout, norm, st, out, raw2=raw_s, norm2=snorm, stats2=st_s,
+                                    relu_outer=outer_relu, want_lo=want_lo, want8=want8)
                 x = out
             return x
 
         outer = gn   # TransPoseNet applies ReLU after every residual add (networks.py:240-254); Network does not (:105-120)
-        for block in spec['blocks']:
+        for bi, block in enumerate(blocks):
             kind = block['kind']
+            readers = first_conv_of(bi + 1)
             if kind == 'residual':
-                res = conv_block(block['convs'], res, res, outer)
+                res = chain(block['convs'], res, res, outer, readers)
             elif kind == 'residual_skip':
                 # x = chain(res); res = skip_norm(skip(res)); res = [relu](res + x)   (networks.py:242-249)
-                names = block['convs']
-                x = res
-                for i, name in enumerate(names[:-1]):
-                    conv, norm = convs[name]
-                    pack = self._pack(name, conv)
-                    raw = self._raw(ws, 'r%d' % (i % 2), 3, pack.cout)
-                    st = next_stats() if norm is not None else None
-                    self._conv(stream, pack, x, 1, g3, raw, st, groups_of(norm, pack.cout), name)
-                    out = scratch(pack.cout, (x, res))
-                    self._apply(stream, raw, g3, pack.cout, norm, st, out, 1)
-                    x = out
-                conv, norm = convs[names[-1]]
-                pack = self._pack(names[-1], conv)
-                raw_x = self._raw(ws, 'r0', 3, pack.cout)
-                st_x = next_stats() if norm is not None else None
-                self._conv(stream, pack, x, 1, g3, raw_x, st_x, groups_of(norm, pack.cout), names[-1])
                 sconv, snorm = convs[block['skip']]
-                spack = self._pack(block['skip'], sconv)
-                raw_s = self._raw(ws, 'r1', 3, spack.cout)
+                spack = packs[block['skip']]
+                raw_s = self._raw(ws, 'rs', 3, spack.cout)
                 st_s = next_stats() if snorm is not None else None
-                self._conv(stream, spack, res, 1, g3, raw_s, st_s, groups_of(snorm, spack.cout), block['skip'])
-                out = scratch(pack.cout, (x, res))
+                self._conv(stream, spack, res, g3, raw_s, st_s, groups_of(snorm, spack.cout), block['skip'])
                 if gn:
-                    self._apply(stream, raw_x, g3, pack.cout, norm, st_x, out, 1, relu_inner=True,
-                                raw2=raw_s, norm2=snorm, stats2=st_s, relu_outer=outer)
+                    res = chain(block['convs'], res, res, outer, readers, merge_raw2=(raw_s, snorm, st_s))
                 else:
                     # vanilla Network: res = skip(res) + relu(conv(x)), no normalisation anywhere
-                    tmp = scratch(pack.cout, (x, res, out))
-                    self._apply(stream, raw_s, g3, spack.cout, None, None, tmp, 1, relu_inner=False)
-                    self._apply(stream, raw_x, g3, pack.cout, None, None, out, 1, relu_inner=True, res=tmp)
-                res = out
+                    skip_pf = scratch(spack.cout, (res,))
+                    self._apply(stream, raw_s, g3, spack.cout, None, None, skip_pf, relu_inner=False)
+                    res = chain(block['convs'], res, skip_pf, outer, readers)
             elif kind == 'plain':
-                # conv -> [GN] -> relu without a residual (fc1, fc2)
-                for name in block['convs']:
+                # conv -> [GN] -> relu without a residual (fc1, fc2); the last output feeds the head (hi + lo)
+                names = block['convs']
+                for i, name in enumerate(names):
                     conv, norm = convs[name]
-                    pack = self._pack(name, conv)
+                    pack = packs[name]
                     raw = self._raw(ws, 'r0', 3, pack.cout)
                     st = next_stats() if norm is not None else None
-                    self._conv(stream, pack, res, 1, g3, raw, st, groups_of(norm, pack.cout), name)
+                    self._conv(stream, pack, res, g3, raw, st, groups_of(norm, pack.cout), name)
                     out = scratch(pack.cout, (res,))
-                    self._apply(stream, raw, g3, pack.cout, norm, st, out, 1)
+                    nxt = [names[i + 1]] if i + 1 < len(names) else readers
+                    want_lo, want8 = planes_for(nxt, also_lo=True)
+                    self._apply(stream, raw, g3, pack.cout, norm, st, out, want_lo=want_lo, want8=want8)
                     res = out
             else:
                 raise AssertionError(kind)
@@ -332,7 +374,7 @@ class CoordNetEngine:
         mean = head['mean'].to(device=dev, dtype=torch.float32).contiguous()
         e0 = self._tick()
         _lib.check(self._lib.cl_head_forward(
-            res.data_ptr(), g3.Mp, self.terms, batch, g3.H, g3.W, hconv.in_channels, co,
+            res.h16.data_ptr(), g3.Mp, self.terms, batch, g3.H, g3.W, hconv.in_channels, co,
             hconv.weight.detach().reshape(co, -1).contiguous().data_ptr(),
             hconv.bias.detach().contiguous().data_ptr(), mean.data_ptr(), head['num_task'],
             head['clamp'][0], head['clamp'][1], out.data_ptr(), stream))

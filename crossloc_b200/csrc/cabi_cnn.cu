@@ -29,10 +29,12 @@ int finish(const char* fn, const char* err)
 extern "C" int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int Cin, const void* weights,
                              int Cout, int num_taps, const int32_t* tap_a_row, int nterms, int Mp, int Hp, int Wp,
                              int group_ch, float out_scale, float* raw, const float* bias, double* stats,
+                             const void* act8, int64_t a8_total_rows, int64_t a8_lo_rows, const void* weights8,
                              void* cuda_stream)
 {
     static const char* kFn = "cl_conv_igemm";
     NEED_DEV(act); NEED_DEV(weights); NEED_DEV(raw); NEED_DEV(bias);
+    if (nterms == 2) { NEED_DEV(act8); NEED_DEV(weights8); }
     if (group_ch) NEED_DEV(stats);
     if (!tap_a_row) return cl::fail(-1, "%s: tap_a_row must not be NULL", kFn);
     if (num_taps < 1 || num_taps > 9) return cl::fail(-1, "%s: num_taps=%d out of range", kFn, num_taps);
@@ -44,6 +46,8 @@ extern "C" int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo
     for (int i = 0; i < num_taps; i++) d.tap_a_row[i] = tap_a_row[i];
     d.nterms = nterms; d.Mp = Mp; d.Hp = Hp; d.Wp = Wp; d.group_ch = group_ch; d.out_scale = out_scale;
     d.raw = raw; d.bias = bias; d.stats = stats;
+    d.act8 = act8; d.a8_total_rows = a8_total_rows; d.a8_lo_rows = a8_lo_rows; d.weights8 = weights8;
+    d.corr_scale = cl::kCorrScale;
     return finish(kFn, cl::conv_igemm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 
@@ -51,7 +55,7 @@ extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int gro
                            const float* gamma, const float* beta, float eps, int relu_inner, int add_kind,
                            const void* res, int64_t res_lo_rows, const float* raw2, const double* stats2,
                            const float* gamma2, const float* beta2, int relu_outer, void* out, int out_phases,
-                           int out_terms, void* cuda_stream)
+                           int out_terms, void* out8, void* cuda_stream)
 {
     static const char* kFn = "cl_gn_apply";
     NEED_DEV(raw); NEED_DEV(out);
@@ -65,7 +69,8 @@ extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int gro
     d.beta = beta; d.eps = eps; d.relu_inner = relu_inner; d.add_kind = add_kind;
     d.res = static_cast<const __half*>(res); d.res_lo_rows = res_lo_rows; d.raw2 = raw2; d.stats2 = stats2;
     d.gamma2 = gamma2; d.beta2 = beta2; d.relu_outer = relu_outer; d.out = static_cast<__half*>(out);
-    d.out_phases = out_phases; d.out_terms = out_terms;
+    d.out_phases = out_phases; d.out_terms = out_terms; d.out8 = static_cast<uint8_t*>(out8);
+    if (out8) NEED_DEV(out8);
     return finish(kFn, cl::gn_apply_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 

@@ -8,6 +8,7 @@
 //   conv1 + norm1 + relu                   :189-190, 231                 -> stem_kernel
 //   fc3, += mean, exp(hardtanh())          :349-358                      -> head_kernel
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include "conv.h"
@@ -38,6 +39,23 @@ __device__ __forceinline__ void split_store8(__half* hi_ptr, __half* lo_ptr, con
     }
     *reinterpret_cast<uint4*>(hi_ptr) = *reinterpret_cast<const uint4*>(h);
     if (write_lo) *reinterpret_cast<uint4*>(lo_ptr) = *reinterpret_cast<const uint4*>(l);
+}
+
+// e4m3 operand planes of the fp16 + fp8 convolution mode: plane 0 = fp8(a_hi * 2^2), plane 1 = fp8((a - a_hi) * 2^14)
+// (power-of-two scales keep both inside e4m3's normal range for activations up to ~50; saturating conversion)
+__device__ __forceinline__ void fp8_store8(uint8_t* hi_ptr, uint8_t* lo_ptr, const float (&v)[8])
+{
+    __align__(8) __nv_fp8x2_storage_t h[4];
+    __align__(8) __nv_fp8x2_storage_t l[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float a0 = __half2float(__float2half_rn(v[2 * j])), a1 = __half2float(__float2half_rn(v[2 * j + 1]));
+        h[j] = __nv_cvt_float2_to_fp8x2(make_float2(a0 * kAct8HiScale, a1 * kAct8HiScale), __NV_SATFINITE, __NV_E4M3);
+        l[j] = __nv_cvt_float2_to_fp8x2(make_float2((v[2 * j] - a0) * kAct8LoScale, (v[2 * j + 1] - a1) * kAct8LoScale),
+                                        __NV_SATFINITE, __NV_E4M3);
+    }
+    *reinterpret_cast<uint2*>(hi_ptr) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo_ptr) = *reinterpret_cast<const uint2*>(l);
 }
 
 // One work item = 8 consecutive channels of one interior pixel; every thread handles kGnUnroll items per
@@ -148,6 +166,7 @@ __device__ __forceinline__ void gn_finish(const GnApplyDesc& d, const GnLane& t,
         olo = (size_t)4 * d.B * oplane;
     }
     split_store8(d.out + orow * d.C + c, d.out + (orow + olo) * d.C + c, v, d.out_terms == 2);
+    if (d.out8) fp8_store8(d.out8 + orow * d.C + c, d.out8 + (orow + olo) * d.C + c, v);
 }
 
 template <int ADD_KIND>
@@ -446,6 +465,7 @@ const char* gn_apply_launch(const GnApplyDesc& d, cudaStream_t stream)
     if (d.C % 8 != 0) return "gn_apply: C must be a multiple of 8";
     if (d.out_phases != 1 && d.out_phases != 4) return "gn_apply: out_phases must be 1 or 4";
     if (d.add_kind == 1 && d.out_phases != 1) return "gn_apply: residual add needs a same-resolution output";
+    if (d.out8 && d.out_phases != 1) return "gn_apply: e4m3 planes are only produced for same-resolution outputs";
     const long long total = (long long)d.B * d.H * d.W * (d.C / 8);
     if (total == 0) return nullptr;
     if (total >= (1ll << 31)) return "gn_apply: tensor too large for 32-bit item indices";

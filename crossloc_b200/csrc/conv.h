@@ -12,6 +12,12 @@
 
 namespace cl {
 
+// power-of-two scales of the e4m3 operand planes (fp16 + fp8 convolution mode)
+constexpr float kAct8HiScale = 4.0f;        // fp8(a_hi * 2^2)
+constexpr float kAct8LoScale = 16384.0f;    // fp8((a - a_hi) * 2^14)
+constexpr float kW8LoScale = 4096.0f;       // fp8(w_lo * 2^12)   (w_hi is stored unscaled)
+constexpr float kCorrScale = 1.0f / 16384.0f;   // both correction products carry 2^14
+
 // ---------------------------------------------------------------- tcgen05 implicit GEMM
 struct ConvIgemmDesc {
     const void* act;        // fp16 PF matrix, all planes
@@ -22,7 +28,11 @@ struct ConvIgemmDesc {
     int Cout;
     int num_taps;
     int tap_a_row[9];       // activation row shift of every tap (phase offset included)
-    int nterms;             // 1 (single fp16 pass) or 3 (fp16x3 split)
+    int nterms;             // 1 (single fp16 pass), 2 (fp16 + e4m3 corrections) or 3 (fp16x3 split)
+    const void* act8;       // nterms == 2: e4m3 PF matrix, plane 0 = fp8(a * 2^2), plane 1 = fp8((a - a_hi) * 2^14)
+    int64_t a8_total_rows, a8_lo_rows;
+    const void* weights8;   // nterms == 2: e4m3 [2][tap][Cout][Cin]: fp8(w_hi), fp8(w_lo * 2^12)
+    float corr_scale;       // 2^-14: scale of the correction accumulator
     int Mp, Hp, Wp;         // output rows (B * Hp * Wp) and padded plane size
     int group_ch;           // GroupNorm channels per group (0: no statistics)
     float out_scale;        // undoes the power-of-two weight pre-scale
@@ -34,7 +44,8 @@ struct ConvIgemmDesc {
 struct ConvIgemmParams {
     int num_taps;
     int tap_a_row[9];
-    int kblocks_per_tap, nterms, a_lo_rows, w_tap_rows, w_lo_rows;
+    int kblocks_per_tap, nterms, a_lo_rows, a8_lo_rows, w_tap_rows, w_lo_rows;
+    float corr_scale;
     int Mp, Cout, BN, tiles_m, tiles_n, Hp, Wp, group_ch, groups;
     float out_scale;
     float* raw;
@@ -68,6 +79,7 @@ struct GnApplyDesc {
     __half* out;            // PF matrix at (H, W) for out_phases == 1, at (ceil(H/2), ceil(W/2)) x 4 phases otherwise
     int out_phases;
     int out_terms;          // 2: write hi and lo, 1: hi only
+    uint8_t* out8;          // nullable: e4m3 planes [2][B*(H+2)*(W+2)][C] for a consumer in fp16 + fp8 mode
 };
 const char* gn_apply_launch(const GnApplyDesc& d, cudaStream_t stream);
 

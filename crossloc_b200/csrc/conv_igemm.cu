@@ -14,6 +14,10 @@
 // Precision.  fp32 parity with the reference (1e-3 relative on the coordinate map) needs more than one
 // fp16/TF32 pass (measured 1.07e-3), so by default each product is evaluated as three fp16
 // MMAs  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  with fp32 accumulation in TMEM ("fp16x3", ~2^-22 relative).
+// The two correction products are 2^-11 of the result, so they only need a few bits: in "fp16+fp8" mode
+// (nterms == 2) they are issued as e4m3 MMAs (kind::f8f6f4, twice the fp16 rate) on power-of-two scaled
+// operands into a second TMEM accumulator and folded in by the epilogue: 2/3 of the tensor work of fp16x3
+// at 2e-5 relative error on the coordinate map (measured).
 //
 // Warp roles (256 threads, one CTA per SM, persistent over output tiles):
 //   warp 0   TMA producer          warp 1   tcgen05.mma issuer       warp 2   TMEM allocator
@@ -131,7 +135,8 @@ __device__ __forceinline__ void stats_chunk(const float (&f)[32], bool valid, in
 template <int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ CUtensorMap tmO, const ConvIgemmParams p)
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA8,
+                  const __grid_constant__ CUtensorMap tmW8, const ConvIgemmParams p)
 {
     constexpr int kSwizzle = BK * 2;   // bytes per operand row = swizzle span (128 B or 64 B)
     extern __shared__ uint8_t smem_raw[];
@@ -143,7 +148,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms need 1 KB alignment
-    const int nA = p.nterms == 3 ? 2 : 1;
+    const int nA = p.nterms == 1 ? 1 : 2;   // 16-bit-equivalent operand tiles per stage (fp16+fp8: hi + two half-size fp8 tiles)
+    const bool f8c = p.nterms == 2;
     const int num_tiles = p.tiles_m * p.tiles_n;
     const int kblocks = p.num_taps * p.kblocks_per_tap;
 
@@ -151,6 +157,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmW);
         ptx::prefetch_tensormap(&tmO);
+        if (f8c) {
+            ptx::prefetch_tensormap(&tmA8);
+            ptx::prefetch_tensormap(&tmW8);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.num_stages; s++) {
@@ -192,7 +202,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         ptx::mbar_expect_tx(bar, tx_bytes);
                         ptx::tma_load_2d(sa, &tmA, bar, kb * BK, a_row);
                         ptx::tma_load_2d(sw, &tmW, bar, kb * BK, w_row);
-                        if (nA == 2) {
+                        if (f8c) {
+                            // e4m3 planes: [0] = hi8, [1] = lo8; tiles are half the bytes of the fp16 ones
+                            ptx::tma_load_2d(sa + p.a_bytes, &tmA8, bar, kb * BK, p.a8_lo_rows + a_row);                 // a_lo8
+                            ptx::tma_load_2d(sa + p.a_bytes + p.a_bytes / 2, &tmA8, bar, kb * BK, a_row);               // a_hi8
+                            ptx::tma_load_2d(sw + p.w_bytes, &tmW8, bar, kb * BK, w_row);                               // w_hi8
+                            ptx::tma_load_2d(sw + p.w_bytes + p.w_bytes / 2, &tmW8, bar, kb * BK, p.w_lo_rows + w_row); // w_lo8
+                        } else if (nA == 2) {
                             ptx::tma_load_2d(sa + p.a_bytes, &tmA, bar, kb * BK, p.a_lo_rows + a_row);
                             ptx::tma_load_2d(sw + p.w_bytes, &tmW, bar, kb * BK, p.w_lo_rows + w_row);
                         }
@@ -218,6 +234,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (lane == 0) {
                     const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                     const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
+                    if (f8c) {
+                        // D1 += a_hi * w_hi (fp16);  D2 += a_lo8 * w_hi8 + a_hi8 * w_lo8 (e4m3, K = 32 per MMA)
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++) {
+                            const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(sa + k * 32);
+                            const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(sw + k * 32);
+                            ptx::mma_f16_ss(tmem_d, da, db, idesc, (kbi | k) != 0 ? 1u : 0u);
+                        }
+                        const uint32_t a8lo = sa + p.a_bytes, a8hi = a8lo + p.a_bytes / 2;
+                        const uint32_t w8hi = sw + p.w_bytes, w8lo = w8hi + p.w_bytes / 2;
+#pragma unroll
+                        for (int k = 0; k < BK / 32; k++) {
+                            const uint64_t da = ptx::make_kmajor_desc<kSwizzle / 2>(a8lo + k * 32);
+                            const uint64_t db = ptx::make_kmajor_desc<kSwizzle / 2>(w8hi + k * 32);
+                            ptx::mma_f8_ss(tmem_d + (uint32_t)p.BN, da, db, idesc, (kbi | k) != 0 ? 1u : 0u);
+                        }
+#pragma unroll
+                        for (int k = 0; k < BK / 32; k++) {
+                            const uint64_t da = ptx::make_kmajor_desc<kSwizzle / 2>(a8hi + k * 32);
+                            const uint64_t db = ptx::make_kmajor_desc<kSwizzle / 2>(w8lo + k * 32);
+                            ptx::mma_f8_ss(tmem_d + (uint32_t)p.BN, da, db, idesc, 1u);
+                        }
+                    } else {
                     // term 0: a_hi * w_hi, term 1: a_lo * w_hi, term 2: a_hi * w_lo
                     for (int term = 0; term < p.nterms; term++) {
                         const uint32_t a_addr = sa + (term == 1 ? p.a_bytes : 0u);
@@ -228,6 +267,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(w_addr + k * 32);
                             ptx::mma_f16_ss(tmem_d, da, db, idesc, (kbi | term | k) != 0 ? 1u : 0u);
                         }
+                    }
                     }
                     ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));          // frees the smem stage
                     if (kbi == kblocks - 1) ptx::mma_commit(ptx::smem_u32(&tfull_bar[as]));   // accumulator ready
@@ -264,7 +304,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int c0 = 0; c0 < p.BN; c0 += 32, chunk_no++) {
                 uint32_t u[32];
                 ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
-                ptx::tmem_ld_wait();
+                if (f8c) {
+                    uint32_t u2[32];
+                    ptx::tmem_ld_32x32(taddr + (uint32_t)(p.BN + c0), u2);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) u[j] = __float_as_uint(fmaf(__uint_as_float(u2[j]), p.corr_scale, __uint_as_float(u[j])));
+                } else {
+                    ptx::tmem_ld_wait();
+                }
                 float f[32];
                 const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
@@ -344,8 +392,11 @@ bool make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
     const cuuint64_t strides[1] = {cols * elem_bytes};
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapSwizzle sw = box_cols * elem_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const uint32_t row_bytes = box_cols * elem_bytes;
+    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                   : (elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
     return fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -357,12 +408,14 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     if (d.Cin % 32 != 0) return "conv_igemm: Cin must be a multiple of 32";
     if (d.Cout % 64 != 0) return "conv_igemm: Cout must be a multiple of 64";
     if (d.num_taps < 1 || d.num_taps > 9) return "conv_igemm: 1..9 taps";
-    if (d.nterms != 1 && d.nterms != 3) return "conv_igemm: nterms must be 1 or 3";
+    if (d.nterms < 1 || d.nterms > 3) return "conv_igemm: nterms must be 1 (fp16), 2 (fp16 + fp8 corrections) or 3 (fp16x3)";
+    if (d.nterms == 2 && (d.Cin % 64 != 0 || !d.act8 || !d.weights8))
+        return "conv_igemm: the fp16 + fp8 mode needs Cin % 64 == 0 and the e4m3 operand planes";
     if (d.group_ch != 0 && d.group_ch != 2 && d.group_ch != 4 && d.group_ch != 8 && d.group_ch != 16)
         return "conv_igemm: GroupNorm group size must be 2, 4, 8 or 16 channels";
     const int BK = d.Cin % 64 == 0 ? 64 : 32;
     const int BN = d.Cout % 256 == 0 ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
-    const int nA = d.nterms == 3 ? 2 : 1;
+    const int nA = d.nterms == 1 ? 1 : 2;
 
     ConvIgemmParams p{};
     p.num_taps = d.num_taps;
@@ -370,6 +423,8 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     p.kblocks_per_tap = d.Cin / BK;
     p.nterms = d.nterms;
     p.a_lo_rows = (int)d.a_lo_rows;
+    p.a8_lo_rows = (int)d.a8_lo_rows;
+    p.corr_scale = d.corr_scale;
     p.w_tap_rows = d.Cout;
     p.w_lo_rows = d.num_taps * d.Cout;
     p.Mp = d.Mp; p.Cout = d.Cout; p.BN = BN;
@@ -387,7 +442,8 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     p.num_stages = smem_budget / (int)p.stage_bytes;
     if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
     if (p.num_stages < 2) return "conv_igemm: tile does not fit two pipeline stages";
-    p.accum_stages = 2 * BN <= (int)kTmemCols ? 2 : 1;
+    // fp16 + fp8 mode keeps two accumulators (main, corrections) per tile
+    p.accum_stages = (d.nterms == 2 ? 4 : 2) * BN <= (int)kTmemCols ? 2 : 1;
     const size_t smem = (size_t)p.num_stages * p.stage_bytes + kEpilogueStagingBytes + 1024;
 
     CUtensorMap tmA, tmW, tmO;
@@ -397,6 +453,13 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
         return "conv_igemm: cuTensorMapEncodeTiled failed for the weight matrix";
     if (!make_tensor_map(&tmO, d.raw, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 4))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the output matrix";
+    CUtensorMap tmA8 = tmA, tmW8 = tmW;
+    if (d.nterms == 2) {
+        if (!make_tensor_map(&tmA8, d.act8, (uint64_t)d.a8_total_rows, (uint64_t)d.Cin, kBlockM, BK, 1))
+            return "conv_igemm: cuTensorMapEncodeTiled failed for the e4m3 activation matrix";
+        if (!make_tensor_map(&tmW8, d.weights8, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin, BN, BK, 1))
+            return "conv_igemm: cuTensorMapEncodeTiled failed for the e4m3 weight matrix";
+    }
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -408,11 +471,11 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     if (BK == 64) {
         e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        conv_igemm_kernel<64><<<grid, kThreads, smem, stream>>>(tmA, tmW, tmO, p);
+        conv_igemm_kernel<64><<<grid, kThreads, smem, stream>>>(tmA, tmW, tmO, tmA8, tmW8, p);
     } else {
         e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        conv_igemm_kernel<32><<<grid, kThreads, smem, stream>>>(tmA, tmW, tmO, p);
+        conv_igemm_kernel<32><<<grid, kThreads, smem, stream>>>(tmA, tmW, tmO, tmA8, tmW8, p);
     }
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

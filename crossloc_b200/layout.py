@@ -33,6 +33,20 @@ def to_pf(x, phases=1, terms=2):
     return torch.cat(out, 0).contiguous()
 
 
+def to_pf8(x, hi_scale=4.0, lo_scale=16384.0):
+    """NCHW fp32 -> e4m3 PF planes (uint8 view) [2 * B * (H+2) * (W+2)][C]: fp8(a_hi * 2^2), fp8((a - a_hi) * 2^14)."""
+    b, c, h, w = x.shape
+    x = x.to(torch.float32)
+    hi = x.to(torch.float16).to(torch.float32)
+    out = []
+    for val in (hi * hi_scale, (x - hi) * lo_scale):
+        q = val.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+        pad = torch.zeros(b, h + 2, w + 2, c, dtype=torch.uint8, device=x.device)
+        pad[:, 1:-1, 1:-1, :] = q.permute(0, 2, 3, 1)
+        out.append(pad.reshape(-1, c))
+    return torch.cat(out, 0).contiguous()
+
+
 def from_pf(buf, batch, h, w, terms=2):
     """fp16 PF matrix (phases = 1) -> NCHW fp32 (hi + lo)."""
     c = buf.size(1)

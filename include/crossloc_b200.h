@@ -82,7 +82,11 @@ int cl_dsac_forward_rgb(const float* coords, int B, int Hc, int Wc, float* out_p
  *   a_lo_rows     row distance between the hi and the lo plane (ignored when nterms == 1)
  *   weights       fp16 [nterms == 3 ? 2 : 1][num_taps][Cout][Cin], pre-scaled by 1 / out_scale
  *   tap_a_row     HOST int32 [num_taps]: activation row shift of each tap (phase offset included)
- *   nterms        1 = one fp16 pass; 3 = fp16x3 split (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo), fp32-grade
+ *   nterms        1 = one fp16 pass; 3 = fp16x3 split (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo), fp32-grade;
+ *                 2 = fp16 + fp8: a_hi*w_hi in fp16, the two correction products as e4m3 MMAs on scaled operands
+ *   act8          nterms == 2 only: e4m3 PF matrix with a8_total_rows rows, plane 0 = fp8(a_hi * 2^2),
+ *                 plane 1 (a8_lo_rows further) = fp8((a - a_hi) * 2^14), as cl_gn_apply writes them
+ *   weights8      nterms == 2 only: e4m3 [2][num_taps][Cout][Cin] = fp8(w_hi), fp8(w_lo * 2^12)
  *   Mp, Hp, Wp    output rows B * Hp * Wp and padded plane size (Hp = H + 2, Wp = W + 2)
  *   group_ch      channels per GroupNorm group for the statistics (0 = none; 2, 4, 8 or 16)
  *   raw           fp32 [Mp][Cout] output (interior rows written), bias fp32 [Cout]
@@ -90,7 +94,8 @@ int cl_dsac_forward_rgb(const float* coords, int B, int Hc, int Wc, float* out_p
  */
 int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int Cin, const void* weights, int Cout,
                   int num_taps, const int32_t* tap_a_row, int nterms, int Mp, int Hp, int Wp, int group_ch,
-                  float out_scale, float* raw, const float* bias, double* stats, void* cuda_stream);
+                  float out_scale, float* raw, const float* bias, double* stats, const void* act8,
+                  int64_t a8_total_rows, int64_t a8_lo_rows, const void* weights8, void* cuda_stream);
 
 /*
  * GroupNorm apply + ReLU + residual merge, fp32 raw -> fp16 hi/lo PF input of the next convolution.
@@ -98,11 +103,12 @@ int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int 
  *   out = relu_outer( add + relu_inner( gn(raw) ) ),  add = 0 | res_hi + res_lo | gn2(raw2)
  *   res_lo_rows: row distance of the residual's lo plane, 0 when it has none (single-pass mode)
  *   out_phases 1: same geometry;  4: the four parity phases at (ceil(H/2), ceil(W/2)).
+ *   out8: nullable e4m3 planes [2][B*(H+2)*(W+2)][C] written alongside (input of an nterms == 2 convolution).
  */
 int cl_gn_apply(const float* raw, int B, int H, int W, int C, int group_ch, const double* stats, const float* gamma,
                 const float* beta, float eps, int relu_inner, int add_kind, const void* res, int64_t res_lo_rows,
                 const float* raw2, const double* stats2, const float* gamma2, const float* beta2, int relu_outer,
-                void* out, int out_phases, int out_terms, void* cuda_stream);
+                void* out, int out_phases, int out_terms, void* out8, void* cuda_stream);
 
 /*
  * Stem: conv3x3 s1 (Cin = 1 or 3 -> 32) + per-channel GroupNorm(32, 32) + ReLU, written as the

@@ -32,11 +32,12 @@ def run_conv(x, conv, nterms, groups):
     b, cin, h, w = x.shape
     stride = conv.stride[0]
     pack = PackedConv(conv.weight, conv.bias, stride, nterms)
-    terms = 2 if nterms == 3 else 1
+    terms = 1 if nterms == 1 else 2
     ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
     geo = _Geometry(b, ho, wo)
     phases = 4 if stride == 2 else 1
     act = layout.to_pf(x, phases=phases, terms=terms)
+    act8 = layout.to_pf8(x) if nterms == 2 else None
     raw = torch.zeros(geo.Mp, pack.cout, dtype=torch.float32, device=DEV)
     group_ch = pack.cout // groups if groups else 0
     stats = torch.zeros(b, max(groups, 1), 2, dtype=torch.float64, device=DEV)
@@ -45,6 +46,8 @@ def run_conv(x, conv, nterms, groups):
     _lib.check(lib.cl_conv_igemm(act.data_ptr(), act.size(0), phases * geo.Mp, cin, pack.weights.data_ptr(), pack.cout,
                                  len(taps), arr, nterms, geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale,
                                  raw.data_ptr(), pack.bias.data_ptr(), stats.data_ptr(),
+                                 act8.data_ptr() if nterms == 2 else 0, act8.size(0) if nterms == 2 else 0,
+                                 geo.Mp if nterms == 2 else 0, pack.weights8.data_ptr() if nterms == 2 else 0,
                                  torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return layout.raw_to_nchw(raw, b, ho, wo), stats
@@ -81,6 +84,25 @@ def test_conv_igemm_matches_torch(shape, nterms):
     assert torch.allclose(stats[:, :, 1], (g * g).sum(-1), rtol=5e-3 if nterms == 1 else 1e-4)
 
 
+@pytest.mark.parametrize('shape', [(256, 256, 3, 1, 2, 9, 14), (512, 512, 3, 1, 1, 60, 90), (256, 512, 3, 1, 3, 7, 5),
+                                   (512, 512, 1, 1, 2, 9, 14)])
+def test_conv_igemm_fp16_plus_fp8_corrections(shape):
+    """nterms == 2: a_hi*w_hi in fp16, both correction products as e4m3 MMAs into a second TMEM accumulator."""
+    cin, cout, k, stride, b, h, w = shape
+    torch.manual_seed(cin + cout + k)
+    conv = torch.nn.Conv2d(cin, cout, k, stride, k // 2).to(DEV)
+    x = (torch.randn(b, cin, h, w, device=DEV) * 1.5).relu()
+    with torch.no_grad():
+        ref = conv(x)
+    out, stats = run_conv(x, conv, 2, 32)
+    err = rel_l2(out, ref)
+    assert err < 1e-4, err          # 2^-11 corrections carried with ~4 bits: ~3e-5
+    one, _ = run_conv(x, conv, 1, 32)
+    assert err < 0.2 * rel_l2(one, ref)   # and clearly better than a single fp16 pass
+    g = ref.double().reshape(b, 32, -1)
+    assert torch.allclose(stats[:, :, 1], (g * g).sum(-1), rtol=1e-3)
+
+
 def test_gn_apply_variants():
     lib = _lib.load()
     b, c, h, w = 2, 256, 9, 13
@@ -109,13 +131,28 @@ def test_gn_apply_variants():
     def run(phases, add_kind, relu_outer):
         ho, wo = ((h + 1) // 2, (w + 1) // 2) if phases == 4 else (h, w)
         out = torch.zeros(2 * phases * b * (ho + 2) * (wo + 2), c, dtype=torch.float16, device=DEV)
+        out8 = torch.zeros(2 * b * (h + 2) * (w + 2), c, dtype=torch.uint8, device=DEV)
         res_pf = layout.to_pf(res)
         r1, r2, s1, s2 = raw_of(x), raw_of(x2), stats_of(x), stats_of(x2)
         _lib.check(lib.cl_gn_apply(r1.data_ptr(), b, h, w, c, c // 32, s1.data_ptr(), gn.weight.data_ptr(),
                                    gn.bias.data_ptr(), 1e-5, 1, add_kind, res_pf.data_ptr(), geo.Mp, r2.data_ptr(),
                                    s2.data_ptr(), gn2.weight.data_ptr(), gn2.bias.data_ptr(), relu_outer,
-                                   out.data_ptr(), phases, 2, torch.cuda.current_stream().cuda_stream))
+                                   out.data_ptr(), phases, 2, out8.data_ptr() if phases == 1 else 0,
+                                   torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
+        if phases == 1:
+            # the e4m3 planes written alongside decode to the fp16 result: hi8 / 2^2 ~ a (3 mantissa bits),
+            # lo8 / 2^14 ~ a - fp16(a)
+            val = layout.from_pf(out, b, h, w)
+            rows = b * (h + 2) * (w + 2)
+            dec = out8.view(torch.float8_e4m3fn).to(torch.float32)
+            hi8 = layout.raw_to_nchw(dec[:rows].contiguous(), b, h, w) / 4.0
+            lo8 = layout.raw_to_nchw(dec[rows:].contiguous(), b, h, w) / 16384.0
+            hi16 = val.to(torch.float16).to(torch.float32)
+            assert float((hi8 - hi16).abs().max()) <= float(hi16.abs().max()) * 2.0 ** -4 + 2.0 ** -11
+            # (fp16 rounding ties can flip between the device's exact fp32 value and the reconstructed hi + lo: quantile)
+            lo_err = (lo8 - (val - hi16)).abs().flatten()
+            assert float(torch.quantile(lo_err[:1000000], 0.999)) <= float(val.abs().max()) * 2.0 ** -11 * 2.0 ** -3
         return layout.from_pf(out, b, h, w) if phases == 1 else layout.from_pf_phases(out, b, h, w)
 
     with torch.no_grad():
@@ -186,7 +223,7 @@ def test_network_matches_reference_fixture_and_torch(name):
     assert rel_l2(out[:, :k], ref[:, :k]) < 1e-3          # north-star tolerance: 1e-3 relative fp32
     assert rel_l2(out[:, :k], gold[:, :k]) < 1e-3
     assert rel_l2(out, gold) < 1e-3
-    assert rel_l2(out[:, :k], gold[:, :k]) < 5e-5          # what fp16x3 actually delivers
+    assert rel_l2(out[:, :k], gold[:, :k]) < 1e-4          # what the default fp16 + fp8 scheme actually delivers
     assert float((out[:, :k] - gold[:, :k]).abs().max() / gold[:, :k].abs().max()) < 1e-3
 
 
@@ -208,18 +245,20 @@ def test_network_full_resolution_parity_and_determinism():
     # batch entries are independent: image 1 alone gives the same map
     with torch.no_grad():
         single = net(x[1:2])
-    assert rel_l2(single, out[1:2]) < 1e-6
+    assert rel_l2(single, out[1:2]) < 2e-5   # e4m3 rounding of the correction operands amplifies last-bit statistics noise
 
 
-def test_single_pass_precision_is_reported_not_hidden():
-    """fp16x1 is a speed mode that misses the 1e-3 bar by design; make sure the knob does what it says."""
+def test_precision_modes():
+    """fp16x3 and the default fp16+fp8 meet the bar with margin; fp16x1 is a speed mode that misses it by design."""
     import networks.networks as nets
     torch.manual_seed(2021)
     net = nets.TransPoseNet(torch.zeros(3), False, False, 2, 2, 3, 1).eval().to(DEV)
     x = torch.rand(1, 3, 96, 128, generator=torch.Generator().manual_seed(0)).to(DEV)
-    eng = CoordNetEngine(precision='fp16x1')
+    errs = {}
     with torch.no_grad():
-        fast = eng.forward(net._spec(), x)
         ref = net.forward_reference(x)
-    err = rel_l2(fast[:, :3], ref[:, :3])
-    assert 1e-5 < err < 1e-2
+        for prec in ('fp16x3', 'fp16+fp8', 'fp16x1'):
+            out = CoordNetEngine(precision=prec).forward(net._spec(), x)
+            errs[prec] = rel_l2(out[:, :3], ref[:, :3])
+    assert errs['fp16x3'] < 5e-5 and errs['fp16+fp8'] < 2e-4
+    assert 1e-4 < errs['fp16x1'] < 1e-2
