@@ -1,6 +1,8 @@
 // extern "C" entry points of the CNN operators declared in include/crossloc_b200.h.
 #include "../../include/crossloc_b200.h"
 
+#include <cstdlib>
+
 #include "cabi_common.h"
 #include "conv.h"
 
@@ -48,6 +50,10 @@ extern "C" int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo
     d.raw = raw; d.bias = bias; d.stats = stats;
     d.act8 = act8; d.a8_total_rows = a8_total_rows; d.a8_lo_rows = a8_lo_rows; d.weights8 = weights8;
     d.corr_scale = cl::kCorrScale;
+    {
+        const char* env = getenv("CROSSLOC_B200_CONV_CLUSTER");   // tuning knob: 1, 2 or 4 CTAs share a weight tile
+        d.cluster = env ? atoi(env) : 0;
+    }
     return finish(kFn, cl::conv_igemm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 

@@ -33,6 +33,7 @@ struct ConvIgemmDesc {
     int64_t a8_total_rows, a8_lo_rows;
     const void* weights8;   // nterms == 2: e4m3 [2][tap][Cout][Cin]: fp8(w_hi), fp8(w_lo * 2^12)
     float corr_scale;       // 2^-14: scale of the correction accumulator
+    int cluster;            // CTAs sharing a weight tile by TMA multicast (0 = default 2; 1, 2 or 4)
     int Mp, Hp, Wp;         // output rows (B * Hp * Wp) and padded plane size
     int group_ch;           // GroupNorm channels per group (0: no statistics)
     float out_scale;        // undoes the power-of-two weight pre-scale
@@ -47,6 +48,7 @@ struct ConvIgemmParams {
     int kblocks_per_tap, nterms, a_lo_rows, a8_lo_rows, w_tap_rows, w_lo_rows;
     float corr_scale;
     int Mp, Cout, BN, tiles_m, tiles_n, Hp, Wp, group_ch, groups;
+    int cluster, super_m;
     float out_scale;
     float* raw;
     const float* bias;

@@ -19,6 +19,12 @@
 // operands into a second TMEM accumulator and folded in by the epilogue: 2/3 of the tensor work of fp16x3
 // at 2e-5 relative error on the coordinate map (measured).
 //
+// L2 traffic.  A 128 x 256 tile needs 96 KB of operands per 64-wide K block, two thirds of it weights; at full
+// tensor rate that is more than the L2 can deliver to 148 SMs (measured: 12-13 TB/s).  CTAs are therefore
+// launched as clusters of `cluster` (2 or 4): the CTAs of a cluster work on consecutive pixel tiles of the same
+// output-channel tile, each loads 1/cluster of the weight tile and TMA-multicasts it to its peers.  A stage is
+// released to the producers only when every CTA of the cluster has consumed it (tcgen05.commit multicast).
+//
 // Warp roles (256 threads, one CTA per SM, persistent over output tiles):
 //   warp 0   TMA producer          warp 1   tcgen05.mma issuer       warp 2   TMEM allocator
 //   warps 4-7 epilogue: tcgen05.ld -> scale + bias -> swizzled smem staging -> TMA store (fp32) + GroupNorm
@@ -150,7 +156,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms need 1 KB alignment
     const int nA = p.nterms == 1 ? 1 : 2;   // 16-bit-equivalent operand tiles per stage (fp16+fp8: hi + two half-size fp8 tiles)
     const bool f8c = p.nterms == 2;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    // cluster geometry: rank r of cluster c handles pixel tile (super_m * cluster + r) of super-tile list entry c, c + n, ...
+    const int cs = p.cluster;
+    const uint32_t crank = cs > 1 ? ptx::cluster_ctarank() : 0u;
+    const int cluster_id = cs > 1 ? (int)ptx::cluster_id_x() : (int)blockIdx.x;
+    const int num_clusters = cs > 1 ? (int)ptx::cluster_count_x() : (int)gridDim.x;
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+    const int num_tiles = p.super_m * p.tiles_n;   // super-tiles: `cluster` consecutive pixel tiles x one channel tile
     const int kblocks = p.num_taps * p.kblocks_per_tap;
 
     if (warp == 0 && lane == 0) {
@@ -165,7 +177,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.num_stages; s++) {
             ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
-            ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), (uint32_t)cs);   // every CTA of the cluster releases the stage
         }
         for (int s = 0; s < 2; s++) {
             ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
@@ -179,6 +191,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (cs > 1) ptx::cluster_sync();   // peers' barriers are initialised before anything is multicast to them
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
@@ -188,8 +201,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = (uint32_t)nA * (p.a_bytes + p.w_bytes);
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.tiles_n) * kBlockM;
+            const int w_slice_rows = p.BN / cs;                      // rows of the weight tile this CTA fetches
+            const uint32_t w_slice_off = crank * (p.w_bytes / (uint32_t)cs);
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = ((tile / p.tiles_n) * cs + (int)crank) * kBlockM;
                 const int n0 = (tile % p.tiles_n) * p.BN;
                 for (int tap = 0; tap < p.num_taps; tap++) {
                     const int a_row = p.tap_a_row[tap] + m0;
@@ -201,16 +216,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
                         ptx::mbar_expect_tx(bar, tx_bytes);
                         ptx::tma_load_2d(sa, &tmA, bar, kb * BK, a_row);
-                        ptx::tma_load_2d(sw, &tmW, bar, kb * BK, w_row);
+                        const int wr = w_row + (int)crank * w_slice_rows;   // this CTA's slice of the weight tile
+                        if (cs == 1) {
+                            ptx::tma_load_2d(sw, &tmW, bar, kb * BK, wr);
+                        } else {
+                            ptx::tma_load_2d_multicast(sw + w_slice_off, &tmW, bar, kb * BK, wr, cmask);
+                        }
                         if (f8c) {
                             // e4m3 planes: [0] = hi8, [1] = lo8; tiles are half the bytes of the fp16 ones
                             ptx::tma_load_2d(sa + p.a_bytes, &tmA8, bar, kb * BK, p.a8_lo_rows + a_row);                 // a_lo8
                             ptx::tma_load_2d(sa + p.a_bytes + p.a_bytes / 2, &tmA8, bar, kb * BK, a_row);               // a_hi8
-                            ptx::tma_load_2d(sw + p.w_bytes, &tmW8, bar, kb * BK, w_row);                               // w_hi8
-                            ptx::tma_load_2d(sw + p.w_bytes + p.w_bytes / 2, &tmW8, bar, kb * BK, p.w_lo_rows + w_row); // w_lo8
+                            const uint32_t w8hi = sw + p.w_bytes, w8lo = w8hi + p.w_bytes / 2;
+                            if (cs == 1) {
+                                ptx::tma_load_2d(w8hi, &tmW8, bar, kb * BK, wr);                 // w_hi8
+                                ptx::tma_load_2d(w8lo, &tmW8, bar, kb * BK, p.w_lo_rows + wr);   // w_lo8
+                            } else {
+                                ptx::tma_load_2d_multicast(w8hi + w_slice_off / 2, &tmW8, bar, kb * BK, wr, cmask);
+                                ptx::tma_load_2d_multicast(w8lo + w_slice_off / 2, &tmW8, bar, kb * BK, p.w_lo_rows + wr, cmask);
+                            }
                         } else if (nA == 2) {
                             ptx::tma_load_2d(sa + p.a_bytes, &tmA, bar, kb * BK, p.a_lo_rows + a_row);
-                            ptx::tma_load_2d(sw + p.w_bytes, &tmW, bar, kb * BK, p.w_lo_rows + w_row);
+                            if (cs == 1) {
+                                ptx::tma_load_2d(sw + p.w_bytes, &tmW, bar, kb * BK, p.w_lo_rows + wr);
+                            } else {
+                                ptx::tma_load_2d_multicast(sw + p.w_bytes + w_slice_off, &tmW, bar, kb * BK, p.w_lo_rows + wr, cmask);
+                            }
                         }
                         if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                     }
@@ -222,7 +252,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t idesc = ptx::make_idesc_f16(kBlockM, p.BN);
         int stage = 0, local = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
             const int as = local % p.accum_stages;
             const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
             ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aphase ^ 1u);   // epilogue has drained this accumulator
@@ -269,7 +299,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                     }
-                    ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));          // frees the smem stage
+                    // frees the smem stage -- in every CTA of the cluster, whose multicast loads also fill it
+                    if (cs == 1) ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));
+                    else ptx::mma_commit_multicast(ptx::smem_u32(&empty_bar[stage]), cmask);
                     if (kbi == kblocks - 1) ptx::mma_commit(ptx::smem_u32(&tfull_bar[as]));   // accumulator ready
                 }
                 __syncwarp();
@@ -284,10 +316,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t stage_base = smem_base + (uint32_t)p.num_stages * p.stage_bytes + (uint32_t)q * 2u * kStageChunkBytes;
         uint32_t chunk_no = 0;
         int local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
             const int as = local % p.accum_stages;
             const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
-            const int m0 = (tile / p.tiles_n) * kBlockM;
+            const int m0 = ((tile / p.tiles_n) * cs + (int)crank) * kBlockM;
             const int n0 = (tile % p.tiles_n) * p.BN;
             const int m = m0 + q * 32 + lane;
             int image = 0;
@@ -361,6 +393,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (cs > 1) ptx::cluster_sync();   // no CTA retires while a peer may still multicast into it or signal its barriers
     if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -430,6 +463,14 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     p.Mp = d.Mp; p.Cout = d.Cout; p.BN = BN;
     p.tiles_m = (d.Mp + kBlockM - 1) / kBlockM;
     p.tiles_n = d.Cout / BN;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // cluster size: weights are shared by `cluster` CTAs (TMA multicast); needs enough pixel tiles to fill the chip
+    int cluster = d.cluster > 0 ? d.cluster : 2;
+    while (cluster > 1 && (p.tiles_m < cluster * 8 || sms % cluster != 0 || BN % (cluster * 8) != 0)) cluster >>= 1;
+    p.cluster = cluster;
+    p.super_m = (p.tiles_m + cluster - 1) / cluster;
     p.Hp = d.Hp; p.Wp = d.Wp;
     p.group_ch = d.group_ch;
     p.groups = d.group_ch ? d.Cout / d.group_ch : 0;
@@ -449,7 +490,7 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     CUtensorMap tmA, tmW, tmO;
     if (!make_tensor_map(&tmA, d.act, (uint64_t)d.a_total_rows, (uint64_t)d.Cin, kBlockM, BK, 2))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the activation matrix";
-    if (!make_tensor_map(&tmW, d.weights, (uint64_t)(d.nterms == 3 ? 2 : 1) * d.num_taps * d.Cout, (uint64_t)d.Cin, BN, BK, 2))
+    if (!make_tensor_map(&tmW, d.weights, (uint64_t)(d.nterms == 3 ? 2 : 1) * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, BK, 2))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the weight matrix";
     if (!make_tensor_map(&tmO, d.raw, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 4))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the output matrix";
@@ -457,26 +498,39 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     if (d.nterms == 2) {
         if (!make_tensor_map(&tmA8, d.act8, (uint64_t)d.a8_total_rows, (uint64_t)d.Cin, kBlockM, BK, 1))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the e4m3 activation matrix";
-        if (!make_tensor_map(&tmW8, d.weights8, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin, BN, BK, 1))
+        if (!make_tensor_map(&tmW8, d.weights8, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, BK, 1))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the e4m3 weight matrix";
     }
 
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int num_tiles = p.tiles_m * p.tiles_n;
-    const int grid = num_tiles < sms ? num_tiles : sms;
+    const int num_super = p.super_m * p.tiles_n;
+    int clusters = sms / cluster;
+    if (clusters > num_super) clusters = num_super;
+    const int grid = clusters * cluster;
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
 
     cudaError_t e;
     if (BK == 64) {
         e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        conv_igemm_kernel<64><<<grid, kThreads, smem, stream>>>(tmA, tmW, tmO, tmA8, tmW8, p);
+        e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<64>, tmA, tmW, tmO, tmA8, tmW8, p);
     } else {
         e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        conv_igemm_kernel<32><<<grid, kThreads, smem, stream>>>(tmA, tmW, tmO, tmA8, tmW8, p);
+        e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<32>, tmA, tmW, tmO, tmA8, tmW8, p);
     }
+    if (e != cudaSuccess) return cudaGetErrorString(e);
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
