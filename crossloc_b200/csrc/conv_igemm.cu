@@ -138,6 +138,65 @@ __device__ __forceinline__ void stats_chunk(const float (&f)[32], bool valid, in
     }
 }
 
+// Epilogue of one 128 x BN tile for one warp (32 accumulator rows): TMEM -> registers -> (+ corrections) x scale
+// + bias -> swizzled smem staging -> TMA store, plus the GroupNorm partial sums of the interior rows.
+__device__ __forceinline__ void epilogue_tile(const ConvIgemmParams& p, const CUtensorMap* tmO, uint32_t taddr, int m0,
+                                              int n0, int q, int lane, uint32_t stage_base, uint32_t& chunk_no, bool f8c,
+                                              bool valid, int image)
+{
+            for (int c0 = 0; c0 < p.BN; c0 += 32, chunk_no++) {
+                uint32_t u[32];
+                ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
+                if (f8c) {
+                    uint32_t u2[32];
+                    ptx::tmem_ld_32x32(taddr + (uint32_t)(p.BN + c0), u2);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) u[j] = __float_as_uint(fmaf(__uint_as_float(u2[j]), p.corr_scale, __uint_as_float(u[j])));
+                } else {
+                    ptx::tmem_ld_wait();
+                }
+                float f[32];
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 bb = __ldg(b4 + j);
+                    f[4 * j + 0] = __uint_as_float(u[4 * j + 0]) * p.out_scale + bb.x;
+                    f[4 * j + 1] = __uint_as_float(u[4 * j + 1]) * p.out_scale + bb.y;
+                    f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) * p.out_scale + bb.z;
+                    f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) * p.out_scale + bb.w;
+                }
+                // the staging buffer used two chunks ago must have been read by its TMA store
+                if (lane == 0) ptx::tma_store_wait_read<1>();
+                __syncwarp();
+                const uint32_t sbuf = stage_base + (chunk_no & 1u) * kStageChunkBytes;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t dst = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                                 "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                                 : "memory");
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    // border rows carry garbage that nothing reads; rows >= Mp are clipped by the TMA unit
+                    ptx::tma_store_2d(tmO, sbuf, n0 + c0, m0 + q * 32);
+                    ptx::tma_store_commit();
+                }
+                if (p.group_ch) {
+                    const int first_group = (n0 + c0) / p.group_ch;
+                    switch (p.group_ch) {
+                        case 2: stats_chunk<2>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 4: stats_chunk<4>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 8: stats_chunk<8>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 16: stats_chunk<16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        default: break;
+                    }
+                }
+            }
+}
+
 template <int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -333,57 +392,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
-            for (int c0 = 0; c0 < p.BN; c0 += 32, chunk_no++) {
-                uint32_t u[32];
-                ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
-                if (f8c) {
-                    uint32_t u2[32];
-                    ptx::tmem_ld_32x32(taddr + (uint32_t)(p.BN + c0), u2);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j++) u[j] = __float_as_uint(fmaf(__uint_as_float(u2[j]), p.corr_scale, __uint_as_float(u[j])));
-                } else {
-                    ptx::tmem_ld_wait();
-                }
-                float f[32];
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 bb = __ldg(b4 + j);
-                    f[4 * j + 0] = __uint_as_float(u[4 * j + 0]) * p.out_scale + bb.x;
-                    f[4 * j + 1] = __uint_as_float(u[4 * j + 1]) * p.out_scale + bb.y;
-                    f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) * p.out_scale + bb.z;
-                    f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) * p.out_scale + bb.w;
-                }
-                // the staging buffer used two chunks ago must have been read by its TMA store
-                if (lane == 0) ptx::tma_store_wait_read<1>();
-                __syncwarp();
-                const uint32_t sbuf = stage_base + (chunk_no & 1u) * kStageChunkBytes;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t dst = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "f"(f[4 * j]), "f"(f[4 * j + 1]),
-                                 "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
-                                 : "memory");
-                }
-                ptx::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    // border rows carry garbage that nothing reads; rows >= Mp are clipped by the TMA unit
-                    ptx::tma_store_2d(&tmO, sbuf, n0 + c0, m0 + q * 32);
-                    ptx::tma_store_commit();
-                }
-                if (p.group_ch) {
-                    const int first_group = (n0 + c0) / p.group_ch;
-                    switch (p.group_ch) {
-                        case 2: stats_chunk<2>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        case 4: stats_chunk<4>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        case 8: stats_chunk<8>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        case 16: stats_chunk<16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        default: break;
-                    }
-                }
-            }
+            epilogue_tile(p, &tmO, taddr, m0, n0, q, lane, stage_base, chunk_no, f8c, valid, image);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
@@ -395,6 +404,207 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     if (cs > 1) ptx::cluster_sync();   // no CTA retires while a peer may still multicast into it or signal its barriers
     if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2).  In the single-CTA kernel every 128 x 256 x 16 MMA reads 12 KB of
+// operands from shared memory in 128 cycles while TMA writes the next stage: more than the 128 B/clk an SM's
+// shared memory delivers, so the tensor pipe starves (measured: 1.75 ms where the MMA count needs 1.2 ms).
+// Here two CTAs form one 256 x 256 tile: each keeps its own 128 pixel rows and only HALF of the weight tile,
+// the MMA unit of the pair reads the other half from the peer.  Per CTA and stage: half the weight bytes from
+// L2, 8 KB instead of 12 KB of smem reads per MMA, three pipeline stages instead of two.
+// Protocol (leader = even CTA of the pair): both CTAs' producers load with the 2-SM TMA form that signals the
+// LEADER's full barrier; the leader's MMA warp issues for the pair and releases stages / publishes accumulators
+// with tcgen05.commit multicast to both CTAs; both epilogues signal the leader's accumulator-empty barrier.
+template <int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA8,
+                       const __grid_constant__ CUtensorMap tmW8, const ConvIgemmParams p)
+{
+    constexpr int kSwizzle = BK * 2;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int nA = p.nterms == 1 ? 1 : 2;
+    const bool f8c = p.nterms == 2;
+    const uint32_t crank = ptx::cluster_ctarank();
+    const bool leader = crank == 0;
+    const int cluster_id = (int)ptx::cluster_id_x();
+    const int num_clusters = (int)ptx::cluster_count_x();
+    const int num_tiles = p.super_m * p.tiles_n;
+    const int kblocks = p.num_taps * p.kblocks_per_tap;
+    const uint32_t w_half = p.w_bytes / 2;   // this CTA's half of the weight tile (BN / 2 rows)
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmW);
+        ptx::prefetch_tensormap(&tmO);
+        if (f8c) {
+            ptx::prefetch_tensormap(&tmA8);
+            ptx::prefetch_tensormap(&tmW8);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.num_stages; s++) {
+            ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);    // leader's producer arms it; both CTAs' TMA complete_tx
+            ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);   // the leader's MMA commit, multicast to both CTAs
+        }
+        for (int s = 0; s < 2; s++) {
+            ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);   // MMA commit, multicast to both CTAs
+            ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 8);  // leader only: 4 epilogue warps of each CTA
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc_pair(ptx::smem_u32(&tmem_base_s), kTmemCols);
+        ptx::tmem_relinquish_pair();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_pair = 2u * (uint32_t)nA * (p.a_bytes + w_half);
+            const int w_rows = p.BN / 2;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+                const int n0 = (tile % p.tiles_n) * p.BN;
+                for (int tap = 0; tap < p.num_taps; tap++) {
+                    const int a_row = p.tap_a_row[tap] + m0;
+                    const int w_row = tap * p.w_tap_rows + n0 + (int)crank * w_rows;
+                    for (int kb = 0; kb < p.kblocks_per_tap; kb++) {
+                        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                        const uint32_t bar = ptx::smem_u32(&full_bar[stage]);   // resolved to the leader's copy by the load
+                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
+                        if (leader) ptx::mbar_expect_tx(bar, tx_pair);
+                        ptx::tma_load_2d_pair(sa, &tmA, bar, kb * BK, a_row);
+                        ptx::tma_load_2d_pair(sw, &tmW, bar, kb * BK, w_row);
+                        if (f8c) {
+                            ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA8, bar, kb * BK, p.a8_lo_rows + a_row);         // a_lo8
+                            ptx::tma_load_2d_pair(sa + p.a_bytes + p.a_bytes / 2, &tmA8, bar, kb * BK, a_row);       // a_hi8
+                            ptx::tma_load_2d_pair(sw + w_half, &tmW8, bar, kb * BK, w_row);                          // w_hi8
+                            ptx::tma_load_2d_pair(sw + w_half + w_half / 2, &tmW8, bar, kb * BK, p.w_lo_rows + w_row); // w_lo8
+                        } else if (nA == 2) {
+                            ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA, bar, kb * BK, p.a_lo_rows + a_row);
+                            ptx::tma_load_2d_pair(sw + w_half, &tmW, bar, kb * BK, p.w_lo_rows + w_row);
+                        }
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint32_t idesc = ptx::make_idesc_f16(2 * kBlockM, p.BN);
+            int stage = 0, local = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
+                const int as = local % p.accum_stages;
+                const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
+                ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aphase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.BN);
+                for (int kbi = 0; kbi < kblocks; kbi++) {
+                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                    ptx::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
+                        if (f8c) {
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++) {
+                                const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(sa + k * 32);
+                                const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(sw + k * 32);
+                                ptx::mma_f16_ss_pair(tmem_d, da, db, idesc, (kbi | k) != 0 ? 1u : 0u);
+                            }
+                            const uint32_t a8lo = sa + p.a_bytes, a8hi = a8lo + p.a_bytes / 2;
+                            const uint32_t w8hi = sw + w_half, w8lo = w8hi + w_half / 2;
+#pragma unroll
+                            for (int k = 0; k < BK / 32; k++) {
+                                const uint64_t da = ptx::make_kmajor_desc<kSwizzle / 2>(a8lo + k * 32);
+                                const uint64_t db = ptx::make_kmajor_desc<kSwizzle / 2>(w8hi + k * 32);
+                                ptx::mma_f8_ss_pair(tmem_d + (uint32_t)p.BN, da, db, idesc, (kbi | k) != 0 ? 1u : 0u);
+                            }
+#pragma unroll
+                            for (int k = 0; k < BK / 32; k++) {
+                                const uint64_t da = ptx::make_kmajor_desc<kSwizzle / 2>(a8hi + k * 32);
+                                const uint64_t db = ptx::make_kmajor_desc<kSwizzle / 2>(w8lo + k * 32);
+                                ptx::mma_f8_ss_pair(tmem_d + (uint32_t)p.BN, da, db, idesc, 1u);
+                            }
+                        } else {
+                            for (int term = 0; term < p.nterms; term++) {
+                                const uint32_t a_addr = sa + (term == 1 ? p.a_bytes : 0u);
+                                const uint32_t w_addr = sw + (term == 2 ? w_half : 0u);
+#pragma unroll
+                                for (int k = 0; k < BK / 16; k++) {
+                                    const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(a_addr + k * 32);
+                                    const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(w_addr + k * 32);
+                                    ptx::mma_f16_ss_pair(tmem_d, da, db, idesc, (kbi | term | k) != 0 ? 1u : 0u);
+                                }
+                            }
+                        }
+                        ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 0x3);            // frees the stage in both CTAs
+                        if (kbi == kblocks - 1) ptx::mma_commit_pair(ptx::smem_u32(&tfull_bar[as]), 0x3);   // accumulators ready
+                    }
+                    __syncwarp();
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        const int q = warp & 3;
+        const int plane = p.Hp * p.Wp;
+        const uint32_t stage_base = smem_base + (uint32_t)p.num_stages * p.stage_bytes + (uint32_t)q * 2u * kStageChunkBytes;
+        uint32_t chunk_no = 0;
+        int local = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
+            const int as = local % p.accum_stages;
+            const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
+            const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+            const int n0 = (tile % p.tiles_n) * p.BN;
+            const int m = m0 + q * 32 + lane;
+            int image = 0;
+            bool valid = false;
+            if (m < p.Mp) {
+                image = m / plane;
+                const int r = m - image * plane;
+                const int y = r / p.Wp, x = r - y * p.Wp;
+                valid = y >= 1 && y <= p.Hp - 2 && x >= 1 && x <= p.Wp - 2;
+            }
+            ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+            epilogue_tile(p, &tmO, taddr, m0, n0, q, lane, stage_base, chunk_no, f8c, valid, image);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+                else ptx::mbar_arrive_remote(ptx::smem_u32(&tempty_bar[as]), 0u);
+            }
+        }
+        if (lane == 0) ptx::tma_store_wait<0>();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -466,9 +676,11 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // cluster size: weights are shared by `cluster` CTAs (TMA multicast); needs enough pixel tiles to fill the chip
-    int cluster = d.cluster > 0 ? d.cluster : 2;
-    while (cluster > 1 && (p.tiles_m < cluster * 8 || sms % cluster != 0 || BN % (cluster * 8) != 0)) cluster >>= 1;
+    // d.cluster: 0 / 2 = CTA pairs (cta_group::2, default), 1 = single CTAs, 12 / 14 = single-CTA MMAs with the
+    // weight tile TMA-multicast across clusters of 2 / 4 (kept for comparison)
+    const bool pair = (d.cluster == 2 || (d.cluster == 0 && p.tiles_m >= 16)) && sms % 2 == 0 && BN % 32 == 0;
+    int cluster = pair ? 2 : (d.cluster > 10 ? d.cluster - 10 : 1);
+    while (!pair && cluster > 1 && (p.tiles_m < cluster * 8 || sms % cluster != 0 || BN % (cluster * 8) != 0)) cluster >>= 1;
     p.cluster = cluster;
     p.super_m = (p.tiles_m + cluster - 1) / cluster;
     p.Hp = d.Hp; p.Wp = d.Wp;
@@ -478,7 +690,7 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     p.raw = d.raw; p.bias = d.bias; p.stats = d.stats;
     p.a_bytes = (uint32_t)(kBlockM * BK * 2);
     p.w_bytes = (uint32_t)(BN * BK * 2);
-    p.stage_bytes = (uint32_t)nA * (p.a_bytes + p.w_bytes);
+    p.stage_bytes = (uint32_t)nA * (p.a_bytes + (pair ? p.w_bytes / 2 : p.w_bytes));   // a CTA pair splits the weight tile
     const int smem_budget = 227 * 1024 - 2048 - (int)kEpilogueStagingBytes;
     p.num_stages = smem_budget / (int)p.stage_bytes;
     if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
@@ -521,7 +733,15 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     cfg.numAttrs = 1;
 
     cudaError_t e;
-    if (BK == 64) {
+    if (pair && BK == 64) {
+        e = cudaFuncSetAttribute(conv_igemm_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        e = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<64>, tmA, tmW, tmO, tmA8, tmW8, p);
+    } else if (pair) {
+        e = cudaFuncSetAttribute(conv_igemm_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        e = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<32>, tmA, tmW, tmO, tmA8, tmW8, p);
+    } else if (BK == 64) {
         e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cudaGetErrorString(e);
         e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<64>, tmA, tmW, tmO, tmA8, tmW8, p);

@@ -68,7 +68,9 @@ CONV_SHAPES = [
 
 @pytest.mark.parametrize('shape', CONV_SHAPES)
 @pytest.mark.parametrize('nterms', [3, 1])
-def test_conv_igemm_matches_torch(shape, nterms):
+@pytest.mark.parametrize('cluster', ['2', '1', '12'])   # CTA pairs (cta_group::2) | single CTAs | weight multicast
+def test_conv_igemm_matches_torch(shape, nterms, cluster, monkeypatch):
+    monkeypatch.setenv('CROSSLOC_B200_CONV_CLUSTER', cluster)
     cin, cout, k, stride, b, h, w = shape
     torch.manual_seed(cin + cout + k + stride)
     conv = torch.nn.Conv2d(cin, cout, k, stride, k // 2).to(DEV)
@@ -86,8 +88,10 @@ def test_conv_igemm_matches_torch(shape, nterms):
 
 @pytest.mark.parametrize('shape', [(256, 256, 3, 1, 2, 9, 14), (512, 512, 3, 1, 1, 60, 90), (256, 512, 3, 1, 3, 7, 5),
                                    (512, 512, 1, 1, 2, 9, 14)])
-def test_conv_igemm_fp16_plus_fp8_corrections(shape):
+@pytest.mark.parametrize('cluster', ['2', '1'])
+def test_conv_igemm_fp16_plus_fp8_corrections(shape, cluster, monkeypatch):
     """nterms == 2: a_hi*w_hi in fp16, both correction products as e4m3 MMAs into a second TMEM accumulator."""
+    monkeypatch.setenv('CROSSLOC_B200_CONV_CLUSTER', cluster)
     cin, cout, k, stride, b, h, w = shape
     torch.manual_seed(cin + cout + k)
     conv = torch.nn.Conv2d(cin, cout, k, stride, k // 2).to(DEV)
