@@ -214,9 +214,12 @@ def run_native(args):
         torch.cuda.synchronize()
 
     def step_device(image_base):
-        pose = loc.localize_device(images_d, focal_d, offsets_d, image_base=image_base)
+        # the solve (and the pose gather behind it) run on the localizer's solver stream and overlap the next step's CNN
+        pose = loc.localize_device(images_d, focal_d, offsets_d, image_base=image_base, overlap=True)
         if world > 1:   # trivial pose gather: 2 KB per rank
-            dist.all_gather_into_tensor(gathered, pose.reshape(B, 16))
+            with torch.cuda.stream(loc.solver_stream):
+                dist.all_gather_into_tensor(gathered, pose.reshape(B, 16))
+                loc.solver_done.record(loc.solver_stream)
         return pose
 
     # ---- device-resident throughput ("value")
@@ -235,6 +238,7 @@ def run_native(args):
     for k in range(args.steps):
         # no explicit L2 flush: one step streams >1 GB of activations through the 126 MB L2 (config.l2)
         pose = step_device((args.warmup + k) * world * B + rank * B)
+    torch.cuda.current_stream().wait_event(loc.solver_done)   # the last solve is inside the timed region
     stop.record()
     barrier()
     clocks = sampler.stop()
@@ -276,9 +280,15 @@ def run_native(args):
         avg_ms = sum(ms for _, ms in dom) / len(dom)
         achieved = dom[0][0] / (avg_ms * 1e-3) / 1e12
         nterms = engine.nterms
-        roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel<64> 3x3 512->512 @60x90 x%d images' % B,
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (same shape and mode)
+        traffic = None
+        prof = os.path.join(ROOT, 'profiles', 'r1_conv3x3_pair_ncu_full.json')
+        if os.path.exists(prof) and B == BATCH and engine.precision == 'fp16+fp8':
+            traffic = json.load(open(prof)).get('dram_bytes_per_launch')
+        roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel<64> 3x3 512->512 @60x90 x%d images' % B,
                     'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                    'traffic': None, 'peak_source': peak_src, 'avg_launch_ms': avg_ms, 'launches_timed': len(dom),
+                    'traffic': traffic, 'traffic_unit': 'bytes per launch (dram read + write, ncu)',
+                    'peak_source': peak_src, 'avg_launch_ms': avg_ms, 'launches_timed': len(dom),
                     'issued_tflops': achieved * nterms, 'issued_frac': achieved * nterms / peak_tf,
                     'note': 'achieved counts algorithmic FLOPs (2*pixels*Cout*Cin*9); %s issues %d fp16-MMA equivalents per '
                             'product (fp16+fp8: one fp16 MMA + two e4m3 MMAs at twice the rate)' % (engine.precision, nterms),

@@ -22,20 +22,29 @@ class Localizer:
         self.subsample = int(getattr(network, 'OUTPUT_SUBSAMPLE', 8))
         self.num_task = int(getattr(network, 'num_task_channel', 3))
         self._copy_stream = torch.cuda.Stream(self.device)
+        # the pose solver runs on its own stream: its three small kernels (2 ms, one of them a 32-block serial
+        # chain) overlap the convolutions of the next batch instead of idling most of the chip
+        self.solver_stream = torch.cuda.Stream(self.device)
+        self.solver_done = None   # event recorded after the last solve; wait on it before reading poses
         self._slots = [None, None]
         self._turn = 0
         self._pending = []
         self.kernel_launches = 0
 
     # ------------------------------------------------------------------ device-resident entry
-    def localize_device(self, images, focal, coord_offset=None, image_base=0, out_pose=None, debug=False):
+    def localize_device(self, images, focal, coord_offset=None, image_base=0, out_pose=None, debug=False, overlap=False):
         """images [B,C,H,W] fp32 CUDA, focal float or [B]; returns poses [B,4,4] fp32 CUDA (camera-to-world).
 
         `coord_offset` ([B,3,Hc,Wc], optional) is added to the regressed coordinates before the solve: with
         random-initialised weights the raw map is geometrically meaningless, so the synthetic benchmark turns
         it into a consistent scene the same way the decoder's `mean` buffer offsets it.
+
+        overlap=False: the poses are ready in the caller's stream on return (stream-ordered).
+        overlap=True: the solve is left running on `self.solver_stream`; wait on `self.solver_done` (or keep
+        working on that stream) before touching the poses.  The caller's stream is free for the next batch.
         """
         b, _, h, w = images.shape
+        main = torch.cuda.current_stream(images.device)
         with torch.no_grad():
             pred = self.net(images)
             coords = pred[:, :self.num_task]
@@ -44,9 +53,19 @@ class Localizer:
             coords = coords.contiguous()
             if out_pose is None:
                 out_pose = torch.empty(b, 4, 4, dtype=torch.float32, device=images.device)
-            dbg = dsac.forward_rgb_batch(coords, out_pose, self.hyps, self.threshold, focal, w / 2, h / 2, self.alpha,
-                                         self.max_reproj, self.subsample, seed=self.seed, image_base=image_base,
-                                         debug=debug)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(self.solver_stream):
+                self.solver_stream.wait_event(ready)
+                for t in (coords, out_pose) + ((focal,) if torch.is_tensor(focal) and focal.is_cuda else ()):
+                    t.record_stream(self.solver_stream)
+                dbg = dsac.forward_rgb_batch(coords, out_pose, self.hyps, self.threshold, focal, w / 2, h / 2,
+                                             self.alpha, self.max_reproj, self.subsample, seed=self.seed,
+                                             image_base=image_base, debug=debug)
+                self.solver_done = torch.cuda.Event()
+                self.solver_done.record(self.solver_stream)
+            if not overlap:
+                main.wait_event(self.solver_done)
         engine = getattr(self.net, '_engine', None)
         self.kernel_launches = (engine.launches if engine is not None else 0)
         return (out_pose, dbg) if debug else out_pose
@@ -75,11 +94,12 @@ class Localizer:
             st['images'].copy_(images_host, non_blocking=True)
             st['copied'].record(self._copy_stream)
         compute.wait_event(st['copied'])
-        self.localize_device(st['images'], focal, coord_offset, image_base, out_pose=st['pose_dev'])
+        self.localize_device(st['images'], focal, coord_offset, image_base, out_pose=st['pose_dev'], overlap=True)
         st['free'] = torch.cuda.Event()
-        st['free'].record(compute)
-        st['pose_host'].copy_(st['pose_dev'], non_blocking=True)
-        st['done'].record(compute)
+        st['free'].record(compute)          # the network has consumed the device frames
+        with torch.cuda.stream(self.solver_stream):   # poses leave on the solver stream, behind the solve
+            st['pose_host'].copy_(st['pose_dev'], non_blocking=True)
+            st['done'].record(self.solver_stream)
         self._pending.append(st)
         return st
 
