@@ -26,6 +26,9 @@ SIGNATURES = {
         _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _i32p, _c.c_int,
         _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p,
         _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p]),
+    'cl_conv_wgrad': (_c.c_int, [
+        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _i32p, _i32p,
+        _c.c_int, _c.c_float, _c.c_void_p, _c.c_void_p]),
     'cl_gn_apply': (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
         _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,

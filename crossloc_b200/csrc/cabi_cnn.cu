@@ -57,6 +57,26 @@ extern "C" int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo
     return finish(kFn, cl::conv_igemm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 
+extern "C" int cl_conv_wgrad(const void* grad, const void* act, int B, int Cout, int Cin, int plane, int plane_stride,
+                             int phases, int num_taps, const int32_t* tap_shift, const int32_t* tap_phase, int nterms,
+                             float out_scale, float* dw, void* cuda_stream)
+{
+    static const char* kFn = "cl_conv_wgrad";
+    NEED_DEV(grad); NEED_DEV(act); NEED_DEV(dw);
+    if (!tap_shift || !tap_phase) return cl::fail(-1, "%s: tap tables must not be NULL", kFn);
+    if (num_taps < 1 || num_taps > 9) return cl::fail(-1, "%s: num_taps=%d out of range", kFn, num_taps);
+    if (B <= 0 || plane <= 0 || phases < 1 || phases > 16) return cl::fail(-1, "%s: invalid sizes", kFn);
+    for (int i = 0; i < num_taps; i++)
+        if (tap_shift[i] % 8 != 0)   // TMA needs 16-byte aligned box starts along the pixel axis
+            return cl::fail(-1, "%s: tap_shift[%d]=%d is not a multiple of 8 pixels (use column-shifted copies)", kFn, i, tap_shift[i]);
+    cl::ConvWgradDesc d{};
+    d.grad = grad; d.act = act; d.B = B; d.Cout = Cout; d.Cin = Cin; d.plane = plane; d.plane_stride = plane_stride;
+    d.phases = phases; d.num_taps = num_taps;
+    for (int i = 0; i < num_taps; i++) { d.tap_shift[i] = tap_shift[i]; d.tap_phase[i] = tap_phase[i]; }
+    d.nterms = nterms; d.out_scale = out_scale; d.dw = dw;
+    return finish(kFn, cl::conv_wgrad_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}
+
 extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int group_ch, const double* stats,
                            const float* gamma, const float* beta, float eps, int relu_inner, int add_kind,
                            const void* res, int64_t res_lo_rows, const float* raw2, const double* stats2,

@@ -60,6 +60,35 @@ struct ConvIgemmParams {
 // returns nullptr on success, else a static error string
 const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream);
 
+// ---------------------------------------------------------------- weight gradient (training path)
+// dW[tap][co][ci] = sum over images and pixels of dY[b][co][p] * X[b][ci][p + shift(tap)] on channel-major
+// ("CM") fp16 matrices [term][phase][image][channel][plane_stride] (zero-bordered planes, pixel index fastest).
+struct ConvWgradDesc {
+    const void* grad;       // dY, CM, terms x B x Cout planes
+    const void* act;        // X, CM, terms x phases x B x Cin planes
+    int B, Cout, Cin;
+    int plane;              // pixels per padded plane (H + 2) * (W + 2) at the OUTPUT resolution
+    int plane_stride;       // row pitch in elements (plane rounded up to a multiple of 8)
+    int phases;             // 1, or 4 for a stride-2 convolution
+    int num_taps;
+    int tap_shift[9];       // pixel shift of X for each tap
+    int tap_phase[9];       // phase plane of X for each tap
+    int nterms;             // 1 or 3
+    float out_scale;
+    float* dw;              // fp32 [tap][Cout][Cin], accumulated with atomics: caller zeroes it
+};
+const char* conv_wgrad_launch(const ConvWgradDesc& d, cudaStream_t stream);
+
+struct ConvWgradParams {
+    int num_taps;
+    int tap_shift[9], tap_phase[9];
+    int B, Cout, Cin, BN, tiles_co, tiles_ci, splits, images_per_split, plane_kblocks, phases, nterms;
+    float out_scale;
+    float* dw;
+    int num_stages, accum_stages;
+    uint32_t a_bytes, w_bytes, stage_bytes;
+};
+
 // ---------------------------------------------------------------- GroupNorm apply / residual merge
 struct GnApplyDesc {
     const float* raw;       // fp32 PF [B*(H+2)*(W+2)][C]

@@ -98,6 +98,23 @@ int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int 
                   int64_t a8_total_rows, int64_t a8_lo_rows, const void* weights8, void* cuda_stream);
 
 /*
+ * Convolution weight gradient (training step):
+ *   dw[tap][co][ci] += out_scale * sum_{b, p} grad[b][co][p] * act[b][ci][p + tap_shift[tap]]
+ * on channel-major fp16 hi/lo matrices [term][phase][image][channel][plane_stride] whose planes are the
+ * zero-bordered images at the convolution's OUTPUT resolution (pixel index fastest, row pitch a multiple of 8).
+ * `act` holds `phases` plane groups; tap_phase[tap] selects the group a tap reads and tap_shift[tap] the pixel
+ * shift inside it.  TMA needs 16-byte aligned box starts, so tap_shift must be a multiple of 8: horizontal
+ * neighbours are provided as column-shifted copies (3 groups for a 3x3 stride-1 convolution, 4 parity phases x 2
+ * copies for stride 2) and only whole rows are shifted by the kernel.
+ * Replaces the cuDNN wgrad kernels autograd launches for nn.Conv2d (train_single_task.py:298).
+ *   grad   terms x B x Cout planes;  act  terms x phases x B x Cin planes;  nterms 1 | 3 (fp16x3)
+ *   dw     fp32 [num_taps][Cout][Cin], accumulated with atomics: the caller zeroes it
+ */
+int cl_conv_wgrad(const void* grad, const void* act, int B, int Cout, int Cin, int plane, int plane_stride, int phases,
+                  int num_taps, const int32_t* tap_shift, const int32_t* tap_phase, int nterms, float out_scale,
+                  float* dw, void* cuda_stream);
+
+/*
  * GroupNorm apply + ReLU + residual merge, fp32 raw -> fp16 hi/lo PF input of the next convolution.
  * Replaces nn.GroupNorm + F.relu (+ `res + x`) (networks.py:231-254, 332-343).
  *   out = relu_outer( add + relu_inner( gn(raw) ) ),  add = 0 | res_hi + res_lo | gn2(raw2)

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from crossloc_b200 import train as native_train
 from crossloc_b200.cnn import CoordNetEngine
 
 try:   # the reference logs through utils.io.safe_printout (networks.py:40); optional here
@@ -38,6 +39,17 @@ def _res_block(tiny, num_gn_channel, in_ch=None):
         nn.Conv2d(in_ch, ch, 3, 1, 1), nn.GroupNorm(groups, ch), nn.ReLU(),
         nn.Conv2d(ch, ch, 1, 1, 0), nn.GroupNorm(groups, ch), nn.ReLU(),
         nn.Conv2d(ch, ch, 3, 1, 1), nn.GroupNorm(groups, ch), nn.ReLU())
+
+
+def _torch_conv(conv, x):
+    return conv(x)
+
+
+def _run_block(block, x, conv):
+    """nn.Sequential of conv / GroupNorm / ReLU with a pluggable convolution operator."""
+    for m in block:
+        x = conv(m, x) if isinstance(m, nn.Conv2d) else m(x)
+    return x
 
 
 def _native_ok(module, x):
@@ -94,33 +106,37 @@ class Network(nn.Module):
             'head': {'conv': self.fc3, 'mean': self.mean, 'num_task': 3, 'clamp': _POS_CLAMP},
         }
 
-    def forward_reference(self, inputs):
-        x = F.relu(self.conv1(inputs))
-        x = F.relu(self.conv2(x))
-        x = F.relu(self.conv3(x))
-        res = F.relu(self.conv4(x))
-        x = F.relu(self.res1_conv1(res))
-        x = F.relu(self.res1_conv2(x))
-        x = F.relu(self.res1_conv3(x))
+    def forward_reference(self, inputs, conv=_torch_conv):
+        x = F.relu(conv(self.conv1, inputs))
+        x = F.relu(conv(self.conv2, x))
+        x = F.relu(conv(self.conv3, x))
+        res = F.relu(conv(self.conv4, x))
+        x = F.relu(conv(self.res1_conv1, res))
+        x = F.relu(conv(self.res1_conv2, x))
+        x = F.relu(conv(self.res1_conv3, x))
         res = res + x
-        x = F.relu(self.res2_conv1(res))
-        x = F.relu(self.res2_conv2(x))
-        x = F.relu(self.res2_conv3(x))
+        x = F.relu(conv(self.res2_conv1, res))
+        x = F.relu(conv(self.res2_conv2, x))
+        x = F.relu(conv(self.res2_conv3, x))
         if not self.tiny:
-            res = self.res2_skip(res)
+            res = conv(self.res2_skip, res)
         res = res + x
-        x = F.relu(self.res3_conv1(res))
-        x = F.relu(self.res3_conv2(x))
-        x = F.relu(self.res3_conv3(x))
+        x = F.relu(conv(self.res3_conv1, res))
+        x = F.relu(conv(self.res3_conv2, x))
+        x = F.relu(conv(self.res3_conv3, x))
         res = res + x
-        sc = F.relu(self.fc1(res))
-        sc = F.relu(self.fc2(sc))
-        sc = self.fc3(sc)
+        sc = F.relu(conv(self.fc1, res))
+        sc = F.relu(conv(self.fc2, sc))
+        sc = conv(self.fc3, sc)
         return sc + self.mean.to(sc.device)[None, :, None, None]
+
+    def forward_train(self, inputs):
+        """Autograd path with the convolutions (forward, dgrad, wgrad) on the native tensor-core kernels."""
+        return self.forward_reference(inputs, conv=native_train.conv2d)
 
     def forward(self, inputs):
         if not _native_ok(self, inputs):
-            return self.forward_reference(inputs)
+            return self.forward_train(inputs)
         if self._engine is None:
             self._engine = CoordNetEngine()
         return self._engine.forward(self._spec(), inputs)
@@ -180,23 +196,23 @@ class TransPoseNetEncoder(nn.Module):
             blocks.append({'kind': 'residual', 'convs': names})
         return layers, blocks
 
-    def forward_reference(self, inputs):
-        x = F.relu(self.norm1(self.conv1(inputs)))
-        x = F.relu(self.norm2(self.conv2(x)))
-        x = F.relu(self.norm3(self.conv3(x)))
-        res = F.relu(self.norm4(self.conv4(x)))
-        x = F.relu(self.res1_norm1(self.res1_conv1(res)))
-        x = F.relu(self.res1_norm2(self.res1_conv2(x)))
-        x = F.relu(self.res1_norm3(self.res1_conv3(x)))
+    def forward_reference(self, inputs, conv=_torch_conv):
+        x = F.relu(self.norm1(conv(self.conv1, inputs)))
+        x = F.relu(self.norm2(conv(self.conv2, x)))
+        x = F.relu(self.norm3(conv(self.conv3, x)))
+        res = F.relu(self.norm4(conv(self.conv4, x)))
+        x = F.relu(self.res1_norm1(conv(self.res1_conv1, res)))
+        x = F.relu(self.res1_norm2(conv(self.res1_conv2, x)))
+        x = F.relu(self.res1_norm3(conv(self.res1_conv3, x)))
         res = F.relu(res + x)
-        x = F.relu(self.res2_norm1(self.res2_conv1(res)))
-        x = F.relu(self.res2_norm2(self.res2_conv2(x)))
-        x = F.relu(self.res2_norm3(self.res2_conv3(x)))
+        x = F.relu(self.res2_norm1(conv(self.res2_conv1, res)))
+        x = F.relu(self.res2_norm2(conv(self.res2_conv2, x)))
+        x = F.relu(self.res2_norm3(conv(self.res2_conv3, x)))
         if not self.tiny:
-            res = self.res2_skip_norm(self.res2_skip(res))
+            res = self.res2_skip_norm(conv(self.res2_skip, res))
         res = F.relu(res + x)
         for block in self.enc_add_res_block_ls:
-            res = F.relu(res + block(res))
+            res = F.relu(res + _run_block(block, res, conv))
         return res
 
     def forward(self, inputs):
@@ -270,20 +286,20 @@ class TransPoseNetDecoder(nn.Module):
         head = {'conv': self.fc3, 'mean': self.mean, 'num_task': self.num_task_channel, 'clamp': _POS_CLAMP}
         return layers, blocks, head
 
-    def forward_reference(self, inputs, up_height=None, up_width=None):
+    def forward_reference(self, inputs, up_height=None, up_width=None, conv=_torch_conv):
         res = inputs
         for block in self.dec_add_res_block_ls:
-            res = F.relu(res + block(res))
-        x = F.relu(self.res3_norm1(self.res3_conv1(res)))
-        x = F.relu(self.res3_norm2(self.res3_conv2(x)))
-        x = F.relu(self.res3_norm3(self.res3_conv3(x)))
+            res = F.relu(res + _run_block(block, res, conv))
+        x = F.relu(self.res3_norm1(conv(self.res3_conv1, res)))
+        x = F.relu(self.res3_norm2(conv(self.res3_conv2, x)))
+        x = F.relu(self.res3_norm3(conv(self.res3_conv3, x)))
         res = F.relu(res + x)
-        sc = F.relu(self.fc1_norm(self.fc1(res)))
-        sc = F.relu(self.fc2_norm(self.fc2(sc)))
+        sc = F.relu(self.fc1_norm(conv(self.fc1, res)))
+        sc = F.relu(self.fc2_norm(conv(self.fc2, sc)))
         if self.full_size_output:
             sc = self.duc_upsample(sc)
             sc = F.interpolate(sc, (up_height, up_width), mode='bilinear', align_corners=False)
-        sc = self.fc3(sc)
+        sc = conv(self.fc3, sc)
         k = self.num_task_channel
         task = sc[:, :k] + self.mean.to(sc.device)[None, :, None, None]
         if not self.num_pos_channel:
@@ -355,22 +371,28 @@ class TransPoseNet(nn.Module):
         dec_layers, dec_blocks, head = self.decoder.plan('decoder.')
         return {'group_norm': True, 'layers': enc_layers + dec_layers, 'blocks': enc_blocks + dec_blocks, 'head': head}
 
-    def forward_reference(self, inputs):
+    def forward_reference(self, inputs, conv=_torch_conv):
         up_height, up_width = inputs.size()[2:4]
         if self.num_mlr == 0:
-            res = self.encoder.forward_reference(inputs)
+            res = self.encoder.forward_reference(inputs, conv)
         else:
-            mlr = torch.cat([enc.forward_reference(inputs) for enc in self.mlr_encoder_ls], dim=1)
+            mlr = torch.cat([enc.forward_reference(inputs, conv) for enc in self.mlr_encoder_ls], dim=1)
             res = self.mlr_skip(mlr)
             mlr = self.mlr_forward(self.mlr_norm(mlr))
             res = F.relu(res + mlr)
         if self.full_size_output:
-            return self.decoder.forward_reference(res, up_height, up_width)
-        return self.decoder.forward_reference(res)
+            return self.decoder.forward_reference(res, up_height, up_width, conv)
+        return self.decoder.forward_reference(res, conv=conv)
+
+    def forward_train(self, inputs):
+        """Autograd path: every eligible convolution runs its forward, dgrad and wgrad on the native tensor-core
+        kernels (crossloc_b200.train.NativeConv2d); GroupNorm, ReLU, the residual adds, the 3-channel stem and the
+        4-channel head stay stock torch ops in this round."""
+        return self.forward_reference(inputs, conv=native_train.conv2d)
 
     def forward(self, inputs):
         if not _native_ok(self, inputs):
-            return self.forward_reference(inputs)
+            return self.forward_train(inputs)
         if self.num_mlr != 0 or self.full_size_output:
             raise NotImplementedError('crossloc_b200: the native path covers the single-encoder, sub-sampled '
                                       'coordinate network; MLR / full-size variants are SURVEY.md section 8f rows 1-2 '
