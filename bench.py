@@ -178,7 +178,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- native arm
@@ -345,14 +345,32 @@ def run_native(args):
             'pose_error_median': {'t_m': float(np.median(errs[:, 0])), 'r_deg': float(np.median(errs[:, 1]))},
             'kernel_ms': kernel_ms,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there) get stderr instead."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
     args = parse_args()
+    _protect_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
