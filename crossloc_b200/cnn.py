@@ -217,6 +217,8 @@ class CoordNetEngine:
         self._lib = _lib.load()
         image = image.contiguous().to(torch.float32)
         batch, cin, h, w = image.shape
+        if batch == 0:
+            raise RuntimeError('crossloc_b200: empty batch')
         dev = image.device
         torch.cuda.set_device(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream

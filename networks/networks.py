@@ -197,6 +197,8 @@ class TransPoseNetEncoder(nn.Module):
         return layers, blocks
 
     def forward_reference(self, inputs, conv=_torch_conv):
+        if inputs.size(0) == 0:
+            raise RuntimeError('crossloc_b200: empty batch')
         x = F.relu(self.norm1(conv(self.conv1, inputs)))
         x = F.relu(self.norm2(conv(self.conv2, x)))
         x = F.relu(self.norm3(conv(self.conv3, x)))
@@ -231,8 +233,8 @@ class DenseUpsamplingConvolution(nn.Module):
         self.relu = nn.ReLU(inplace=True)
         self.pixel_shuffle = nn.PixelShuffle(down_sampling_rate)
 
-    def forward(self, x):
-        return self.pixel_shuffle(self.relu(self.norm(self.conv(x))))
+    def forward(self, x, conv=_torch_conv):
+        return self.pixel_shuffle(self.relu(self.norm(conv(self.conv, x))))
 
 
 class TransPoseNetDecoder(nn.Module):
@@ -297,7 +299,7 @@ class TransPoseNetDecoder(nn.Module):
         sc = F.relu(self.fc1_norm(conv(self.fc1, res)))
         sc = F.relu(self.fc2_norm(conv(self.fc2, sc)))
         if self.full_size_output:
-            sc = self.duc_upsample(sc)
+            sc = self.duc_upsample(sc, conv)
             sc = F.interpolate(sc, (up_height, up_width), mode='bilinear', align_corners=False)
         sc = conv(self.fc3, sc)
         k = self.num_task_channel
@@ -377,8 +379,8 @@ class TransPoseNet(nn.Module):
             res = self.encoder.forward_reference(inputs, conv)
         else:
             mlr = torch.cat([enc.forward_reference(inputs, conv) for enc in self.mlr_encoder_ls], dim=1)
-            res = self.mlr_skip(mlr)
-            mlr = self.mlr_forward(self.mlr_norm(mlr))
+            res = _run_block(self.mlr_skip, mlr, conv)
+            mlr = _run_block(self.mlr_forward, self.mlr_norm(mlr), conv)
             res = F.relu(res + mlr)
         if self.full_size_output:
             return self.decoder.forward_reference(res, up_height, up_width, conv)
@@ -394,9 +396,9 @@ class TransPoseNet(nn.Module):
         if not _native_ok(self, inputs):
             return self.forward_train(inputs)
         if self.num_mlr != 0 or self.full_size_output:
-            raise NotImplementedError('crossloc_b200: the native path covers the single-encoder, sub-sampled '
-                                      'coordinate network; MLR / full-size variants are SURVEY.md section 8f rows 1-2 '
-                                      '(forward_reference() runs them with stock torch ops)')
+            # MLR multi-encoder / full-size DUC variants have no fused plan yet:
+            # their convolutions still run on the tensor-core kernels, GroupNorm / concat / PixelShuffle are torch ops
+            return self.forward_train(inputs)
         if self._engine is None:
             self._engine = CoordNetEngine()
         return self._engine.forward(self._spec(), inputs)

@@ -266,3 +266,18 @@ def test_precision_modes():
             errs[prec] = rel_l2(out[:, :3], ref[:, :3])
     assert errs['fp16x3'] < 5e-5 and errs['fp16+fp8'] < 2e-4
     assert 1e-4 < errs['fp16x1'] < 1e-2
+
+
+def test_mlr_and_fullsize_variants_run_on_native_convolutions():
+    """The paper's MLR model (3 encoders) and the full-size DUC head: no fused plan yet, but forward() works and
+    its convolutions (incl. the 1536-channel ones) run on the tensor-core kernels; parity vs plain torch."""
+    import networks.networks as nets
+    torch.manual_seed(9)
+    x = torch.rand(1, 3, 64, 96, device=DEV)
+    for kwargs in ({'num_mlr': 3}, {'full_size_output': True}):
+        net = nets.TransPoseNet(torch.zeros(3), False, False, 1, 1, 3, 1, **kwargs).eval().to(DEV)
+        with torch.no_grad():
+            out = net(x)
+            ref = net.forward_reference(x)
+        assert out.shape == ref.shape
+        assert rel_l2(out[:, :3], ref[:, :3]) < 1e-3
