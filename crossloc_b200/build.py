@@ -25,6 +25,7 @@ UNITS = {
     'cabi_cnn.cu': [],
     'conv_igemm.cu': [],
     'cnn_pointwise.cu': [],
+    'train_layout.cu': [],
 }
 
 

@@ -77,6 +77,69 @@ extern "C" int cl_conv_wgrad(const void* grad, const void* act, int B, int Cout,
     return finish(kFn, cl::conv_wgrad_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 
+extern "C" int cl_nchw_to_pf(const float* x, const float* scale, void* out, int B, int C, int H, int W, int phases,
+                             void* cuda_stream)
+{
+    static const char* kFn = "cl_nchw_to_pf";
+    NEED_DEV(x); NEED_DEV(out);
+    if (scale) NEED_DEV(scale);
+    cl::NchwToPfDesc d{x, scale, static_cast<__half*>(out), B, C, H, W, phases};
+    return finish(kFn, cl::nchw_to_pf_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}
+
+extern "C" int cl_pf_to_nchw(const float* raw, int B, int H, int W, int Craw, float* out, int C, int Hout, int Wout,
+                             int step, int off_y, int off_x, const float* scale, const float* bias, void* cuda_stream)
+{
+    static const char* kFn = "cl_pf_to_nchw";
+    NEED_DEV(raw); NEED_DEV(out);
+    if (scale) NEED_DEV(scale);
+    if (bias) NEED_DEV(bias);
+    if (step != 1 && step != 2) return cl::fail(-1, "%s: step must be 1 or 2", kFn);
+    cl::PfToNchwDesc d{raw, B, H, W, Craw, out, C, Hout, Wout, step, off_y, off_x, scale, bias};
+    return finish(kFn, cl::pf_to_nchw_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}
+
+extern "C" int cl_nchw_to_cm(const float* x, const float* scale, void* out, int B, int C, int H, int W, int hp, int wp,
+                             int rows, int cols, int step, int groups, const int32_t* pa, const int32_t* pb,
+                             const int32_t* col0, void* cuda_stream)
+{
+    static const char* kFn = "cl_nchw_to_cm";
+    NEED_DEV(x); NEED_DEV(out);
+    if (scale) NEED_DEV(scale);
+    if (!pa || !pb || !col0) return cl::fail(-1, "%s: group tables must not be NULL", kFn);
+    if (groups < 1 || groups > 8) return cl::fail(-1, "%s: groups=%d out of range", kFn, groups);
+    cl::NchwToCmDesc d{};
+    d.x = x; d.scale = scale; d.out = static_cast<__half*>(out); d.B = B; d.C = C; d.H = H; d.W = W; d.hp = hp; d.wp = wp;
+    d.rows = rows; d.cols = cols; d.step = step; d.groups = groups;
+    for (int g = 0; g < groups; g++) { d.pa[g] = pa[g]; d.pb[g] = pb[g]; d.col0[g] = col0[g]; }
+    return finish(kFn, cl::nchw_to_cm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}
+
+extern "C" int cl_pow2_scale(const float* x, int64_t n, float target, void* workspace, void* cuda_stream)
+{
+    static const char* kFn = "cl_pow2_scale";
+    NEED_DEV(x); NEED_DEV(workspace);
+    if (n <= 0) return cl::fail(-1, "%s: empty tensor", kFn);
+    float* out = static_cast<float*>(workspace);
+    return finish(kFn, cl::pow2_scale_launch(x, (size_t)n, target, reinterpret_cast<unsigned*>(out + 2), out,
+                                             static_cast<cudaStream_t>(cuda_stream)));
+}
+
+extern "C" int cl_pack_filter(const float* w, const float* scale, void* out, int Cout, int Cin, int ksize, int num_taps,
+                              const int32_t* tap_kh, const int32_t* tap_kw, int transpose, int N, int K,
+                              void* cuda_stream)
+{
+    static const char* kFn = "cl_pack_filter";
+    NEED_DEV(w); NEED_DEV(scale); NEED_DEV(out);
+    if (!tap_kh || !tap_kw || num_taps < 1 || num_taps > 9) return cl::fail(-1, "%s: invalid tap table", kFn);
+    cl::PackFilterDesc d{};
+    d.w = w; d.scale = scale; d.out = static_cast<__half*>(out); d.Cout = Cout; d.Cin = Cin; d.ksize = ksize;
+    d.num_taps = num_taps;
+    for (int t = 0; t < num_taps; t++) { d.tap_kh[t] = tap_kh[t]; d.tap_kw[t] = tap_kw[t]; }
+    d.transpose = transpose; d.N = N; d.K = K;
+    return finish(kFn, cl::pack_filter_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}
+
 extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int group_ch, const double* stats,
                            const float* gamma, const float* beta, float eps, int relu_inner, int add_kind,
                            const void* res, int64_t res_lo_rows, const float* raw2, const double* stats2,

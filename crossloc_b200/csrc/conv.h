@@ -89,6 +89,53 @@ struct ConvWgradParams {
     uint32_t a_bytes, w_bytes, stage_bytes;
 };
 
+// ---------------------------------------------------------------- layout kernels of the training path
+struct NchwToPfDesc {
+    const float* x;         // NCHW fp32 [B][C][H][W]
+    const float* scale;     // nullable device scalar multiplied in
+    __half* out;            // PF hi/lo [2][phases][B*(H'+2)*(W'+2)][C], zero-initialised by the caller
+    int B, C, H, W, phases;
+};
+const char* nchw_to_pf_launch(const NchwToPfDesc& d, cudaStream_t stream);
+
+struct PfToNchwDesc {
+    const float* raw;       // fp32 PF [B*(H+2)*(W+2)][Craw]
+    int B, H, W, Craw;
+    float* out;             // NCHW fp32 [B][C][Hout][Wout]; pixel (y, x) of raw goes to (y*step + off_y, x*step + off_x)
+    int C, Hout, Wout, step, off_y, off_x;
+    const float* scale;     // nullable device scalar
+    const float* bias;      // nullable [C]
+};
+const char* pf_to_nchw_launch(const PfToNchwDesc& d, cudaStream_t stream);
+
+struct NchwToCmDesc {
+    const float* x;         // NCHW fp32 [B][C][H][W]
+    const float* scale;     // nullable device scalar
+    __half* out;            // CM hi/lo [2][groups][B][C][hp*wp]
+    int B, C, H, W;
+    int hp, wp;             // padded plane; source pixel (r, q) of group g lands at row r + 1, column q + col0[g]
+    int rows, cols;         // valid source extent of a plane (output resolution of the convolution)
+    int step;               // 1, or 2: group g holds the parity phase (pa[g], pb[g]) of x
+    int groups;
+    int pa[8], pb[8], col0[8];
+};
+const char* nchw_to_cm_launch(const NchwToCmDesc& d, cudaStream_t stream);
+
+// {2^k, 2^-k} with k = floor(log2(target / max|x|)); scratch: two 32-bit words (zeroed by the launch), out: two floats
+const char* pow2_scale_launch(const float* x, size_t n, float target, unsigned* scratch, float* out, cudaStream_t stream);
+
+struct PackFilterDesc {
+    const float* w;         // OIHW fp32 [Cout][Cin][k][k]
+    const float* scale;     // device scalar (power of two)
+    __half* out;            // hi/lo [2][num_taps][N][K]
+    int Cout, Cin, ksize;
+    int num_taps;
+    int tap_kh[9], tap_kw[9];
+    int transpose;          // 0: N = Cout, K = Cin (forward);  1: N = Cin (zero-padded to N), K = Cout (data gradient)
+    int N, K;
+};
+const char* pack_filter_launch(const PackFilterDesc& d, cudaStream_t stream);
+
 // ---------------------------------------------------------------- GroupNorm apply / residual merge
 struct GnApplyDesc {
     const float* raw;       // fp32 PF [B*(H+2)*(W+2)][C]

@@ -4,18 +4,19 @@ torch.autograd.Function (BASELINE config 4 / SURVEY.md section 8a row a19).
 The reference trains through stock autograd (/root/reference/train_single_task.py:262-299): every nn.Conv2d
 contributes a cuDNN forward, dgrad and wgrad kernel.  Here
   forward  = cl_conv_igemm on the padded-flat layout (same kernel as inference, fp16x3, no GroupNorm statistics),
-  dgrad    = cl_conv_igemm on the output gradient with the transposed, flipped filter (a stride-2 convolution
-             decomposes into one small stride-1 convolution per input parity phase),
-  wgrad    = cl_conv_wgrad on channel-major operands (split-K over images, fp32 atomics).
-GroupNorm / ReLU / residual adds and the loss stay stock torch ops in this round, and the NCHW <-> kernel-layout
-conversions are torch ops as well: this is a first correct native training path, not yet a fast one.
+  dgrad    = cl_conv_igemm on the output gradient with the transposed filter and negated tap shifts (a stride-2
+             convolution decomposes into one small stride-1 problem per input parity phase),
+  wgrad    = cl_conv_wgrad on channel-major operands (split-K over images, fp32 atomics),
+with the NCHW <-> operand-layout conversions and the filter packing done by cl_nchw_to_pf / cl_pf_to_nchw /
+cl_nchw_to_cm / cl_pack_filter.  GroupNorm / ReLU / residual adds and the loss stay stock torch ops in this round.
+Gradients are rescaled by a power of two computed on the device (no host synchronisation) so that they stay
+inside fp16's range; filters are scaled the same way.
 """
 import ctypes
 
 import torch
-import torch.nn.functional as F
 
-from . import _lib, layout
+from . import _lib
 from .cnn import _Geometry
 
 _NTERMS = 3
@@ -29,14 +30,40 @@ def eligible(conv):
             and conv.dilation[0] == 1 and conv.groups == 1)
 
 
-def _pack_taps(w_taps):
-    """[taps][N][K] fp32 -> (fp16 [2][taps][N][K] hi/lo planes scaled by 2^k, 2^-k)."""
-    amax = w_taps.abs().amax().clamp_min(1e-30)
-    scale = torch.exp2(torch.floor(torch.log2(128.0 / amax)))       # device scalar, no host sync
-    w = w_taps * scale
-    hi = w.to(torch.float16)
-    lo = (w - hi.to(torch.float32)).to(torch.float16)
-    return torch.stack([hi, lo], 0).contiguous(), 1.0 / scale
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _i32(values):
+    return (ctypes.c_int32 * len(values))(*values)
+
+
+def _pow2_scale(t, target):
+    """Device scalars (2^k, 2^-k) bringing max|t| to about `target`, computed on the GPU (no host sync)."""
+    lib = _lib.load()
+    ws = torch.empty(4, dtype=torch.float32, device=t.device)
+    _lib.check(lib.cl_pow2_scale(t.data_ptr(), t.numel(), float(target), ws.data_ptr(), _stream(t)))
+    return ws[0:1], ws[1:2]
+
+
+def _pack(weight, scale, pairs, transpose, n, k):
+    """fp16 hi/lo [2][taps][n][k] operand of the filter taps `pairs` ((kh, kw) list), x scale."""
+    lib = _lib.load()
+    cout, cin, ks, _ = weight.shape
+    out = torch.empty(2, len(pairs), n, k, dtype=torch.float16, device=weight.device)
+    _lib.check(lib.cl_pack_filter(weight.data_ptr(), scale.data_ptr(), out.data_ptr(), cout, cin, ks, len(pairs),
+                                  _i32([p[0] for p in pairs]), _i32([p[1] for p in pairs]), 1 if transpose else 0, n, k,
+                                  _stream(weight)))
+    return out
+
+
+def _to_pf(x, phases, geo, scale=None):
+    lib = _lib.load()
+    b, c, h, w = x.shape
+    out = torch.zeros(2 * phases * geo.Mp, c, dtype=torch.float16, device=x.device)
+    _lib.check(lib.cl_nchw_to_pf(x.data_ptr(), 0 if scale is None else scale.data_ptr(), out.data_ptr(), b, c, h, w,
+                                 phases, _stream(x)))
+    return out
 
 
 def _igemm(act_pf, in_phases, geo, packed, taps, cin, cout):
@@ -44,32 +71,19 @@ def _igemm(act_pf, in_phases, geo, packed, taps, cin, cout):
     lib = _lib.load()
     raw = torch.empty(geo.Mp, cout, dtype=torch.float32, device=act_pf.device)
     zero_bias = torch.zeros(cout, dtype=torch.float32, device=act_pf.device)
-    arr = (ctypes.c_int32 * len(taps))(*taps)
     _lib.check(lib.cl_conv_igemm(act_pf.data_ptr(), act_pf.size(0), in_phases * geo.Mp, cin, packed.data_ptr(), cout,
-                                 len(taps), arr, _NTERMS, geo.Mp, geo.Hp, geo.Wp, 0, 1.0, raw.data_ptr(),
-                                 zero_bias.data_ptr(), 0, 0, 0, 0, 0,
-                                 torch.cuda.current_stream(act_pf.device).cuda_stream))
+                                 len(taps), _i32(taps), _NTERMS, geo.Mp, geo.Hp, geo.Wp, 0, 1.0, raw.data_ptr(),
+                                 zero_bias.data_ptr(), 0, 0, 0, 0, 0, _stream(act_pf)))
     return raw
 
 
-def _amax_scale(t):
-    """Power-of-two factor (device scalar) that brings max|t| to about 2^8: keeps gradients inside fp16's range."""
-    amax = t.abs().amax().clamp_min(1e-30)
-    return torch.exp2(torch.floor(torch.log2(256.0 / amax)))
-
-
-def conv_forward(x, weight, stride):
-    """y = conv2d(x, weight, stride, padding = k // 2) without bias; NCHW fp32 in and out."""
-    cout, cin, k, _ = weight.shape
-    b, _, h, w = x.shape
-    ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
-    geo = _Geometry(b, ho, wo)
-    phases = 4 if stride == 2 else 1
-    act = layout.to_pf(x, phases=phases, terms=2)
-    packed, inv = _pack_taps(weight.permute(2, 3, 0, 1).reshape(k * k, cout, cin).to(torch.float32))
-    taps = _forward_taps(k, stride, geo)
-    raw = _igemm(act, phases, geo, packed, taps, cin, cout)
-    return layout.raw_to_nchw(raw, b, ho, wo) * inv
+def _from_raw(raw, geo, craw, out, step=1, off=(0, 0), scale=None, bias=None):
+    lib = _lib.load()
+    b, c, hout, wout = out.shape
+    _lib.check(lib.cl_pf_to_nchw(raw.data_ptr(), geo.B, geo.H, geo.W, craw, out.data_ptr(), c, hout, wout, step, off[0],
+                                 off[1], 0 if scale is None else scale.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                                 _stream(raw)))
+    return out
 
 
 def _forward_taps(k, stride, geo):
@@ -87,24 +101,34 @@ def _forward_taps(k, stride, geo):
     return out
 
 
+def conv_forward(x, weight, bias, stride):
+    """y = conv2d(x, weight, bias, stride, padding = k // 2); NCHW fp32 in and out."""
+    cout, cin, k, _ = weight.shape
+    b, _, h, w = x.shape
+    ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
+    geo = _Geometry(b, ho, wo)
+    phases = 4 if stride == 2 else 1
+    act = _to_pf(x, phases, geo)
+    ws, ws_inv = _pow2_scale(weight, 128.0)
+    pairs = [(kh, kw) for kh in range(k) for kw in range(k)]
+    packed = _pack(weight, ws, pairs, False, cout, cin)
+    raw = _igemm(act, phases, geo, packed, _forward_taps(k, stride, geo), cin, cout)
+    y = torch.empty(b, cout, ho, wo, dtype=torch.float32, device=x.device)
+    return _from_raw(raw, geo, cout, y, scale=ws_inv, bias=bias)
+
+
 def conv_dgrad(gy, weight, in_hw, stride):
     """dL/dx of y = conv2d(x, weight, stride, padding = k // 2); gy NCHW fp32 [B, Cout, Ho, Wo]."""
     cout, cin, k, _ = weight.shape
     b, _, ho, wo = gy.shape
     h, w = in_hw
-    s = _amax_scale(gy)
+    gs, gs_inv = _pow2_scale(gy, 256.0)
+    ws, ws_inv = _pow2_scale(weight, 128.0)
+    out_scale = gs_inv * ws_inv
     geo = _Geometry(b, ho, wo)
-    g_pf = layout.to_pf(gy * s, phases=1, terms=2)
-    n_out = cin if cin % 64 == 0 else ((cin + 63) // 64) * 64      # the kernel wants Cout' % 64 == 0: zero-pad
-    wt = weight.to(torch.float32)
-
-    def taps_weight(pairs):
-        """[taps][cin'][cout] for (kh, kw) pairs: dX[ci] = sum_co dY[co] * W[co][ci][kh][kw]."""
-        mats = torch.stack([wt[:, :, kh, kw].t() for kh, kw in pairs], 0)      # [taps][cin][cout]
-        if n_out != cin:
-            mats = F.pad(mats, (0, 0, 0, n_out - cin))
-        return mats.contiguous()
-
+    g_pf = _to_pf(gy, 1, geo, gs)
+    n_out = (cin + 63) // 64 * 64          # the kernel wants Cout' % 64 == 0: zero-padded filter rows
+    gx = torch.empty(b, cin, h, w, dtype=torch.float32, device=gy.device)
     if stride == 1:
         if k == 1:
             pairs, shifts = [(0, 0)], [0]
@@ -112,30 +136,32 @@ def conv_dgrad(gy, weight, in_hw, stride):
             # x[p] feeds y[p - (kh-1, kw-1)] through tap (kh, kw): dX[p] = sum dY[p + (1-kh, 1-kw)] W[kh][kw]
             pairs = [(kh, kw) for kh in range(3) for kw in range(3)]
             shifts = [(1 - kh) * geo.Wp + (1 - kw) for kh, kw in pairs]
-        packed, inv = _pack_taps(taps_weight(pairs))
-        raw = _igemm(g_pf, 1, geo, packed, shifts, cout, n_out)
-        gx = layout.raw_to_nchw(raw, b, ho, wo)[:, :cin]
-        return gx * (inv / s)
-    # stride 2: input rows of parity a receive from kh in {1} (a = 0: oy = i) or {0 (oy = i + 1), 2 (oy = i)} (a = 1)
-    per_parity = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}
-    gx = torch.zeros(b, cin, 2 * ho, 2 * wo, dtype=torch.float32, device=gy.device)
+        raw = _igemm(g_pf, 1, geo, _pack(weight, ws, pairs, True, n_out, cout), shifts, cout, n_out)
+        return _from_raw(raw, geo, n_out, gx, scale=out_scale)
+    # stride 2: input rows of parity a receive from kh = 1 (a = 0: oy = i) or kh = 0 (oy = i + 1), 2 (oy = i) (a = 1)
+    per_parity = {0: [(1, 0)], 1: [(0, 1), (2, 0)]} if k == 3 else {0: [(0, 0)], 1: []}
+    if h % 2 or w % 2 or k == 1:
+        gx.zero_()                          # phases a 1x1 stride-2 filter never touches / cropped odd rows
     for a in (0, 1):
         for bb in (0, 1):
             pairs = [(kh, kw) for kh, _ in per_parity[a] for kw, _ in per_parity[bb]]
+            if not pairs:
+                continue
             shifts = [dy * geo.Wp + dx for _, dy in per_parity[a] for _, dx in per_parity[bb]]
-            packed, inv = _pack_taps(taps_weight(pairs))
-            raw = _igemm(g_pf, 1, geo, packed, shifts, cout, n_out)
-            gx[:, :, a::2, bb::2] = layout.raw_to_nchw(raw, b, ho, wo)[:, :cin] * (inv / s)
-    return gx[:, :, :h, :w].contiguous()
+            raw = _igemm(g_pf, 1, geo, _pack(weight, ws, pairs, True, n_out, cout), shifts, cout, n_out)
+            _from_raw(raw, geo, n_out, gx, step=2, off=(a, bb), scale=out_scale)
+    return gx
 
 
-def _to_cm(x, hp, wp, col0):
-    """NCHW fp32 -> channel-major fp16 hi/lo planes [2][B][C][hp * wp]: x placed at rows 1.., columns col0.., zeros elsewhere."""
+def _to_cm(x, hp, wp, rows, cols, step, groups, scale=None):
+    """NCHW fp32 -> channel-major fp16 hi/lo planes [2][groups][B][C][hp * wp]; groups = [(pa, pb, col0)]."""
+    lib = _lib.load()
     b, c, h, w = x.shape
-    p = F.pad(x, (col0, wp - w - col0, 1, hp - h - 1)).reshape(b, c, hp * wp)
-    hi = p.to(torch.float16)
-    lo = (p - hi.to(torch.float32)).to(torch.float16)
-    return torch.stack([hi, lo], 0)
+    out = torch.empty(2, len(groups), b, c, hp * wp, dtype=torch.float16, device=x.device)
+    _lib.check(lib.cl_nchw_to_cm(x.data_ptr(), 0 if scale is None else scale.data_ptr(), out.data_ptr(), b, c, h, w, hp,
+                                 wp, rows, cols, step, len(groups), _i32([g[0] for g in groups]),
+                                 _i32([g[1] for g in groups]), _i32([g[2] for g in groups]), _stream(x)))
+    return out
 
 
 def conv_wgrad(gy, x, weight_shape, stride):
@@ -150,41 +176,36 @@ def conv_wgrad(gy, x, weight_shape, stride):
     hp = ho + 2
     wp = (wo + 3 + 7) // 8 * 8                                         # room for the -1 column shift, pitch % 8 == 0
     plane = hp * wp
-    s = _amax_scale(gy)
-    g_cm = _to_cm(gy * s, hp, wp, 1).contiguous()                      # [2][B][Cout][plane]
-    groups, shifts, tphase = [], [], []
+    gs, gs_inv = _pow2_scale(gy, 256.0)
+    g_cm = _to_cm(gy, hp, wp, ho, wo, 1, [(0, 0, 1)], gs)              # [2][1][B][Cout][plane]
+    shifts, tphase = [], []
     if k == 1:
-        groups.append(_to_cm(x if stride == 1 else x[:, :, ::2, ::2], hp, wp, 1))
+        groups = [(0, 0, 1)]
         shifts, tphase = [0], [0]
     elif stride == 1:
         # group kw holds x shifted by (kw - 1) columns: reading it at row shift (kh - 1) gives x[p + (kh-1, kw-1)]
-        for kw in range(3):
-            groups.append(_to_cm(x, hp, wp, 1 - (kw - 1)))
+        groups = [(0, 0, 1 - (kw - 1)) for kw in range(3)]
         for kh in range(3):
             for kw in range(3):
                 shifts.append((kh - 1) * wp); tphase.append(kw)
     else:
         # parity phases of x at the output resolution, each with column shifts 0 and -1 (dx of the tap)
-        index = {}
+        groups, index = [], {}
         for a in (0, 1):
             for bb in (0, 1):
-                sub = x[:, :, a::2, bb::2]
-                sub = F.pad(sub, (0, wo - sub.size(3), 0, ho - sub.size(2)))
                 for dx in (0, -1):
                     index[(a, bb, dx)] = len(groups)
-                    groups.append(_to_cm(sub, hp, wp, 1 - dx))
+                    groups.append((a, bb, 1 - dx))
         for kh in range(3):
             for kw in range(3):
                 a, dy = (1, -1) if kh == 0 else ((0, 0) if kh == 1 else (1, 0))
                 bb, dx = (1, -1) if kw == 0 else ((0, 0) if kw == 1 else (1, 0))
                 shifts.append(dy * wp); tphase.append(index[(a, bb, dx)])
-    x_cm = torch.stack(groups, 1).contiguous()                        # [2][groups][B][Cin][plane]
+    x_cm = _to_cm(x, hp, wp, ho, wo, stride, groups)                   # [2][groups][B][Cin][plane]
     dw = torch.zeros(k * k, cout, cin, dtype=torch.float32, device=gy.device)
-    a_shift = (ctypes.c_int32 * len(shifts))(*shifts)
-    a_phase = (ctypes.c_int32 * len(tphase))(*tphase)
-    _lib.check(lib.cl_conv_wgrad(g_cm.data_ptr(), x_cm.data_ptr(), b, cout, cin, plane, plane, len(groups), k * k, a_shift,
-                                 a_phase, _NTERMS, 1.0, dw.data_ptr(), torch.cuda.current_stream(gy.device).cuda_stream))
-    return (dw / s).reshape(k, k, cout, cin).permute(2, 3, 0, 1).contiguous()
+    _lib.check(lib.cl_conv_wgrad(g_cm.data_ptr(), x_cm.data_ptr(), b, cout, cin, plane, plane, len(groups), k * k,
+                                 _i32(shifts), _i32(tphase), _NTERMS, 1.0, dw.data_ptr(), _stream(gy)))
+    return (dw * gs_inv).reshape(k, k, cout, cin).permute(2, 3, 0, 1).contiguous()
 
 
 class NativeConv2d(torch.autograd.Function):
@@ -192,9 +213,8 @@ class NativeConv2d(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, stride):
-        y = conv_forward(x, weight, stride)
-        if bias is not None:
-            y = y + bias[None, :, None, None]
+        x = x.contiguous()
+        y = conv_forward(x, weight.contiguous(), bias, stride)
         ctx.save_for_backward(x, weight)
         ctx.stride = stride
         ctx.has_bias = bias is not None
@@ -204,6 +224,7 @@ class NativeConv2d(torch.autograd.Function):
     def backward(ctx, gy):
         x, weight = ctx.saved_tensors
         gy = gy.contiguous()
+        weight = weight.contiguous()
         gx = conv_dgrad(gy, weight, x.shape[2:], ctx.stride) if ctx.needs_input_grad[0] else None
         gw = conv_wgrad(gy, x, weight.shape, ctx.stride) if ctx.needs_input_grad[1] else None
         gb = gy.sum((0, 2, 3)) if ctx.has_bias and ctx.needs_input_grad[2] else None
@@ -212,6 +233,6 @@ class NativeConv2d(torch.autograd.Function):
 
 def conv2d(conv, x):
     """Apply an nn.Conv2d through the native autograd function when it is eligible, else through torch."""
-    if x.is_cuda and eligible(conv):
+    if x.is_cuda and x.dtype == torch.float32 and eligible(conv):
         return NativeConv2d.apply(x, conv.weight, conv.bias, conv.stride[0])
     return conv(x)

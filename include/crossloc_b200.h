@@ -115,6 +115,30 @@ int cl_conv_wgrad(const void* grad, const void* act, int B, int Cout, int Cin, i
                   float* dw, void* cuda_stream);
 
 /*
+ * Layout kernels of the training path (device pointers): NCHW fp32 tensors, as autograd hands them over, to and
+ * from the operand layouts of cl_conv_igemm / cl_conv_wgrad, and filter packing.  `scale` arguments are device
+ * scalars (power-of-two factors computed on the GPU, no host synchronisation), NULL = 1.
+ *   cl_nchw_to_pf   x [B][C][H][W] -> fp16 hi/lo PF [2][phases][B*(H'+2)*(W'+2)][C] (interior; caller zero-fills)
+ *   cl_pf_to_nchw   raw fp32 PF [B*(H+2)*(W+2)][Craw] -> out [B][C][Hout][Wout] at (y*step+off_y, x*step+off_x),
+ *                   x scale, + bias (the per-phase results of a stride-2 data gradient use step 2)
+ *   cl_nchw_to_cm   x -> fp16 hi/lo channel-major planes [2][groups][B][C][hp*wp]; group g holds parity phase
+ *                   (pa[g], pb[g]) of x (step 2) or x itself (step 1) shifted to column col0[g], rows from 1
+ *   cl_pack_filter  w OIHW -> fp16 hi/lo [2][num_taps][N][K] for taps (tap_kh, tap_kw), transposed for dgrad
+ */
+int cl_nchw_to_pf(const float* x, const float* scale, void* out, int B, int C, int H, int W, int phases,
+                  void* cuda_stream);
+int cl_pf_to_nchw(const float* raw, int B, int H, int W, int Craw, float* out, int C, int Hout, int Wout, int step,
+                  int off_y, int off_x, const float* scale, const float* bias, void* cuda_stream);
+int cl_nchw_to_cm(const float* x, const float* scale, void* out, int B, int C, int H, int W, int hp, int wp, int rows,
+                  int cols, int step, int groups, const int32_t* pa, const int32_t* pb, const int32_t* col0,
+                  void* cuda_stream);
+/* workspace: 4 x 32-bit device words; on completion workspace[0] = 2^k, workspace[1] = 2^-k (floats) with
+ * k = floor(log2(target / max|x|)) -- the power-of-two operand scales, computed without a host round trip */
+int cl_pow2_scale(const float* x, int64_t n, float target, void* workspace, void* cuda_stream);
+int cl_pack_filter(const float* w, const float* scale, void* out, int Cout, int Cin, int ksize, int num_taps,
+                   const int32_t* tap_kh, const int32_t* tap_kw, int transpose, int N, int K, void* cuda_stream);
+
+/*
  * GroupNorm apply + ReLU + residual merge, fp32 raw -> fp16 hi/lo PF input of the next convolution.
  * Replaces nn.GroupNorm + F.relu (+ `res + x`) (networks.py:231-254, 332-343).
  *   out = relu_outer( add + relu_inner( gn(raw) ) ),  add = 0 | res_hi + res_lo | gn2(raw2)

@@ -126,3 +126,20 @@ def test_full_size_batch_accuracy():
     errs = np.array([synth.pose_errors(poses[b], pose[b]) for b in range(32)])
     assert np.median(errs[:, 0]) < 0.3 and np.median(errs[:, 1]) < 0.2
     assert errs[:, 0].max() < 2.0
+
+
+def test_full_size_map_sub_sampling_one():
+    """SURVEY.md section 8f row 2 shape: a 120x180-cell map with sub-sampling 4 and a 480x720 one with sub-sampling 1
+    (345,600 cells) go through the same kernels; decisions match the CPU oracle on the smaller one."""
+    s = synth.make_scene(31, subsample=4)
+    c = torch.from_numpy(s['coords']).unsqueeze(0).cuda()
+    pose = torch.zeros(1, 4, 4, device='cuda')
+    dbg = dsac.forward_rgb_batch(c, pose, 32, 10.0, 480.0, 360.0, 240.0, 100.0, 100.0, 4, seed=1305, image_base=31, debug=True)
+    ref = tier2.forward_rgb(s['coords'], 32, 10.0, 480.0, 360.0, 240.0, 100.0, 100.0, 4, seed=1305, image=31)
+    assert ref['best'] == int(dbg['best'][0]) and (np.asarray(ref['tries']) == dbg['tries'][0].numpy()).all()
+    assert np.abs(ref['pose'] - pose[0].cpu().numpy()).max() < 1e-4 * np.abs(ref['pose']).max()
+    big = synth.make_scene(32, subsample=1)
+    c = torch.from_numpy(big['coords']).unsqueeze(0).cuda()
+    dsac.forward_rgb_batch(c, pose, 64, 10.0, 480.0, 360.0, 240.0, 100.0, 100.0, 1, seed=1305, image_base=32)
+    t_err, r_err = synth.pose_errors(big['pose'], pose[0].cpu().numpy())
+    assert t_err < 0.05 and r_err < 0.02
