@@ -157,7 +157,7 @@ def run_reference(args):
     if rank != 0:
         return   # one CPU path per box: the other ranks exit without work
     threads = len(os.sched_getaffinity(0))
-    os.environ.setdefault('OMP_NUM_THREADS', str(threads))
+    os.environ['OMP_NUM_THREADS'] = str(threads)   # torchrun pins it to 1; the CPU arm may use every host core
     per_step = 2   # bounded sample: two frames per step keeps --steps 10 --warmup 3 within a few minutes
     path = CpuPath(args.hyps, threads, per_step)
     rates = []
@@ -320,7 +320,7 @@ def run_native(args):
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
-            os.environ.setdefault('OMP_NUM_THREADS', str(threads))
+            os.environ['OMP_NUM_THREADS'] = str(threads)
             sample = 6
             rate, detail = CpuPath(args.hyps, threads, sample).rate(sample)
             cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
