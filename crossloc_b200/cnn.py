@@ -119,10 +119,12 @@ class CoordNetEngine:
         self.events = None   # set to a list to record (layer, shape, flops, start, end) CUDA events around every launch
 
     # ------------------------------------------------------------------ parameters
-    def _pack(self, name, conv):
-        ver = (conv.weight._version, conv.weight.data_ptr(), None if conv.bias is None else conv.bias._version)
+    def _pack(self, name, conv, force_split=False):
+        ver = (conv.weight._version, conv.weight.data_ptr(), None if conv.bias is None else conv.bias._version, force_split)
         if self._pack_versions.get(name) != ver:
             nterms = _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0])
+            if force_split and nterms == 2:
+                nterms = 3   # the operand comes from outside the plan and has no e4m3 planes
             self._packs[name] = PackedConv(conv.weight, conv.bias, conv.stride[0], nterms)
             self._pack_versions[name] = ver
         return self._packs[name]
@@ -211,7 +213,12 @@ class CoordNetEngine:
 
     # ------------------------------------------------------------------ plans
     def forward(self, spec, image):
-        """spec: dict produced by networks.networks (layer modules + head description). image: NCHW fp32 CUDA."""
+        """spec: dict produced by networks.networks (layer modules + head description). image: NCHW fp32 CUDA.
+
+        Optional spec keys: 'roles' maps conv1..conv4 to layer names (several encoders can share one engine);
+        'input': 'image' (default) | 'activation' (`image` is an NCHW fp32 activation at the output resolution: the
+        stem and the strided ladder are skipped); 'output': 'head' (default) | 'activation' (returns the final
+        residual stream as an NCHW fp32 tensor instead of running a head)."""
         if not image.is_cuda:
             raise RuntimeError('crossloc_b200: the coordinate network runs on a CUDA device only (no CPU fallback)')
         self._lib = _lib.load()
@@ -222,8 +229,12 @@ class CoordNetEngine:
         dev = image.device
         torch.cuda.set_device(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        ws = self._workspace(dev, batch, h, w, {'cin': cin})
+        from_activation = spec.get('input', 'image') == 'activation'
+        ws = self._workspace(dev, batch, h, w, {'cin': cin, 'act': int(from_activation)})
         geo = ws['geo']
+        if from_activation:
+            geo[3] = _Geometry(batch, h, w)
+        roles = spec.get('roles', {'conv1': 'conv1', 'conv2': 'conv2', 'conv3': 'conv3', 'conv4': 'conv4'})
         gn = spec['group_norm']
         layers = spec['layers']          # ordered list of (name, conv, norm or None)
         n_stat = len(layers) + 1
@@ -241,7 +252,11 @@ class CoordNetEngine:
             return s
 
         convs = {name: (conv, norm) for name, conv, norm in layers}
-        packs = {name: self._pack(name, conv) for name, conv, _ in layers if name != 'conv1'}
+        blocks = spec['blocks']
+        entry = set()
+        if from_activation and blocks:   # convolutions reading the externally supplied activation
+            entry = {blocks[0]['convs'][0]} | ({blocks[0]['skip']} if blocks[0]['kind'] == 'residual_skip' else set())
+        packs = {name: self._pack(name, conv, name in entry) for name, conv, _ in layers if name != roles.get('conv1')}
 
         def groups_of(norm, channels):
             return 0 if norm is None else channels // norm.num_groups
@@ -252,8 +267,6 @@ class CoordNetEngine:
             want_lo = also_lo or any(packs[c].nterms == 3 for c in consumers)
             return want_lo, want8
 
-        blocks = spec['blocks']
-
         def first_conv_of(block_index):
             """Name(s) of the convolution(s) that read the residual stream entering block `block_index`."""
             if block_index >= len(blocks):
@@ -261,39 +274,48 @@ class CoordNetEngine:
             blk = blocks[block_index]
             return [blk['convs'][0]] + ([blk['skip']] if blk['kind'] == 'residual_skip' else [])
 
-        # ---- stem: conv1 (+ norm1) + relu, written as the 4-phase input of conv2
-        conv1, norm1 = convs['conv1']
-        if conv1.out_channels != 32 or (norm1 is not None and norm1.num_groups != 32):
-            raise RuntimeError('crossloc_b200: the stem kernel is built for 32 channels / 32 groups')
-        a = self._act(ws, 'stem', 1, 32, 4)
-        st = next_stats() if norm1 is not None else None
-        e0 = self._tick()
-        _lib.check(self._lib.cl_stem_forward(
-            image.data_ptr(), batch, cin, h, w, conv1.weight.detach().contiguous().data_ptr(),
-            conv1.bias.detach().contiguous().data_ptr(), 1 if norm1 is not None else 0,
-            0 if st is None else st.data_ptr(), 0 if norm1 is None else norm1.weight.data_ptr(),
-            0 if norm1 is None else norm1.bias.data_ptr(), 1e-5 if norm1 is None else float(norm1.eps),
-            a.h16.data_ptr(), self.terms, stream))
-        self._tock(e0, 'stem', ('stem',), 2.0 * batch * h * w * 32 * cin * 9)
-        self.launches += 2 if norm1 is not None else 1
-
-        # ---- strided ladder conv2..conv4
-        for level, name in ((1, 'conv2'), (2, 'conv3'), (3, 'conv4')):
-            conv, norm = convs[name]
-            pack = packs[name]
-            raw = self._raw(ws, 'ladder', level, pack.cout)
-            st = next_stats() if norm is not None else None
-            self._conv(stream, pack, a, geo[level], raw, st, groups_of(norm, pack.cout), name)
-            if level < 3:
-                out = self._act(ws, 'ladder', level + 1, pack.cout, 4)
-                self._apply(stream, raw, geo[level], pack.cout, norm, st, out)
-            else:
-                out = self._act(ws, 'res', 3, pack.cout, 1)
-                want_lo, want8 = planes_for(first_conv_of(0), also_lo=True)   # residual stream: always hi + lo
-                self._apply(stream, raw, geo[level], pack.cout, norm, st, out, want_lo=want_lo, want8=want8)
-            a = out
         g3 = geo[3]
-        res = a
+        if from_activation:
+            # externally produced activation (e.g. the MLR merge): NCHW fp32 -> fp16 hi/lo padded-flat planes
+            res = ws['act'].get('ext')
+            if res is None:   # cl_nchw_to_pf always writes both planes, whatever the precision mode
+                res = ws['act']['ext'] = _PF(g3, cin, 1, 2, dev)
+            _lib.check(self._lib.cl_nchw_to_pf(image.data_ptr(), 0, res.h16.data_ptr(), batch, cin, h, w, 1, stream))
+            self.launches += 1
+        else:
+            # ---- stem: conv1 (+ norm1) + relu, written as the 4-phase input of conv2
+            conv1, norm1 = convs[roles['conv1']]
+            if conv1.out_channels != 32 or (norm1 is not None and norm1.num_groups != 32):
+                raise RuntimeError('crossloc_b200: the stem kernel is built for 32 channels / 32 groups')
+            a = self._act(ws, 'stem', 1, 32, 4)
+            st = next_stats() if norm1 is not None else None
+            e0 = self._tick()
+            _lib.check(self._lib.cl_stem_forward(
+                image.data_ptr(), batch, cin, h, w, conv1.weight.detach().contiguous().data_ptr(),
+                conv1.bias.detach().contiguous().data_ptr(), 1 if norm1 is not None else 0,
+                0 if st is None else st.data_ptr(), 0 if norm1 is None else norm1.weight.data_ptr(),
+                0 if norm1 is None else norm1.bias.data_ptr(), 1e-5 if norm1 is None else float(norm1.eps),
+                a.h16.data_ptr(), self.terms, stream))
+            self._tock(e0, 'stem', ('stem',), 2.0 * batch * h * w * 32 * cin * 9)
+            self.launches += 2 if norm1 is not None else 1
+
+            # ---- strided ladder conv2..conv4
+            for level, role in ((1, 'conv2'), (2, 'conv3'), (3, 'conv4')):
+                name = roles[role]
+                conv, norm = convs[name]
+                pack = packs[name]
+                raw = self._raw(ws, 'ladder', level, pack.cout)
+                st = next_stats() if norm is not None else None
+                self._conv(stream, pack, a, geo[level], raw, st, groups_of(norm, pack.cout), name)
+                if level < 3:
+                    out = self._act(ws, 'ladder', level + 1, pack.cout, 4)
+                    self._apply(stream, raw, geo[level], pack.cout, norm, st, out)
+                else:
+                    out = self._act(ws, 'res', 3, pack.cout, 1)
+                    want_lo, want8 = planes_for(first_conv_of(0), also_lo=True)   # residual stream: always hi + lo
+                    self._apply(stream, raw, geo[level], pack.cout, norm, st, out, want_lo=want_lo, want8=want8)
+                a = out
+            res = a
 
         rot = {}
 
@@ -367,6 +389,10 @@ class CoordNetEngine:
                     res = out
             else:
                 raise AssertionError(kind)
+
+        if spec.get('output', 'head') == 'activation':
+            from . import layout
+            return layout.from_pf(res.h16, batch, g3.H, g3.W, self.terms)
 
         # ---- head
         head = spec['head']

@@ -180,11 +180,12 @@ class TransPoseNetEncoder(nn.Module):
             self.add_module('enc_add_res_block{:d}'.format(i + 1), block)
 
     def plan(self, prefix):
-        """(layers, blocks) of this encoder for the native engine; names are state-dict prefixes."""
+        """(layers, blocks, roles) of this encoder for the native engine; names are state-dict keys under `prefix`."""
         pairs = [('conv1', 'norm1'), ('conv2', 'norm2'), ('conv3', 'norm3'), ('conv4', 'norm4'),
                  ('res1_conv1', 'res1_norm1'), ('res1_conv2', 'res1_norm2'), ('res1_conv3', 'res1_norm3'),
                  ('res2_conv1', 'res2_norm1'), ('res2_conv2', 'res2_norm2'), ('res2_conv3', 'res2_norm3')]
-        layers = [(c if c.startswith('conv') else prefix + c, getattr(self, c), getattr(self, n)) for c, n in pairs]
+        layers = [(prefix + c, getattr(self, c), getattr(self, n)) for c, n in pairs]
+        roles = {r: prefix + r for r in ('conv1', 'conv2', 'conv3', 'conv4')}
         res2 = {'kind': 'residual', 'convs': [prefix + 'res2_conv%d' % i for i in (1, 2, 3)]}
         if not self.tiny:
             layers.append((prefix + 'res2_skip', self.res2_skip, self.res2_skip_norm))
@@ -194,7 +195,7 @@ class TransPoseNetEncoder(nn.Module):
             names = [prefix + 'enc_add_res_block%d.%d' % (i + 1, j) for j in (0, 3, 6)]
             layers += [(names[k], block[3 * k], block[3 * k + 1]) for k in range(3)]
             blocks.append({'kind': 'residual', 'convs': names})
-        return layers, blocks
+        return layers, blocks, roles
 
     def forward_reference(self, inputs, conv=_torch_conv):
         if inputs.size(0) == 0:
@@ -369,9 +370,28 @@ class TransPoseNet(nn.Module):
                           tiny, grayscale, full_size_output, num_mlr, enc_add_res_block, dec_add_res_block, count))
 
     def _spec(self):
-        enc_layers, enc_blocks = self.encoder.plan('encoder.')
+        enc_layers, enc_blocks, roles = self.encoder.plan('encoder.')
         dec_layers, dec_blocks, head = self.decoder.plan('decoder.')
-        return {'group_norm': True, 'layers': enc_layers + dec_layers, 'blocks': enc_blocks + dec_blocks, 'head': head}
+        return {'group_norm': True, 'layers': enc_layers + dec_layers, 'blocks': enc_blocks + dec_blocks, 'head': head,
+                'roles': roles}
+
+    def _forward_mlr(self, inputs):
+        """MLR model (networks.py:482-494): every encoder and the decoder run their fused plans; the merge in between
+        (1536-channel GroupNorm, mlr_skip, mlr_forward) runs its convolutions on the tensor-core kernels with stock
+        GroupNorm -- 89 % of the FLOPs are in the fused parts."""
+        acts = []
+        for i, enc in enumerate(self.mlr_encoder_ls):
+            layers, blocks, roles = enc.plan('mlr_encoder_%d.' % (i + 1))
+            acts.append(self._engine.forward({'group_norm': True, 'layers': layers, 'blocks': blocks, 'roles': roles,
+                                              'output': 'activation'}, inputs))
+        mlr = torch.cat(acts, dim=1)
+        conv = native_train.conv2d
+        res = _run_block(self.mlr_skip, mlr, conv)
+        mlr = _run_block(self.mlr_forward, self.mlr_norm(mlr), conv)
+        res = F.relu(res + mlr)
+        dec_layers, dec_blocks, head = self.decoder.plan('decoder.')
+        return self._engine.forward({'group_norm': True, 'layers': dec_layers, 'blocks': dec_blocks, 'head': head,
+                                     'input': 'activation'}, res)
 
     def forward_reference(self, inputs, conv=_torch_conv):
         up_height, up_width = inputs.size()[2:4]
@@ -395,12 +415,14 @@ class TransPoseNet(nn.Module):
     def forward(self, inputs):
         if not _native_ok(self, inputs):
             return self.forward_train(inputs)
-        if self.num_mlr != 0 or self.full_size_output:
-            # MLR multi-encoder / full-size DUC variants have no fused plan yet:
-            # their convolutions still run on the tensor-core kernels, GroupNorm / concat / PixelShuffle are torch ops
-            return self.forward_train(inputs)
         if self._engine is None:
             self._engine = CoordNetEngine()
+        if self.full_size_output:
+            # full-size DUC variant: no fused plan yet -- its convolutions run on the
+            # tensor-core kernels, GroupNorm / PixelShuffle / bilinear resize are torch ops
+            return self.forward_train(inputs)
+        if self.num_mlr != 0:
+            return self._forward_mlr(inputs)
         return self._engine.forward(self._spec(), inputs)
 
 

@@ -269,8 +269,8 @@ def test_precision_modes():
 
 
 def test_mlr_and_fullsize_variants_run_on_native_convolutions():
-    """The paper's MLR model (3 encoders) and the full-size DUC head: no fused plan yet, but forward() works and
-    its convolutions (incl. the 1536-channel ones) run on the tensor-core kernels; parity vs plain torch."""
+    """The paper's MLR model (3 encoders) and the full-size DUC head. MLR: fused encoders + fused decoder, merge on the
+    native convolutions (incl. the 1536-channel ones); full-size: native convolutions; parity vs plain torch."""
     import networks.networks as nets
     torch.manual_seed(9)
     x = torch.rand(1, 3, 64, 96, device=DEV)
@@ -281,3 +281,24 @@ def test_mlr_and_fullsize_variants_run_on_native_convolutions():
             ref = net.forward_reference(x)
         assert out.shape == ref.shape
         assert rel_l2(out[:, :3], ref[:, :3]) < 1e-3
+
+
+def test_mlr_fused_plan_matches_reference_math():
+    """MLR forward (networks.py:482-494) = 3 fused encoder plans -> cat -> merge -> fused decoder plan: batch 2 at a
+    ragged resolution, uncertainty channel included, and identical to the all-native-convolution training path."""
+    import networks.networks as nets
+    torch.manual_seed(10)
+    net = nets.TransPoseNet(torch.tensor([1.0, -2.0, 3.0]), False, False, 1, 1, 3, 1, num_mlr=3).eval().to(DEV)
+    x = torch.rand(2, 3, 120, 136, device=DEV)
+    with torch.no_grad():
+        out = net(x)
+        ref = net.forward_reference(x)
+        via_train = net.forward_train(x)
+    assert out.shape == ref.shape == (2, 4, 15, 17)
+    assert rel_l2(out[:, :3], ref[:, :3]) < 2e-4
+    assert rel_l2(out[:, 3:], ref[:, 3:]) < 1e-3
+    assert rel_l2(out[:, :3], via_train[:, :3]) < 2e-4
+    launches = net._engine.launches
+    with torch.no_grad():
+        out2 = net(x)
+    assert torch.equal(out, out2) and net._engine.launches > launches
