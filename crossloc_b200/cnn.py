@@ -27,7 +27,7 @@ def _nterms_for(precision, cin, ksize, stride):
     """MMA scheme of one convolution: 1 = fp16, 2 = fp16 + e4m3 corrections, 3 = fp16x3."""
     if precision == 'fp16x1':
         return 1
-    if precision == 'fp16+fp8' and ksize == 3 and stride == 1 and cin % 64 == 0 and cin >= 256:
+    if precision == 'fp16+fp8' and ksize == 3 and stride == 1 and cin % 128 == 0 and cin >= 256:
         return 2
     return 3
 

@@ -42,6 +42,7 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kThreads = 256;
 constexpr int kMaxStages = 8;
+constexpr int kCorrShift = 14;   // conv.h kCorrScale = 2^-14
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kStageChunkBytes = 32 * 32 * 4;   // one epilogue staging chunk: 32 rows x 32 fp32
 constexpr uint32_t kEpilogueStagingBytes = 4 * 2 * kStageChunkBytes;
@@ -413,6 +414,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Here two CTAs form one 256 x 256 tile: each keeps its own 128 pixel rows and only HALF of the weight tile,
 // the MMA unit of the pair reads the other half from the peer.  Per CTA and stage: half the weight bytes from
 // L2, 8 KB instead of 12 KB of smem reads per MMA, three pipeline stages instead of two.
+// fp16 + fp8 mode: a tile first accumulates BOTH e4m3 correction products over all k-blocks (they carry 2^14),
+// then the fp16 main product; the first main MMA folds the corrections with scale-input-d (D = A*B + D * 2^-14).
+// One 256-column accumulator per tile instead of two, so the accumulator is double-buffered and the epilogue of a
+// tile overlaps the MMAs of the next one.  A stage holds 2 * BK channels of the e4m3 planes (128-byte rows, 4 boxes)
+// or of the fp16 planes (4 boxes): fewer, wider TMA rows than interleaving both in every stage.
 // Protocol (leader = even CTA of the pair): both CTAs' producers load with the 2-SM TMA form that signals the
 // LEADER's full barrier; the leader's MMA warp issues for the pair and releases stages / publishes accumulators
 // with tcgen05.commit multicast to both CTAs; both epilogues signal the leader's accumulator-empty barrier.
@@ -479,30 +485,42 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             uint32_t phase = 0;
             const uint32_t tx_pair = 2u * (uint32_t)nA * (p.a_bytes + w_half);
             const int w_rows = p.BN / 2;
+            // fp16 + fp8: a stage covers 2 * BK input channels -- pass 0 streams the e4m3 planes (128-byte rows, one box
+            // per plane), pass 1 the fp16 planes (two boxes per operand); the stage size is the same in both passes
+            const int kstep = f8c ? 2 : 1;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
                 const int n0 = (tile % p.tiles_n) * p.BN;
-                for (int tap = 0; tap < p.num_taps; tap++) {
-                    const int a_row = p.tap_a_row[tap] + m0;
-                    const int w_row = tap * p.w_tap_rows + n0 + (int)crank * w_rows;
-                    for (int kb = 0; kb < p.kblocks_per_tap; kb++) {
-                        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
-                        const uint32_t bar = ptx::smem_u32(&full_bar[stage]);   // resolved to the leader's copy by the load
-                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
-                        const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
-                        if (leader) ptx::mbar_expect_tx(bar, tx_pair);
-                        ptx::tma_load_2d_pair(sa, &tmA, bar, kb * BK, a_row);
-                        ptx::tma_load_2d_pair(sw, &tmW, bar, kb * BK, w_row);
-                        if (f8c) {
-                            ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA8, bar, kb * BK, p.a8_lo_rows + a_row);         // a_lo8
-                            ptx::tma_load_2d_pair(sa + p.a_bytes + p.a_bytes / 2, &tmA8, bar, kb * BK, a_row);       // a_hi8
-                            ptx::tma_load_2d_pair(sw + w_half, &tmW8, bar, kb * BK, w_row);                          // w_hi8
-                            ptx::tma_load_2d_pair(sw + w_half + w_half / 2, &tmW8, bar, kb * BK, p.w_lo_rows + w_row); // w_lo8
-                        } else if (nA == 2) {
-                            ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA, bar, kb * BK, p.a_lo_rows + a_row);
-                            ptx::tma_load_2d_pair(sw + w_half, &tmW, bar, kb * BK, p.w_lo_rows + w_row);
+                for (int pass = f8c ? 0 : 1; pass < 2; pass++) {
+                    for (int tap = 0; tap < p.num_taps; tap++) {
+                        const int a_row = p.tap_a_row[tap] + m0;
+                        const int w_row = tap * p.w_tap_rows + n0 + (int)crank * w_rows;
+                        for (int kb = 0; kb < p.kblocks_per_tap; kb += kstep) {
+                            ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                            const uint32_t bar = ptx::smem_u32(&full_bar[stage]);   // resolved to the leader's copy by the load
+                            const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                            const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
+                            if (leader) ptx::mbar_expect_tx(bar, tx_pair);
+                            if (pass == 0) {
+                                ptx::tma_load_2d_pair(sa, &tmA8, bar, kb * BK, p.a8_lo_rows + a_row);           // a_lo8
+                                ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA8, bar, kb * BK, a_row);              // a_hi8
+                                ptx::tma_load_2d_pair(sw, &tmW8, bar, kb * BK, w_row);                          // w_hi8
+                                ptx::tma_load_2d_pair(sw + w_half, &tmW8, bar, kb * BK, p.w_lo_rows + w_row);   // w_lo8
+                            } else if (f8c) {
+                                ptx::tma_load_2d_pair(sa, &tmA, bar, kb * BK, a_row);
+                                ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA, bar, (kb + 1) * BK, a_row);
+                                ptx::tma_load_2d_pair(sw, &tmW, bar, kb * BK, w_row);
+                                ptx::tma_load_2d_pair(sw + w_half, &tmW, bar, (kb + 1) * BK, w_row);
+                            } else {
+                                ptx::tma_load_2d_pair(sa, &tmA, bar, kb * BK, a_row);
+                                ptx::tma_load_2d_pair(sw, &tmW, bar, kb * BK, w_row);
+                                if (nA == 2) {
+                                    ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA, bar, kb * BK, p.a_lo_rows + a_row);
+                                    ptx::tma_load_2d_pair(sw + w_half, &tmW, bar, kb * BK, p.w_lo_rows + w_row);
+                                }
+                            }
+                            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                         }
-                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
@@ -519,32 +537,50 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aphase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.BN);
-                for (int kbi = 0; kbi < kblocks; kbi++) {
+                const int nstages_tile = f8c ? kblocks / 2 : kblocks;
+                if (f8c) {
+                    // pass 0: both correction products (scaled by 2^14) of 2 * BK input channels per stage
+                    for (int kbi = 0; kbi < nstages_tile; kbi++) {
+                        ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                        ptx::tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t a8lo = smem_base + (uint32_t)stage * p.stage_bytes, a8hi = a8lo + p.a_bytes;
+                            const uint32_t w8hi = a8lo + 2u * p.a_bytes, w8lo = w8hi + w_half;
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++) {
+                                const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(a8lo + k * 32);
+                                const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(w8hi + k * 32);
+                                ptx::mma_f8_ss_pair(tmem_d, da, db, idesc, (kbi | k) != 0 ? 1u : 0u);
+                            }
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++) {
+                                const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(a8hi + k * 32);
+                                const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(w8lo + k * 32);
+                                ptx::mma_f8_ss_pair(tmem_d, da, db, idesc, 1u);
+                            }
+                            ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 0x3);
+                        }
+                        __syncwarp();
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                for (int kbi = 0; kbi < nstages_tile; kbi++) {
                     ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
                     ptx::tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                         const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
                         if (f8c) {
+                            // pass 1: the fp16 product; its first MMA rescales the corrections: D = A*B + D * 2^-14
 #pragma unroll
-                            for (int k = 0; k < BK / 16; k++) {
-                                const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(sa + k * 32);
-                                const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(sw + k * 32);
-                                ptx::mma_f16_ss_pair(tmem_d, da, db, idesc, (kbi | k) != 0 ? 1u : 0u);
-                            }
-                            const uint32_t a8lo = sa + p.a_bytes, a8hi = a8lo + p.a_bytes / 2;
-                            const uint32_t w8hi = sw + w_half, w8lo = w8hi + w_half / 2;
+                            for (int half = 0; half < 2; half++) {
 #pragma unroll
-                            for (int k = 0; k < BK / 32; k++) {
-                                const uint64_t da = ptx::make_kmajor_desc<kSwizzle / 2>(a8lo + k * 32);
-                                const uint64_t db = ptx::make_kmajor_desc<kSwizzle / 2>(w8hi + k * 32);
-                                ptx::mma_f8_ss_pair(tmem_d + (uint32_t)p.BN, da, db, idesc, (kbi | k) != 0 ? 1u : 0u);
-                            }
-#pragma unroll
-                            for (int k = 0; k < BK / 32; k++) {
-                                const uint64_t da = ptx::make_kmajor_desc<kSwizzle / 2>(a8hi + k * 32);
-                                const uint64_t db = ptx::make_kmajor_desc<kSwizzle / 2>(w8lo + k * 32);
-                                ptx::mma_f8_ss_pair(tmem_d + (uint32_t)p.BN, da, db, idesc, 1u);
+                                for (int k = 0; k < BK / 16; k++) {
+                                    const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(sa + half * p.a_bytes + k * 32);
+                                    const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(sw + half * w_half + k * 32);
+                                    if (kbi == 0 && half == 0 && k == 0) ptx::mma_f16_ss_pair_scaled_d<kCorrShift>(tmem_d, da, db, idesc);
+                                    else ptx::mma_f16_ss_pair(tmem_d, da, db, idesc, 1u);
+                                }
                             }
                         } else {
                             for (int term = 0; term < p.nterms; term++) {
@@ -559,7 +595,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             }
                         }
                         ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 0x3);            // frees the stage in both CTAs
-                        if (kbi == kblocks - 1) ptx::mma_commit_pair(ptx::smem_u32(&tfull_bar[as]), 0x3);   // accumulators ready
+                        if (kbi == nstages_tile - 1) ptx::mma_commit_pair(ptx::smem_u32(&tfull_bar[as]), 0x3);   // accumulators ready
                     }
                     __syncwarp();
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
@@ -590,7 +626,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
-            epilogue_tile(p, &tmO, taddr, m0, n0, q, lane, stage_base, chunk_no, f8c, valid, image);
+            epilogue_tile(p, &tmO, taddr, m0, n0, q, lane, stage_base, chunk_no, false, valid, image);   // corrections already folded
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -847,13 +883,16 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     p.raw = d.raw; p.bias = d.bias; p.stats = d.stats;
     p.a_bytes = (uint32_t)(kBlockM * BK * 2);
     p.w_bytes = (uint32_t)(BN * BK * 2);
-    p.stage_bytes = (uint32_t)nA * (p.a_bytes + (pair ? p.w_bytes / 2 : p.w_bytes));   // a CTA pair splits the weight tile
+    // a CTA pair splits the weight tile (in fp16 + fp8 mode its stages hold the e4m3 planes OR the fp16 planes of 2 * BK channels)
+    p.stage_bytes = (uint32_t)nA * (p.a_bytes + (pair ? p.w_bytes / 2 : p.w_bytes));
     const int smem_budget = 227 * 1024 - 2048 - (int)kEpilogueStagingBytes;
     p.num_stages = smem_budget / (int)p.stage_bytes;
     if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
     if (p.num_stages < 2) return "conv_igemm: tile does not fit two pipeline stages";
-    // fp16 + fp8 mode keeps two accumulators (main, corrections) per tile
-    p.accum_stages = (d.nterms == 2 ? 4 : 2) * BN <= (int)kTmemCols ? 2 : 1;
+    // fp16 + fp8 mode keeps two accumulators (main, corrections) per tile in the single-CTA kernel; the pair kernel
+    // folds the corrections with scale-input-d and needs one
+    if (d.nterms == 2 && d.corr_scale != 1.0f / (float)(1 << kCorrShift)) return "conv_igemm: corr_scale must be 2^-14";
+    p.accum_stages = (d.nterms == 2 && !pair ? 4 : 2) * BN <= (int)kTmemCols ? 2 : 1;
     const size_t smem = (size_t)p.num_stages * p.stage_bytes + kEpilogueStagingBytes + 1024;
 
     CUtensorMap tmA, tmW, tmO;
@@ -865,9 +904,12 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
         return "conv_igemm: cuTensorMapEncodeTiled failed for the output matrix";
     CUtensorMap tmA8 = tmA, tmW8 = tmW;
     if (d.nterms == 2) {
-        if (!make_tensor_map(&tmA8, d.act8, (uint64_t)d.a8_total_rows, (uint64_t)d.Cin, kBlockM, BK, 1))
+        // the pair kernel streams the e4m3 planes in 128-byte rows (2 * BK channels per box)
+        const int bk8 = pair ? 2 * BK : BK;
+        if (pair && (d.Cin % 128 != 0)) return "conv_igemm: the fp16 + fp8 mode of the CTA-pair kernel needs Cin % 128 == 0";
+        if (!make_tensor_map(&tmA8, d.act8, (uint64_t)d.a8_total_rows, (uint64_t)d.Cin, kBlockM, bk8, 1))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the e4m3 activation matrix";
-        if (!make_tensor_map(&tmW8, d.weights8, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, BK, 1))
+        if (!make_tensor_map(&tmW8, d.weights8, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, bk8, 1))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the e4m3 weight matrix";
     }
 

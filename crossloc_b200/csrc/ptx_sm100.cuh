@@ -225,6 +225,17 @@ __device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D = A * B + D * 2^-SHIFT (scale-input-d, kind::f16 only): folds an accumulator that carries a power-of-two scale
+template <int SHIFT>
+__device__ __forceinline__ void mma_f16_ss_pair_scaled_d(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(SHIFT)
+        : "memory");
+}
 __device__ __forceinline__ void mma_f8_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
