@@ -48,6 +48,10 @@ SIGNATURES = {
     'cl_head_forward': (_c.c_int, [
         _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
         _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p]),
+    'cl_duc_head_forward': (_c.c_int, [
+        _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+        _c.c_void_p, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_float, _c.c_float,
+        _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
 }
 
 _lib = None

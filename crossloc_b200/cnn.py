@@ -21,13 +21,14 @@ from . import _lib
 PRECISION = os.environ.get('CROSSLOC_B200_CONV_PRECISION', 'fp16+fp8')
 _PRECISIONS = ('fp16+fp8', 'fp16x3', 'fp16x1')
 _W8_LO_SCALE = 4096.0   # csrc/conv.h kW8LoScale
+_FP8_1X1 = os.environ.get('CROSSLOC_B200_FP8_1X1', '1') != '0'   # 1x1 512->512 layers in the fp16 + fp8 scheme too
 
 
 def _nterms_for(precision, cin, ksize, stride):
     """MMA scheme of one convolution: 1 = fp16, 2 = fp16 + e4m3 corrections, 3 = fp16x3."""
     if precision == 'fp16x1':
         return 1
-    if precision == 'fp16+fp8' and ksize == 3 and stride == 1 and cin % 128 == 0 and cin >= 256:
+    if precision == 'fp16+fp8' and stride == 1 and cin % 128 == 0 and cin >= 256 and (ksize == 3 or (_FP8_1X1 and cin >= 512)):
         return 2
     return 3
 
@@ -267,10 +268,12 @@ class CoordNetEngine:
             want_lo = also_lo or any(packs[c].nterms == 3 for c in consumers)
             return want_lo, want8
 
+        duc = spec.get('head', {}).get('duc') if spec.get('output', 'head') == 'head' else None
+
         def first_conv_of(block_index):
             """Name(s) of the convolution(s) that read the residual stream entering block `block_index`."""
             if block_index >= len(blocks):
-                return []
+                return [duc['name']] if duc else []
             blk = blocks[block_index]
             return [blk['convs'][0]] + ([blk['skip']] if blk['kind'] == 'residual_skip' else [])
 
@@ -398,6 +401,28 @@ class CoordNetEngine:
         head = spec['head']
         hconv = head['conv']
         co = hconv.out_channels
+        if duc:
+            # full-size variant (networks.py:344-349): DUC 3x3 convolution on the tensor cores, then one kernel for
+            # GroupNorm + ReLU + PixelShuffle + bilinear resize + fc3 + output maps
+            dconv, dnorm = convs[duc['name']]
+            dpack = packs[duc['name']]
+            raw = self._raw(ws, 'duc', 3, dpack.cout)
+            st = next_stats()
+            self._conv(stream, dpack, res, g3, raw, st, groups_of(dnorm, dpack.cout), duc['name'])
+            up_h, up_w = duc['size']
+            out = torch.empty(batch, co, up_h, up_w, dtype=torch.float32, device=dev)
+            mean = head['mean'].to(device=dev, dtype=torch.float32).contiguous()
+            e0 = self._tick()
+            _lib.check(self._lib.cl_duc_head_forward(
+                raw.data_ptr(), batch, g3.H, g3.W, dpack.cout, co, duc['rate'], groups_of(dnorm, dpack.cout),
+                st.data_ptr(), dnorm.weight.data_ptr(), dnorm.bias.data_ptr(), float(dnorm.eps),
+                hconv.weight.detach().reshape(co, -1).contiguous().data_ptr(), hconv.bias.detach().contiguous().data_ptr(),
+                mean.data_ptr(), head['num_task'], head['clamp'][0], head['clamp'][1], out.data_ptr(), up_h, up_w,
+                stream))
+            self._tock(e0, 'duc_head', ('duc_head',), 0.0)
+            self.launches += 1
+            self._keepalive = (mean,)
+            return out
         out = torch.empty(batch, co, g3.H, g3.W, dtype=torch.float32, device=dev)
         mean = head['mean'].to(device=dev, dtype=torch.float32).contiguous()
         e0 = self._tick()

@@ -193,3 +193,18 @@ extern "C" int cl_head_forward(const void* act, int64_t act_lo_rows, int in_term
     d.clamp_lo = clamp_lo; d.clamp_hi = clamp_hi; d.out = out;
     return finish(kFn, cl::head_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
+
+extern "C" int cl_duc_head_forward(const float* raw, int B, int Hc, int Wc, int C, int Co, int rate, int group_ch,
+                                   const double* stats, const float* gamma, const float* beta, float eps,
+                                   const float* weight, const float* bias, const float* mean, int num_task,
+                                   float clamp_lo, float clamp_hi, float* out, int Ho, int Wo, void* cuda_stream)
+{
+    static const char* kFn = "cl_duc_head_forward";
+    NEED_DEV(raw); NEED_DEV(stats); NEED_DEV(gamma); NEED_DEV(beta); NEED_DEV(weight); NEED_DEV(bias); NEED_DEV(out);
+    if (num_task > 0) NEED_DEV(mean);
+    cl::DucHeadDesc d{};
+    d.raw = raw; d.B = B; d.Hc = Hc; d.Wc = Wc; d.C = C; d.Co = Co; d.rate = rate; d.group_ch = group_ch;
+    d.stats = stats; d.gamma = gamma; d.beta = beta; d.eps = eps; d.weight = weight; d.bias = bias; d.mean = mean;
+    d.num_task = num_task; d.clamp_lo = clamp_lo; d.clamp_hi = clamp_hi; d.out = out; d.Ho = Ho; d.Wo = Wo;
+    return finish(kFn, cl::duc_head_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}

@@ -444,6 +444,79 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadDesc d)
     }
 }
 
+// Full-size output head (networks.py:259-273, 344-358): GroupNorm + ReLU of the DUC convolution, PixelShuffle(rate),
+// bilinear resize (align_corners = False, as F.interpolate) to the frame size, 1x1 fc3, mean offset / exp(clamp).
+// One thread per output pixel; the shuffled map is never materialised: a source value at (c, sy, sx) is channel
+// c * rate^2 + (sy % rate) * rate + sx % rate of cell (sy / rate, sx / rate) of the raw DUC output.
+constexpr int kDucThreads = 256;
+constexpr int kDucMaxCo = 8;
+
+__global__ void __launch_bounds__(kDucThreads) duc_head_kernel(DucHeadDesc d)
+{
+    extern __shared__ float2 duc_tab[];   // [B][groups] (mean, rstd)
+    const int groups = d.C / d.group_ch;
+    const double count = (double)d.group_ch * d.Hc * d.Wc;
+    for (int i = threadIdx.x; i < d.B * groups; i += kDucThreads) {
+        float mean, rstd;
+        mean_rstd(d.stats, i / groups, groups, i % groups, count, d.eps, mean, rstd);
+        duc_tab[i] = make_float2(mean, rstd);
+    }
+    __syncthreads();
+    const int Wp = d.Wc + 2, plane = (d.Hc + 2) * Wp;
+    const int Hs = d.Hc * d.rate, Ws = d.Wc * d.rate, r2 = d.rate * d.rate;
+    const float rh = (float)Hs / (float)d.Ho, rw = (float)Ws / (float)d.Wo;   // area_pixel_compute_scale
+    const long long total = (long long)d.B * d.Ho * d.Wo;
+    for (long long pix = blockIdx.x * (long long)kDucThreads + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * kDucThreads) {
+        const int X = (int)(pix % d.Wo);
+        const int Y = (int)((pix / d.Wo) % d.Ho);
+        const int b = (int)(pix / ((long long)d.Wo * d.Ho));
+        const float sy = fmaxf(rh * ((float)Y + 0.5f) - 0.5f, 0.f), sx = fmaxf(rw * ((float)X + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+        const float ly = sy - (float)y0, lx = sx - (float)x0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float2* tab = duc_tab + b * groups;
+        auto fetch = [&](int c, int yy, int xx) -> float {
+            const int ch = c * r2 + (yy % d.rate) * d.rate + (xx % d.rate);
+            const size_t row = (size_t)b * plane + (size_t)(yy / d.rate + 1) * Wp + (xx / d.rate + 1);
+            const float2 mr = tab[ch / d.group_ch];
+            const float v = (__ldg(d.raw + row * d.C + ch) - mr.x) * (mr.y * __ldg(d.gamma + ch)) + __ldg(d.beta + ch);
+            return fmaxf(v, 0.f);
+        };
+        float val[kDucMaxCo];
+#pragma unroll
+        for (int c = 0; c < kDucMaxCo; c++) {
+            if (c < d.Co) {
+                // same expression order as ATen's upsample_bilinear2d kernel
+                const float v00 = fetch(c, y0, x0);
+                const float v01 = lx != 0.f ? fetch(c, y0, x1) : v00;
+                float bottom = 0.f;
+                if (ly != 0.f) {
+                    const float v10 = fetch(c, y1, x0);
+                    const float v11 = lx != 0.f ? fetch(c, y1, x1) : v10;
+                    bottom = ly * (hx * v10 + lx * v11);
+                }
+                val[c] = hy * (hx * v00 + lx * v01) + bottom;
+            } else {
+                val[c] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kDucMaxCo; k++) {
+            if (k < d.Co) {
+                float r = __ldg(d.bias + k);
+#pragma unroll
+                for (int c = 0; c < kDucMaxCo; c++)
+                    if (c < d.Co) r = fmaf(__ldg(d.weight + k * d.Co + c), val[c], r);
+                if (k < d.num_task) r += __ldg(d.mean + k);
+                else r = expf(fminf(fmaxf(r, d.clamp_lo), d.clamp_hi));
+                d.out[(((size_t)b * d.Co + k) * d.Ho + Y) * d.Wo + X] = r;
+            }
+        }
+    }
+}
+
 int sm_count()
 {
     int dev = 0, sms = 148;
@@ -521,6 +594,23 @@ const char* head_launch(const HeadDesc& d, cudaStream_t stream)
     if (blocks > cap) blocks = cap;
     if (d.Co <= 4) head_kernel<4><<<(unsigned)blocks, kHeadThreads, 0, stream>>>(d);
     else head_kernel<8><<<(unsigned)blocks, kHeadThreads, 0, stream>>>(d);
+    return last_error();
+}
+
+const char* duc_head_launch(const DucHeadDesc& d, cudaStream_t stream)
+{
+    if (d.Co < 1 || d.Co > kDucMaxCo) return "duc_head: 1..8 output channels";
+    if (d.rate < 1 || d.C != d.Co * d.rate * d.rate) return "duc_head: C must be Co * rate^2";
+    if (d.group_ch < 1 || d.C % d.group_ch != 0) return "duc_head: the DUC convolution is followed by a GroupNorm";
+    if (d.Ho < 1 || d.Wo < 1) return "duc_head: empty output";
+    const long long total = (long long)d.B * d.Ho * d.Wo;
+    if (total == 0) return nullptr;
+    const size_t smem = (size_t)d.B * (d.C / d.group_ch) * sizeof(float2);
+    if (smem > 48 * 1024) return "duc_head: batch * groups exceeds the 48 KB statistics table";
+    long long blocks = (total + kDucThreads - 1) / kDucThreads;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    duc_head_kernel<<<(unsigned)blocks, kDucThreads, smem, stream>>>(d);
     return last_error();
 }
 

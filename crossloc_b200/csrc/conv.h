@@ -193,4 +193,23 @@ struct HeadDesc {
 };
 const char* head_launch(const HeadDesc& d, cudaStream_t stream);
 
+// ---------------------------------------------------------------- full-size head: GN + ReLU + PixelShuffle + bilinear + fc3
+struct DucHeadDesc {
+    const float* raw;       // fp32 PF [B*(Hc+2)*(Wc+2)][C] raw output of the DUC convolution, C = Co * rate^2
+    int B, Hc, Wc, C, Co, rate;
+    int group_ch;           // channels per GroupNorm group of the DUC norm
+    const double* stats;    // [B][C/group_ch][2]
+    const float* gamma;
+    const float* beta;
+    float eps;
+    const float* weight;    // fc3 fp32 [Co][Co]
+    const float* bias;      // [Co]
+    const float* mean;      // [num_task]
+    int num_task;
+    float clamp_lo, clamp_hi;
+    float* out;             // NCHW fp32 [B][Co][Ho][Wo]
+    int Ho, Wo;             // frame size the shuffled (Hc*rate, Wc*rate) map is resized to
+};
+const char* duc_head_launch(const DucHeadDesc& d, cudaStream_t stream);
+
 }  // namespace cl

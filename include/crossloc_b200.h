@@ -171,6 +171,19 @@ int cl_head_forward(const void* act, int64_t act_lo_rows, int in_terms, int B, i
                     const float* weight, const float* bias, const float* mean, int num_task, float clamp_lo,
                     float clamp_hi, float* out, void* cuda_stream);
 
+/*
+ * Full-size output head: GroupNorm + ReLU of the DUC convolution's raw output, PixelShuffle(rate), bilinear
+ * resize (align_corners = False) to (Ho, Wo), 1x1 fc3 (Co -> Co), mean offset on the task channels and
+ * exp(clamp()) on the rest; NCHW fp32 [B][Co][Ho][Wo] output.  The shuffled map is never materialised.
+ * Replaces DenseUpsamplingConvolution.forward after its convolution (networks.py:269-272), F.interpolate
+ * (:347) and fc3 / the output maps (:349-358) of the full_size_output decoder.
+ *   raw fp32 PF [B*(Hc+2)*(Wc+2)][C] with C = Co * rate^2 (cl_conv_igemm output), stats fp64 [B][C/group_ch][2].
+ */
+int cl_duc_head_forward(const float* raw, int B, int Hc, int Wc, int C, int Co, int rate, int group_ch,
+                        const double* stats, const float* gamma, const float* beta, float eps, const float* weight,
+                        const float* bias, const float* mean, int num_task, float clamp_lo, float clamp_hi,
+                        float* out, int Ho, int Wo, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

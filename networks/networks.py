@@ -287,6 +287,10 @@ class TransPoseNetDecoder(nn.Module):
         layers += [(prefix + 'fc1', self.fc1, self.fc1_norm), (prefix + 'fc2', self.fc2, self.fc2_norm)]
         blocks.append({'kind': 'plain', 'convs': [prefix + 'fc1', prefix + 'fc2']})
         head = {'conv': self.fc3, 'mean': self.mean, 'num_task': self.num_task_channel, 'clamp': _POS_CLAMP}
+        if self.full_size_output:
+            name = prefix + 'duc_upsample.conv'
+            layers.append((name, self.duc_upsample.conv, self.duc_upsample.norm))
+            head['duc'] = {'name': name, 'rate': self.duc_upsample.pixel_shuffle.upscale_factor}
         return layers, blocks, head
 
     def forward_reference(self, inputs, up_height=None, up_width=None, conv=_torch_conv):
@@ -369,9 +373,17 @@ class TransPoseNet(nn.Module):
                       'extra blocks enc {:d} / dec {:d}, trainable parameters {:,d}.'.format(
                           tiny, grayscale, full_size_output, num_mlr, enc_add_res_block, dec_add_res_block, count))
 
-    def _spec(self):
+    def _decoder_plan(self, inputs):
+        layers, blocks, head = self.decoder.plan('decoder.')
+        if 'duc' in head:   # the full-size head resizes to the frame size (networks.py:497-500)
+            if inputs is None:
+                raise RuntimeError('crossloc_b200: the full-size plan needs the input frame size')
+            head['duc']['size'] = (int(inputs.size(2)), int(inputs.size(3)))
+        return layers, blocks, head
+
+    def _spec(self, inputs=None):
         enc_layers, enc_blocks, roles = self.encoder.plan('encoder.')
-        dec_layers, dec_blocks, head = self.decoder.plan('decoder.')
+        dec_layers, dec_blocks, head = self._decoder_plan(inputs)
         return {'group_norm': True, 'layers': enc_layers + dec_layers, 'blocks': enc_blocks + dec_blocks, 'head': head,
                 'roles': roles}
 
@@ -389,7 +401,7 @@ class TransPoseNet(nn.Module):
         res = _run_block(self.mlr_skip, mlr, conv)
         mlr = _run_block(self.mlr_forward, self.mlr_norm(mlr), conv)
         res = F.relu(res + mlr)
-        dec_layers, dec_blocks, head = self.decoder.plan('decoder.')
+        dec_layers, dec_blocks, head = self._decoder_plan(inputs)
         return self._engine.forward({'group_norm': True, 'layers': dec_layers, 'blocks': dec_blocks, 'head': head,
                                      'input': 'activation'}, res)
 
@@ -417,13 +429,9 @@ class TransPoseNet(nn.Module):
             return self.forward_train(inputs)
         if self._engine is None:
             self._engine = CoordNetEngine()
-        if self.full_size_output:
-            # full-size DUC variant: no fused plan yet -- its convolutions run on the
-            # tensor-core kernels, GroupNorm / PixelShuffle / bilinear resize are torch ops
-            return self.forward_train(inputs)
         if self.num_mlr != 0:
             return self._forward_mlr(inputs)
-        return self._engine.forward(self._spec(), inputs)
+        return self._engine.forward(self._spec(inputs), inputs)
 
 
 class ProjHead(nn.Module):

@@ -23,6 +23,13 @@ CASES = {
     'transpose_tiny_gray': ('TransPoseNet', (torch.tensor([1., 2., 3.]), True, True, 1, 0, 3, 0), {}, 5, (2, 1, 40, 56), 2),
     'network_vanilla': ('Network', (torch.tensor([1., 2., 3.]), False), {}, 7, (1, 1, 48, 64), 3),
     'network_tiny': ('Network', (torch.tensor([0., 0., 0.]), True), {}, 8, (1, 1, 48, 64), 4),
+    # full-size DUC head (ragged size: the bilinear resize is not the identity) and MLR
+    'transpose_fullsize_ragged': ('TransPoseNet', (torch.tensor([1., -2., 3.]), False, False, 1, 1, 3, 1),
+                                  {'full_size_output': True}, 13, (2, 3, 52, 76), 5),
+    'transpose_fullsize_even': ('TransPoseNet', (torch.zeros(3), False, False, 0, 1, 3, 1),
+                                {'full_size_output': True}, 15, (1, 3, 64, 96), 7),
+    'transpose_mlr3_tiny': ('TransPoseNet', (torch.tensor([0.5, 0., -1.]), True, False, 1, 1, 3, 1),
+                            {'num_mlr': 3}, 14, (1, 3, 48, 64), 6),
 }
 
 

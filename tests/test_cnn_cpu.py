@@ -16,13 +16,20 @@ CASES = {
     'transpose_tiny_gray': ('TransPoseNet', (torch.tensor([1., 2., 3.]), True, True, 1, 0, 3, 0), 5, (2, 1, 40, 56), 2),
     'network_vanilla': ('Network', (torch.tensor([1., 2., 3.]), False), 7, (1, 1, 48, 64), 3),
     'network_tiny': ('Network', (torch.tensor([0., 0., 0.]), True), 8, (1, 1, 48, 64), 4),
+    'transpose_fullsize_ragged': ('TransPoseNet', (torch.tensor([1., -2., 3.]), False, False, 1, 1, 3, 1), 13, (2, 3, 52, 76), 5,
+                                  {'full_size_output': True}),
+    'transpose_fullsize_even': ('TransPoseNet', (torch.zeros(3), False, False, 0, 1, 3, 1), 15, (1, 3, 64, 96), 7,
+                                {'full_size_output': True}),
+    'transpose_mlr3_tiny': ('TransPoseNet', (torch.tensor([0.5, 0., -1.]), True, False, 1, 1, 3, 1), 14, (1, 3, 48, 64), 6,
+                            {'num_mlr': 3}),
 }
 
 
 def build_case(name, device='cpu'):
-    cls, args, wseed, shape, iseed = CASES[name]
+    cls, args, wseed, shape, iseed = CASES[name][:5]
+    kwargs = CASES[name][5] if len(CASES[name]) > 5 else {}
     torch.manual_seed(wseed)
-    net = getattr(nets, cls)(*args).eval().to(device)
+    net = getattr(nets, cls)(*args, **kwargs).eval().to(device)
     g = torch.Generator().manual_seed(iseed)
     x = torch.rand(*shape, generator=g).to(device)
     return net, x
