@@ -24,6 +24,7 @@ UNITS = {
     'dsac.cu': ['--fmad=false'],
     'cabi_cnn.cu': [],
     'conv_igemm.cu': [],
+    'conv_wgrad_pf.cu': [],
     'cnn_pointwise.cu': [],
     'train_layout.cu': [],
 }

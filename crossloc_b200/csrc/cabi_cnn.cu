@@ -208,3 +208,22 @@ extern "C" int cl_duc_head_forward(const float* raw, int B, int Hc, int Wc, int 
     d.num_task = num_task; d.clamp_lo = clamp_lo; d.clamp_hi = clamp_hi; d.out = out; d.Ho = Ho; d.Wo = Wo;
     return finish(kFn, cl::duc_head_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
+
+extern "C" int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const void* act, int64_t x_plane_rows, int Mp,
+                                int Cout, int Cin, int phases, int num_taps, const int32_t* tap_shift,
+                                const int32_t* tap_phase, int nterms, float out_scale, float* dw, void* cuda_stream)
+{
+    static const char* kFn = "cl_conv_wgrad_pf";
+    NEED_DEV(grad); NEED_DEV(act); NEED_DEV(dw);
+    if (!tap_shift || !tap_phase) return cl::fail(-1, "%s: tap tables must not be NULL", kFn);
+    if (num_taps < 1 || num_taps > 9) return cl::fail(-1, "%s: num_taps=%d out of range", kFn, num_taps);
+    if (Mp <= 0 || phases < 1 || phases > 4) return cl::fail(-1, "%s: invalid sizes", kFn);
+    for (int i = 0; i < num_taps; i++)
+        if (tap_phase[i] < 0 || tap_phase[i] >= phases) return cl::fail(-1, "%s: tap_phase[%d]=%d out of range", kFn, i, tap_phase[i]);
+    cl::ConvWgradPfDesc d{};
+    d.grad = grad; d.g_plane_rows = g_plane_rows; d.act = act; d.x_plane_rows = x_plane_rows; d.Mp = Mp; d.Cout = Cout;
+    d.Cin = Cin; d.phases = phases; d.num_taps = num_taps;
+    for (int i = 0; i < num_taps; i++) { d.tap_shift[i] = tap_shift[i]; d.tap_phase[i] = tap_phase[i]; }
+    d.nterms = nterms; d.out_scale = out_scale; d.dw = dw;
+    return finish(kFn, cl::conv_wgrad_pf_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}

@@ -89,6 +89,25 @@ struct ConvWgradParams {
     uint32_t a_bytes, w_bytes, stage_bytes;
 };
 
+// ---------------------------------------------------------------- weight gradient on padded-flat operands
+// dW[tap][co][ci] += out_scale * sum over PF rows r of dY[r][co] * X[tap_phase][r + tap_shift][ci]; both operands
+// are the [pixel rows][channels] matrices of the forward / GroupNorm-backward kernels (MN-major tensor-core operands).
+struct ConvWgradPfDesc {
+    const void* grad;       // dY fp16 PF [nA][g_plane_rows][Cout]: plane 0 = hi, plane 1 = lo; border rows are zero
+    int64_t g_plane_rows;   // row distance between the planes of dY
+    const void* act;        // X fp16 PF, plane (term * phases + phase) starts x_plane_rows * plane rows in
+    int64_t x_plane_rows;
+    int Mp;                 // rows of one plane: B * (H + 2) * (W + 2) at the OUTPUT resolution
+    int Cout, Cin, phases;  // phases 1, or 4 for a stride-2 convolution
+    int num_taps;
+    int tap_shift[9];       // row shift of X inside its plane for each tap
+    int tap_phase[9];       // phase plane of X for each tap
+    int nterms;             // 1 or 3
+    float out_scale;
+    float* dw;              // fp32 [tap][Cout][Cin], accumulated with atomics: caller zeroes it
+};
+const char* conv_wgrad_pf_launch(const ConvWgradPfDesc& d, cudaStream_t stream);
+
 // ---------------------------------------------------------------- layout kernels of the training path
 struct NchwToPfDesc {
     const float* x;         // NCHW fp32 [B][C][H][W]

@@ -6,9 +6,10 @@ contributes a cuDNN forward, dgrad and wgrad kernel.  Here
   forward  = cl_conv_igemm on the padded-flat layout (same kernel as inference, fp16x3, no GroupNorm statistics),
   dgrad    = cl_conv_igemm on the output gradient with the transposed filter and negated tap shifts (a stride-2
              convolution decomposes into one small stride-1 problem per input parity phase),
-  wgrad    = cl_conv_wgrad on channel-major operands (split-K over images, fp32 atomics),
+  wgrad    = cl_conv_wgrad_pf: the padded-flat operands of the forward input and of the output gradient read as
+             MN-major tensor-core operands (split-K over pixel rows, fp32 atomics),
 with the NCHW <-> operand-layout conversions and the filter packing done by cl_nchw_to_pf / cl_pf_to_nchw /
-cl_nchw_to_cm / cl_pack_filter.  GroupNorm / ReLU / residual adds and the loss stay stock torch ops in this round.
+cl_pack_filter.  GroupNorm / ReLU / residual adds and the loss stay stock torch ops in this round.
 Gradients are rescaled by a power of two computed on the device (no host synchronisation) so that they stay
 inside fp16's range; filters are scaled the same way.
 """
@@ -26,7 +27,8 @@ def eligible(conv):
     """Convolutions the tensor-core path covers: 3x3 / 1x1, stride 1 or 2, Cin % 32 == 0, Cout in {64, 128k}."""
     k = conv.kernel_size[0]
     return (k in (1, 3) and conv.kernel_size[1] == k and conv.stride[0] in (1, 2) and conv.padding[0] == k // 2
-            and conv.in_channels % 32 == 0 and (conv.out_channels == 64 or conv.out_channels % 128 == 0)
+            and (conv.in_channels == 32 or conv.in_channels % 64 == 0)
+            and (conv.out_channels == 64 or conv.out_channels % 128 == 0)
             and conv.dilation[0] == 1 and conv.groups == 1)
 
 
@@ -101,8 +103,9 @@ def _forward_taps(k, stride, geo):
     return out
 
 
-def conv_forward(x, weight, bias, stride):
-    """y = conv2d(x, weight, bias, stride, padding = k // 2); NCHW fp32 in and out."""
+def conv_forward(x, weight, bias, stride, return_operand=False):
+    """y = conv2d(x, weight, bias, stride, padding = k // 2); NCHW fp32 in and out.
+    With return_operand the fp16 hi/lo PF operand of x is returned too (the weight gradient reads it again)."""
     cout, cin, k, _ = weight.shape
     b, _, h, w = x.shape
     ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
@@ -114,19 +117,26 @@ def conv_forward(x, weight, bias, stride):
     packed = _pack(weight, ws, pairs, False, cout, cin)
     raw = _igemm(act, phases, geo, packed, _forward_taps(k, stride, geo), cin, cout)
     y = torch.empty(b, cout, ho, wo, dtype=torch.float32, device=x.device)
-    return _from_raw(raw, geo, cout, y, scale=ws_inv, bias=bias)
+    y = _from_raw(raw, geo, cout, y, scale=ws_inv, bias=bias)
+    return (y, act) if return_operand else y
 
 
-def conv_dgrad(gy, weight, in_hw, stride):
+def grad_operand(gy):
+    """fp16 hi/lo PF operand of an output gradient, rescaled by a device-side power of two: (g_pf, 2^-k, geometry)."""
+    b, _, ho, wo = gy.shape
+    gs, gs_inv = _pow2_scale(gy, 256.0)
+    geo = _Geometry(b, ho, wo)
+    return _to_pf(gy, 1, geo, gs), gs_inv, geo
+
+
+def conv_dgrad(gy, weight, in_hw, stride, operand=None):
     """dL/dx of y = conv2d(x, weight, stride, padding = k // 2); gy NCHW fp32 [B, Cout, Ho, Wo]."""
     cout, cin, k, _ = weight.shape
     b, _, ho, wo = gy.shape
     h, w = in_hw
-    gs, gs_inv = _pow2_scale(gy, 256.0)
+    g_pf, gs_inv, geo = operand if operand is not None else grad_operand(gy)
     ws, ws_inv = _pow2_scale(weight, 128.0)
     out_scale = gs_inv * ws_inv
-    geo = _Geometry(b, ho, wo)
-    g_pf = _to_pf(gy, 1, geo, gs)
     n_out = (cin + 63) // 64 * 64          # the kernel wants Cout' % 64 == 0: zero-padded filter rows
     gx = torch.empty(b, cin, h, w, dtype=torch.float32, device=gy.device)
     if stride == 1:
@@ -153,58 +163,26 @@ def conv_dgrad(gy, weight, in_hw, stride):
     return gx
 
 
-def _to_cm(x, hp, wp, rows, cols, step, groups, scale=None):
-    """NCHW fp32 -> channel-major fp16 hi/lo planes [2][groups][B][C][hp * wp]; groups = [(pa, pb, col0)]."""
-    lib = _lib.load()
-    b, c, h, w = x.shape
-    out = torch.empty(2, len(groups), b, c, hp * wp, dtype=torch.float16, device=x.device)
-    _lib.check(lib.cl_nchw_to_cm(x.data_ptr(), 0 if scale is None else scale.data_ptr(), out.data_ptr(), b, c, h, w, hp,
-                                 wp, rows, cols, step, len(groups), _i32([g[0] for g in groups]),
-                                 _i32([g[1] for g in groups]), _i32([g[2] for g in groups]), _stream(x)))
-    return out
-
-
-def conv_wgrad(gy, x, weight_shape, stride):
+def conv_wgrad(gy, x, weight_shape, stride, operand=None, act=None):
     """dL/dweight of y = conv2d(x, weight, stride, padding = k // 2); returns [Cout, Cin, k, k] fp32.
 
-    The kernel shifts whole rows only (TMA box starts must be 16-byte aligned), so the row pitch is padded to a
-    multiple of 8 pixels and the horizontal neighbours of a 3x3 filter are supplied as column-shifted copies of x.
+    Both GEMM operands are the padded-flat matrices the forward / data-gradient kernels already use (cl_conv_wgrad_pf
+    reads them as MN-major tensor-core operands): `operand` = grad_operand(gy), `act` = the forward's operand of x.
     """
     lib = _lib.load()
     cout, cin, k, _ = weight_shape
-    b, _, ho, wo = gy.shape
-    hp = ho + 2
-    wp = (wo + 3 + 7) // 8 * 8                                         # room for the -1 column shift, pitch % 8 == 0
-    plane = hp * wp
-    gs, gs_inv = _pow2_scale(gy, 256.0)
-    g_cm = _to_cm(gy, hp, wp, ho, wo, 1, [(0, 0, 1)], gs)              # [2][1][B][Cout][plane]
+    g_pf, gs_inv, geo = operand if operand is not None else grad_operand(gy)
+    phases = 4 if stride == 2 else 1
+    if act is None:
+        act = _to_pf(x, phases, geo)
     shifts, tphase = [], []
-    if k == 1:
-        groups = [(0, 0, 1)]
-        shifts, tphase = [0], [0]
-    elif stride == 1:
-        # group kw holds x shifted by (kw - 1) columns: reading it at row shift (kh - 1) gives x[p + (kh-1, kw-1)]
-        groups = [(0, 0, 1 - (kw - 1)) for kw in range(3)]
-        for kh in range(3):
-            for kw in range(3):
-                shifts.append((kh - 1) * wp); tphase.append(kw)
-    else:
-        # parity phases of x at the output resolution, each with column shifts 0 and -1 (dx of the tap)
-        groups, index = [], {}
-        for a in (0, 1):
-            for bb in (0, 1):
-                for dx in (0, -1):
-                    index[(a, bb, dx)] = len(groups)
-                    groups.append((a, bb, 1 - dx))
-        for kh in range(3):
-            for kw in range(3):
-                a, dy = (1, -1) if kh == 0 else ((0, 0) if kh == 1 else (1, 0))
-                bb, dx = (1, -1) if kw == 0 else ((0, 0) if kw == 1 else (1, 0))
-                shifts.append(dy * wp); tphase.append(index[(a, bb, dx)])
-    x_cm = _to_cm(x, hp, wp, ho, wo, stride, groups)                   # [2][groups][B][Cin][plane]
-    dw = torch.zeros(k * k, cout, cin, dtype=torch.float32, device=gy.device)
-    _lib.check(lib.cl_conv_wgrad(g_cm.data_ptr(), x_cm.data_ptr(), b, cout, cin, plane, plane, len(groups), k * k,
-                                 _i32(shifts), _i32(tphase), _NTERMS, 1.0, dw.data_ptr(), _stream(gy)))
+    for t in _forward_taps(k, stride, geo):   # split the forward tap rows into (phase plane, in-plane shift)
+        ph = (t + geo.Mp // 2) // geo.Mp if stride == 2 else 0
+        tphase.append(ph)
+        shifts.append(t - ph * geo.Mp)
+    dw = torch.zeros(k * k, cout, cin, dtype=torch.float32, device=g_pf.device)
+    _lib.check(lib.cl_conv_wgrad_pf(g_pf.data_ptr(), geo.Mp, act.data_ptr(), geo.Mp, geo.Mp, cout, cin, phases, k * k,
+                                    _i32(shifts), _i32(tphase), _NTERMS, 1.0, dw.data_ptr(), _stream(g_pf)))
     return (dw * gs_inv).reshape(k, k, cout, cin).permute(2, 3, 0, 1).contiguous()
 
 
@@ -214,19 +192,21 @@ class NativeConv2d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride):
         x = x.contiguous()
-        y = conv_forward(x, weight.contiguous(), bias, stride)
-        ctx.save_for_backward(x, weight)
+        y, act = conv_forward(x, weight.contiguous(), bias, stride, return_operand=True)
+        ctx.save_for_backward(act, weight)   # the PF operand of x is all the weight gradient needs
         ctx.stride = stride
+        ctx.in_hw = tuple(x.shape[2:])
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight = ctx.saved_tensors
+        act, weight = ctx.saved_tensors
         gy = gy.contiguous()
         weight = weight.contiguous()
-        gx = conv_dgrad(gy, weight, x.shape[2:], ctx.stride) if ctx.needs_input_grad[0] else None
-        gw = conv_wgrad(gy, x, weight.shape, ctx.stride) if ctx.needs_input_grad[1] else None
+        operand = grad_operand(gy)   # shared by the data and the weight gradient
+        gx = conv_dgrad(gy, weight, ctx.in_hw, ctx.stride, operand) if ctx.needs_input_grad[0] else None
+        gw = conv_wgrad(gy, None, weight.shape, ctx.stride, operand, act) if ctx.needs_input_grad[1] else None
         gb = gy.sum((0, 2, 3)) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return gx, gw, gb, None
 

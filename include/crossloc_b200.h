@@ -115,6 +115,20 @@ int cl_conv_wgrad(const void* grad, const void* act, int B, int Cout, int Cin, i
                   float* dw, void* cuda_stream);
 
 /*
+ * Convolution weight gradient on padded-flat operands (the layout of cl_conv_igemm / cl_gn_backward):
+ *   dw[tap][co][ci] += out_scale * sum over rows r < Mp of grad[r][co] * act[tap_phase[tap]][r + tap_shift[tap]][ci]
+ * Both operands are fp16 hi/lo PF matrices [planes][rows][C] read as MN-major tensor-core operands (64-row x
+ * 64-channel TMA boxes, SWIZZLE_128B): no channel-major copies.  grad: plane 0 = hi, 1 = lo, g_plane_rows apart,
+ * zero border rows.  act: plane term * phases + phase, x_plane_rows apart; rows outside a plane read as zero.
+ * tap_shift / tap_phase are the forward convolution's tap table (phase and in-plane row shift kept apart).
+ * Replaces the cuDNN wgrad kernels autograd launches for nn.Conv2d (train_single_task.py:298).
+ *   Cout % 64 == 0, Cin = 32 or a multiple of 64, nterms 1 | 3 (fp16x3); dw fp32 [num_taps][Cout][Cin], atomics.
+ */
+int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const void* act, int64_t x_plane_rows, int Mp, int Cout,
+                     int Cin, int phases, int num_taps, const int32_t* tap_shift, const int32_t* tap_phase, int nterms,
+                     float out_scale, float* dw, void* cuda_stream);
+
+/*
  * Layout kernels of the training path (device pointers): NCHW fp32 tensors, as autograd hands them over, to and
  * from the operand layouts of cl_conv_igemm / cl_conv_wgrad, and filter packing.  `scale` arguments are device
  * scalars (power-of-two factors computed on the GPU, no host synchronisation), NULL = 1.
