@@ -118,9 +118,18 @@ class CoordNetEngine:
         self._ws = {}
         self.launches = 0
         self.events = None   # set to a list to record (layer, shape, flops, start, end) CUDA events around every launch
+        # training mode (crossloc_b200.train_plan): a list that receives one record per GroupNorm/merge stage; every
+        # layer then keeps its own raw / activation buffers (nothing is recycled) and `packer` supplies the filters
+        self.tape = None
+        self.packer = None
+        self.head_in = None
+        self._conv_rec = {}
+        self._keep_i = 0
 
     # ------------------------------------------------------------------ parameters
     def _pack(self, name, conv, force_split=False):
+        if self.packer is not None:
+            return self.packer(name, conv)
         ver = (conv.weight._version, conv.weight.data_ptr(), None if conv.bias is None else conv.bias._version, force_split)
         if self._pack_versions.get(name) != ver:
             nterms = _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0])
@@ -137,6 +146,8 @@ class CoordNetEngine:
         if ws is not None:
             return ws
         ws = {'geo': {}, 'act': {}, 'raw': {}}
+        while len(self._ws) >= 3:   # training frames change size every step (dataloader.py:520-524): keep a few workspaces only
+            self._ws.pop(next(iter(self._ws)))
         hh, wwid = h, w
         for level in range(4):   # level 0 = input resolution, 3 = output resolution
             ws['geo'][level] = _Geometry(batch, hh, wwid)
@@ -154,7 +165,9 @@ class CoordNetEngine:
             ws['act'][key] = buf
         return buf
 
-    def _raw(self, ws, tag, level, channels):
+    def _raw(self, ws, tag, level, channels, name=None):
+        if self.tape is not None and name is not None:
+            tag = 'keep:' + name
         key = (tag, level, channels)
         buf = ws['raw'].get(key)
         if buf is None:
@@ -193,6 +206,9 @@ class CoordNetEngine:
         self._tock(e0, name, (pack.cin, pack.cout, pack.ksize, pack.stride),
                    2.0 * geo.B * geo.H * geo.W * pack.cout * pack.cin * len(taps))
         self.launches += 1
+        if self.tape is not None:
+            self._conv_rec[id(raw)] = {'name': name, 'pack': pack, 'act': act, 'geo': geo, 'taps': taps, 'raw': raw,
+                                       'stats': stats, 'group_ch': group_ch}
 
     def _apply(self, stream, raw, geo, channels, norm, stats, out, relu_inner=True, res=None, raw2=None, norm2=None,
                stats2=None, relu_outer=False, want_lo=True, want8=False):
@@ -211,6 +227,10 @@ class CoordNetEngine:
             out.f8.data_ptr() if want8 else 0, stream))
         self._tock(e0, 'gn_apply', ('gn_apply', channels, out.phases, add_kind), 0.0)
         self.launches += 1
+        if self.tape is not None:
+            self.tape.append({'conv': self._conv_rec[id(raw)], 'norm': norm, 'out': out, 'relu_inner': relu_inner,
+                              'add_kind': add_kind, 'res': res, 'relu_outer': relu_outer,
+                              'skip': None if raw2 is None else self._conv_rec[id(raw2)], 'norm2': norm2})
 
     # ------------------------------------------------------------------ plans
     def forward(self, spec, image):
@@ -246,6 +266,8 @@ class CoordNetEngine:
         else:
             stats_all.zero_()
         self._stat_i = 0
+        self._keep_i = 0
+        self._conv_rec = {}
 
         def next_stats():
             s = stats_all[self._stat_i]
@@ -301,13 +323,14 @@ class CoordNetEngine:
                 a.h16.data_ptr(), self.terms, stream))
             self._tock(e0, 'stem', ('stem',), 2.0 * batch * h * w * 32 * cin * 9)
             self.launches += 2 if norm1 is not None else 1
+            self.stem_out = a if self.tape is not None else None
 
             # ---- strided ladder conv2..conv4
             for level, role in ((1, 'conv2'), (2, 'conv3'), (3, 'conv4')):
                 name = roles[role]
                 conv, norm = convs[name]
                 pack = packs[name]
-                raw = self._raw(ws, 'ladder', level, pack.cout)
+                raw = self._raw(ws, 'ladder', level, pack.cout, name)
                 st = next_stats() if norm is not None else None
                 self._conv(stream, pack, a, geo[level], raw, st, groups_of(norm, pack.cout), name)
                 if level < 3:
@@ -324,6 +347,9 @@ class CoordNetEngine:
 
         def scratch(channels, avoid):
             """A PF buffer at the output resolution that is none of `avoid`."""
+            if self.tape is not None:   # training: every activation is kept for the backward pass
+                self._keep_i += 1
+                return self._act(ws, 'keep%d' % self._keep_i, 3, channels, 1)
             pool = rot.setdefault(channels, [self._act(ws, 'pool%d' % i, 3, channels, 1) for i in range(4)])
             for buf in pool:
                 if all(buf is not o for o in avoid):
@@ -336,7 +362,7 @@ class CoordNetEngine:
             for i, name in enumerate(names):
                 conv, norm = convs[name]
                 pack = packs[name]
-                raw = self._raw(ws, 'r%d' % (i % 2), 3, pack.cout)
+                raw = self._raw(ws, 'r%d' % (i % 2), 3, pack.cout, name)
                 st = next_stats() if norm is not None else None
                 self._conv(stream, pack, x, g3, raw, st, groups_of(norm, pack.cout), name)
                 out = scratch(pack.cout, (x, res_in))
@@ -366,7 +392,7 @@ class CoordNetEngine:
                 # x = chain(res); res = skip_norm(skip(res)); res = [relu](res + x)   (networks.py:242-249)
                 sconv, snorm = convs[block['skip']]
                 spack = packs[block['skip']]
-                raw_s = self._raw(ws, 'rs', 3, spack.cout)
+                raw_s = self._raw(ws, 'rs', 3, spack.cout, block['skip'])
                 st_s = next_stats() if snorm is not None else None
                 self._conv(stream, spack, res, g3, raw_s, st_s, groups_of(snorm, spack.cout), block['skip'])
                 if gn:
@@ -382,7 +408,7 @@ class CoordNetEngine:
                 for i, name in enumerate(names):
                     conv, norm = convs[name]
                     pack = packs[name]
-                    raw = self._raw(ws, 'r0', 3, pack.cout)
+                    raw = self._raw(ws, 'r0', 3, pack.cout, name)
                     st = next_stats() if norm is not None else None
                     self._conv(stream, pack, res, g3, raw, st, groups_of(norm, pack.cout), name)
                     out = scratch(pack.cout, (res,))
@@ -401,6 +427,7 @@ class CoordNetEngine:
         head = spec['head']
         hconv = head['conv']
         co = hconv.out_channels
+        self.head_in = res if self.tape is not None else None
         if duc:
             # full-size variant (networks.py:344-349): DUC 3x3 convolution on the tensor cores, then one kernel for
             # GroupNorm + ReLU + PixelShuffle + bilinear resize + fc3 + output maps

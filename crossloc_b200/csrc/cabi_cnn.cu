@@ -227,3 +227,33 @@ extern "C" int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const vo
     d.nterms = nterms; d.out_scale = out_scale; d.dw = dw;
     return finish(kFn, cl::conv_wgrad_pf_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
+
+extern "C" int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch, const float* raw, const double* stats,
+                              const float* gamma, const float* beta, float eps, int relu_inner, int num_src,
+                              const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
+                              const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out,
+                              double* ab, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows, float* scale_out,
+                              double* dbias, void* cuda_stream)
+{
+    static const char* kFn = "cl_gn_backward";
+    NEED_DEV(raw); NEED_DEV(ab); NEED_DEV(gmax_bits);
+    if (group_ch) { NEED_DEV(stats); NEED_DEV(gamma); NEED_DEV(beta); }
+    if (pass != 0 && pass != 1) return cl::fail(-1, "%s: pass must be 0 (reduce) or 1 (apply)", kFn);
+    if (num_src < 1 || num_src > 3 || !src || !src_scale_a || !src_scale_b || !src_stride || !src_phased)
+        return cl::fail(-1, "%s: 1..3 gradient sources with their tables", kFn);
+    cl::GnBwdDesc d{};
+    d.B = B; d.H = H; d.W = W; d.C = C; d.group_ch = group_ch; d.raw = raw; d.stats = stats; d.gamma = gamma; d.beta = beta;
+    d.eps = eps; d.relu_inner = relu_inner; d.num_src = num_src;
+    for (int i = 0; i < num_src; i++) {
+        d.src[i].g = src[i]; d.src[i].scale_a = src_scale_a[i]; d.src[i].scale_b = src_scale_b[i];
+        d.src[i].stride = src_stride[i]; d.src[i].phased = src_phased[i];
+        if (int rc = need_device(kFn, "src[i]", src[i])) return rc;
+    }
+    d.mask_out = static_cast<const __half*>(mask_out); d.g_out = g_out; d.ab = ab;
+    d.gmax_bits = static_cast<unsigned*>(gmax_bits); d.d_raw = static_cast<__half*>(d_raw); d.d_raw_lo_rows = d_raw_lo_rows;
+    d.scale_out = scale_out; d.dbias = dbias;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    if (pass == 0) return finish(kFn, cl::gn_bwd_reduce_launch(d, s));
+    NEED_DEV(d_raw); NEED_DEV(scale_out);
+    return finish(kFn, cl::gn_bwd_apply_launch(d, s));
+}

@@ -180,6 +180,37 @@ struct GnApplyDesc {
 };
 const char* gn_apply_launch(const GnApplyDesc& d, cudaStream_t stream);
 
+// ---------------------------------------------------------------- GroupNorm / ReLU / residual-merge backward (training)
+struct GnBwdSrc {
+    const float* g;         // fp32 PF gradient [rows][stride] (interior rows valid)
+    const float* scale_a;   // nullable device scalars multiplied into this source
+    const float* scale_b;
+    int stride;             // floats per row (>= C)
+    int phased;             // 1: stored as 4 parity phases at half resolution (data gradient of a stride-2 convolution)
+};
+struct GnBwdDesc {
+    int B, H, W, C;
+    int group_ch;           // 0: no normalisation (vanilla Network)
+    const float* raw;       // fp32 PF raw convolution output of this layer
+    const double* stats;    // [B][C/group_ch][2]
+    const float* gamma;
+    const float* beta;
+    float eps;
+    int relu_inner;
+    int num_src;            // pass 1 sums src[0 .. num_src); pass 2 reads src[0] only
+    GnBwdSrc src[3];
+    const __half* mask_out; // pass 1, nullable: hi plane of the stage's merged output; the gradient passes where it is > 0
+    float* g_out;           // pass 1, nullable: summed / masked gradient, fp32 PF [rows][C]
+    double* ab;             // [B][C][2]: sum dy, sum dy * xhat (pass 1 accumulates, pass 2 reads); caller zeroes
+    unsigned* gmax_bits;    // float bits of max |dy * gamma| * rstd (pass 1 atomicMax, pass 2 reads); caller zeroes
+    __half* d_raw;          // pass 2: gradient of the raw convolution output, fp16 hi / lo PF planes x 2^k
+    int64_t d_raw_lo_rows;
+    float* scale_out;       // pass 2: {2^k, 2^-k}
+    double* dbias;          // pass 2, nullable: [C] += sum d_raw (gradient of the convolution bias)
+};
+const char* gn_bwd_reduce_launch(const GnBwdDesc& d, cudaStream_t stream);
+const char* gn_bwd_apply_launch(const GnBwdDesc& d, cudaStream_t stream);
+
 // ---------------------------------------------------------------- stem convolution (3x3, stride 1, Cin in {1, 3}, Cout = 32)
 struct StemDesc {
     const float* image;     // NCHW fp32 [B][Cin][H][W]

@@ -1,0 +1,297 @@
+"""Fused training step of the coordinate network (BASELINE config 4).
+
+The reference trains through stock autograd (/root/reference/train_single_task.py:262-299): every nn.Conv2d /
+nn.GroupNorm / F.relu / residual add contributes its own forward and backward library kernels on NCHW fp32 tensors.
+Here the whole network is ONE autograd node:
+
+  forward   the inference plan of crossloc_b200.cnn in fp16x3 arithmetic with every raw convolution output,
+            GroupNorm statistic and operand kept (the engine's `tape`);
+  backward  walks the tape in reverse.  Per stage: cl_gn_backward pass 0 (sum of the incoming gradients, residual
+            mask, GroupNorm / ReLU reductions) and pass 1 (gradient of the raw convolution output as fp16 hi / lo
+            padded-flat planes, power-of-two scaled on the device), then the data gradient (cl_conv_igemm with the
+            transposed filter) and the weight gradient (cl_conv_wgrad_pf) read those planes directly.
+
+Activations and gradients never leave the padded-flat layout between layers, so the NCHW <-> operand conversions of
+the per-layer path (crossloc_b200.train) disappear.  The 3-channel stem and the 4-channel head are differentiated
+with stock torch ops (0.2 % of the FLOPs).  Covers TransPoseNet / Network without MLR encoders or the full-size head;
+the other variants keep using the per-layer path.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib, layout
+from .cnn import CoordNetEngine, _Geometry
+from .train import _forward_taps, _i32, _pack, _stream
+
+_NTERMS = 3
+_RESCALE_EVERY = 64   # steps between host-side refreshes of the filters' power-of-two scales
+
+
+class _Src:
+    """One gradient contribution to an activation: fp32 padded-flat buffer x two optional device scalars."""
+
+    def __init__(self, g, stride, scale_a=None, scale_b=None, phased=False):
+        self.g, self.stride, self.scale_a, self.scale_b, self.phased = g, stride, scale_a, scale_b, phased
+
+
+class _TrainPack:
+    """Filter of one convolution in the tensor-core layout, packed on the device (no host synchronisation)."""
+
+    def __init__(self, conv, exp):
+        w = conv.weight.detach().contiguous()
+        cout, cin, k, _ = w.shape
+        self.cin, self.cout, self.ksize, self.stride, self.nterms = cin, cout, k, conv.stride[0], _NTERMS
+        self.out_scale = float(2.0 ** (-exp))
+        self.scale = torch.full((1,), float(2.0 ** exp), dtype=torch.float32, device=w.device)
+        self.inv_scale = torch.full((1,), self.out_scale, dtype=torch.float32, device=w.device)
+        self.weight = w
+        self.weight_param, self.bias_param = conv.weight, conv.bias
+        self.weights = _pack(w, self.scale, [(kh, kw) for kh in range(k) for kw in range(k)], False, cout, cin)
+        self.weights8 = None
+        self.bias = (conv.bias.detach().to(torch.float32) if conv.bias is not None
+                     else torch.zeros(cout, dtype=torch.float32, device=w.device)).contiguous()
+
+
+def supported(net):
+    return not getattr(net, 'num_mlr', 0) and not getattr(net, 'full_size_output', False)
+
+
+class TrainPlan:
+    def __init__(self, net):
+        self.net = net
+        self.engine = CoordNetEngine(precision='fp16x3')
+        self.engine.packer = self._packer
+        self._exps = {}
+        self._step = 0
+        self._pool = {}
+
+    # ------------------------------------------------------------------ filters
+    def _packer(self, name, conv):
+        if name not in self._exps or self._step % _RESCALE_EVERY == 0:
+            amax = float(conv.weight.detach().abs().max())   # host sync, once every _RESCALE_EVERY steps
+            import math
+            exp = 0 if amax == 0.0 or not math.isfinite(amax) else int(math.floor(math.log2(128.0 / amax)))
+            self._exps[name] = max(-24, min(24, exp))
+        return _TrainPack(conv, self._exps[name])
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, image):
+        eng = self.engine
+        eng.tape = []
+        spec = self.net._spec()
+        out = eng.forward(spec, image)
+        state = {'tape': eng.tape, 'head_in': eng.head_in, 'stem_out': eng.stem_out, 'spec': spec, 'image': image,
+                 'geo3': eng.head_in.geo}
+        eng.tape = None
+        self._step += 1
+        return out, state
+
+    # ------------------------------------------------------------------ helpers
+    def _zeros_pf(self, geo, channels, device):
+        """fp16 hi/lo planes with zero borders, recycled between layers of one (resolution, width)."""
+        key = (geo.B, geo.H, geo.W, channels, str(device))
+        buf = self._pool.get(key)
+        if buf is None:
+            if len(self._pool) > 16:
+                self._pool.clear()
+            buf = self._pool[key] = torch.zeros(2 * geo.Mp, channels, dtype=torch.float16, device=device)
+        return buf
+
+    def _gn_backward(self, lib, stream, geo, channels, rec, norm, relu_inner, srcs, mask, want_g):
+        """Both passes of cl_gn_backward for one stage; returns (d_raw, scale_out, ab, dbias, g_buf)."""
+        dev = rec['raw'].device
+        ab = torch.zeros(geo.B, channels, 2, dtype=torch.float64, device=dev)
+        gmax = torch.zeros(1, dtype=torch.int32, device=dev)
+        dbias = torch.zeros(channels, dtype=torch.float64, device=dev)
+        scale_out = torch.empty(2, dtype=torch.float32, device=dev)
+        g_buf = torch.empty(geo.Mp, channels, dtype=torch.float32, device=dev) if want_g else None
+        d_raw = self._zeros_pf(geo, channels, dev)
+        group_ch = 0 if norm is None else channels // norm.num_groups
+
+        def call(pass_id, sources):
+            n = len(sources)
+            ptrs = (ctypes.c_void_p * 3)(*[s.g.data_ptr() for s in sources] + [None] * (3 - n))
+            sa = (ctypes.c_void_p * 3)(*[None if s.scale_a is None else s.scale_a.data_ptr() for s in sources] + [None] * (3 - n))
+            sb = (ctypes.c_void_p * 3)(*[None if s.scale_b is None else s.scale_b.data_ptr() for s in sources] + [None] * (3 - n))
+            _lib.check(lib.cl_gn_backward(
+                pass_id, geo.B, geo.H, geo.W, channels, group_ch, rec['raw'].data_ptr(),
+                None if norm is None else rec['stats'].data_ptr(), None if norm is None else norm.weight.data_ptr(),
+                None if norm is None else norm.bias.data_ptr(), 1e-5 if norm is None else float(norm.eps),
+                1 if relu_inner else 0, n, ptrs, sa, sb, _i32([s.stride for s in sources] + [0] * (3 - n)),
+                _i32([1 if s.phased else 0 for s in sources] + [0] * (3 - n)),
+                None if (mask is None or pass_id == 1) else mask.data_ptr(),
+                None if (g_buf is None or pass_id == 1) else g_buf.data_ptr(), ab.data_ptr(), gmax.data_ptr(),
+                d_raw.data_ptr(), geo.Mp, scale_out.data_ptr(), dbias.data_ptr(), stream))
+
+        call(0, srcs)
+        call(1, [_Src(g_buf, channels)] if want_g else srcs[:1])
+        return d_raw, scale_out, ab, dbias, g_buf
+
+    def _conv_backward(self, lib, stream, rec, d_raw, scale_out, need_dgrad):
+        """Weight gradient (always) and data gradient (as a source for the producer of the conv's input)."""
+        pack, geo, act = rec['pack'], rec['geo'], rec['act']
+        k, stride, cin, cout = pack.ksize, pack.stride, pack.cin, pack.cout
+        dev = d_raw.device
+        # ---- weight gradient: dW[tap][co][ci] from the PF planes of d_raw and of the forward operand
+        shifts, tphase = [], []
+        for t in rec['taps']:
+            ph = (t + geo.Mp // 2) // geo.Mp if stride == 2 else 0
+            tphase.append(ph)
+            shifts.append(t - ph * geo.Mp)
+        dw = torch.zeros(k * k, cout, cin, dtype=torch.float32, device=dev)
+        _lib.check(lib.cl_conv_wgrad_pf(d_raw.data_ptr(), geo.Mp, act.h16.data_ptr(), geo.Mp, geo.Mp, cout, cin, act.phases,
+                                        k * k, _i32(shifts), _i32(tphase), _NTERMS, 1.0, dw.data_ptr(), stream))
+        gw = (dw * scale_out[1:2]).reshape(k, k, cout, cin).permute(2, 3, 0, 1).contiguous()
+        if not need_dgrad:
+            return gw, None
+        # ---- data gradient: transposed filter, negated tap shifts; one small problem per input parity for stride 2
+        n_out = (cin + 63) // 64 * 64
+        zero_bias = torch.zeros(n_out, dtype=torch.float32, device=dev)
+
+        def igemm(pairs, shifts, raw):
+            packed = _pack(pack.weight, pack.scale, pairs, True, n_out, cout)
+            _lib.check(lib.cl_conv_igemm(d_raw.data_ptr(), d_raw.size(0), geo.Mp, cout, packed.data_ptr(), n_out,
+                                         len(shifts), _i32(shifts), _NTERMS, geo.Mp, geo.Hp, geo.Wp, 0, 1.0,
+                                         raw.data_ptr(), zero_bias.data_ptr(), 0, 0, 0, 0, 0, stream))
+
+        if stride == 1:
+            raw = torch.empty(geo.Mp, n_out, dtype=torch.float32, device=dev)
+            if k == 1:
+                igemm([(0, 0)], [0], raw)
+            else:
+                pairs = [(kh, kw) for kh in range(3) for kw in range(3)]
+                igemm(pairs, [(1 - kh) * geo.Wp + (1 - kw) for kh, kw in pairs], raw)
+            return gw, _Src(raw, n_out, scale_out[1:2], pack.inv_scale, phased=False)
+        raw = torch.zeros(4 * geo.Mp, n_out, dtype=torch.float32, device=dev)
+        per_parity = {0: [(1, 0)], 1: [(0, 1), (2, 0)]} if k == 3 else {0: [(0, 0)], 1: []}
+        for a in (0, 1):
+            for bb in (0, 1):
+                pairs = [(kh, kw) for kh, _ in per_parity[a] for kw, _ in per_parity[bb]]
+                if pairs:
+                    shifts = [dy * geo.Wp + dx for _, dy in per_parity[a] for _, dx in per_parity[bb]]
+                    igemm(pairs, shifts, raw[(a * 2 + bb) * geo.Mp:(a * 2 + bb + 1) * geo.Mp])
+        return gw, _Src(raw, n_out, scale_out[1:2], pack.inv_scale, phased=True)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, state, g_out):
+        """Gradients of every parameter given dL/d(output); returns {parameter: gradient}."""
+        lib = _lib.load()
+        image = state['image']
+        dev = image.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        grads = {}
+        spec = state['spec']
+        head = spec['head']
+        geo3 = state['geo3']
+        res = state['head_in']
+
+        # ---- head (1x1 C -> Co, mean offset, exp(clamp)): stock torch ops on the NCHW view of the last activation
+        hconv = head['conv']
+        co, k_task = hconv.out_channels, head['num_task']
+        x = layout.from_pf(res.h16, geo3.B, geo3.H, geo3.W, 2)
+        with torch.enable_grad():
+            x.requires_grad_(True)
+            w = hconv.weight.detach().reshape(co, -1).requires_grad_(True)
+            b = hconv.bias.detach().requires_grad_(True)
+            sc = torch.einsum('bchw,oc->bohw', x, w) + b[None, :, None, None]
+            task = sc[:, :k_task] + head['mean'].to(dev)[None, :, None, None]
+            if co > k_task:
+                pos = torch.exp(F.hardtanh(sc[:, k_task:], min_val=head['clamp'][0], max_val=head['clamp'][1]))
+                task = torch.cat([task, pos], 1)
+            gx, gw, gb = torch.autograd.grad(task, (x, w, b), g_out.contiguous())
+        grads[id(hconv.weight)] = gw.reshape(hconv.weight.shape)
+        grads[id(hconv.bias)] = gb
+        g_pf = F.pad(gx, (1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(geo3.Mp, -1).contiguous()
+        sources = {id(res): [_Src(g_pf, g_pf.size(1))]}
+
+        stem_out = state['stem_out']
+        for e in reversed(state['tape']):
+            rec, out = e['conv'], e['out']
+            geo, channels = rec['geo'], rec['pack'].cout
+            srcs = sources.pop(id(out))
+            merge = e['add_kind'] != 0
+            mask = out.h16 if (merge and e['relu_outer']) else None
+            want_g = merge or len(srcs) > 1
+            d_raw, scale_out, ab, dbias, g_buf = self._gn_backward(lib, stream, geo, channels, rec, e['norm'],
+                                                                   e['relu_inner'], srcs, mask, want_g)
+            self._param_grads(grads, rec, e['norm'], ab, dbias)
+            if e['add_kind'] == 1:
+                sources.setdefault(id(e['res']), []).append(_Src(g_buf, channels))
+            act = rec['act']
+            gw, src = self._conv_backward(lib, stream, rec, d_raw, scale_out, True)
+            grads[id(rec['pack'].weight_param)] = gw
+            sources.setdefault(id(act), []).append(src)
+            if e['add_kind'] == 2:
+                # skip branch: out = [relu](GroupNorm(skip_conv(res)) + main): its gradient is the merged gradient g_buf
+                srec = e['skip']
+                d_raw_s, scale_s, ab_s, dbias_s, _ = self._gn_backward(lib, stream, geo, channels, srec, e['norm2'], False,
+                                                                       [_Src(g_buf, channels)], None, False)
+                self._param_grads(grads, srec, e['norm2'], ab_s, dbias_s)
+                gw, src = self._conv_backward(lib, stream, srec, d_raw_s, scale_s, True)
+                grads[id(srec['pack'].weight_param)] = gw
+                sources.setdefault(id(srec['act']), []).append(src)
+
+        # ---- stem (conv1 + norm1 + relu on the 3-channel frame): stock torch ops, recomputed
+        if stem_out is not None:
+            (src,) = sources.pop(id(stem_out))
+            h, w_ = image.shape[2:]
+            g_stem = torch.empty(image.size(0), 32, h, w_, dtype=torch.float32, device=dev)
+            if h % 2 or w_ % 2:
+                g_stem.zero_()
+            geo1 = _Geometry(image.size(0), (h + 1) // 2, (w_ + 1) // 2)
+            scale = src.scale_a * src.scale_b
+            for a in (0, 1):
+                for bb in (0, 1):
+                    ph = a * 2 + bb
+                    _lib.check(lib.cl_pf_to_nchw(src.g[ph * geo1.Mp:(ph + 1) * geo1.Mp].data_ptr(), geo1.B, geo1.H, geo1.W,
+                                                 src.stride, g_stem.data_ptr(), 32, h, w_, 2, a, bb, scale.data_ptr(), None,
+                                                 stream))
+            convs = {name: (conv, norm) for name, conv, norm in spec['layers']}
+            conv1, norm1 = convs[spec.get('roles', {'conv1': 'conv1'})['conv1']]
+            with torch.enable_grad():
+                params = [conv1.weight.detach().requires_grad_(True), conv1.bias.detach().requires_grad_(True)]
+                y = F.conv2d(image, params[0], params[1], padding=1)
+                if norm1 is not None:
+                    params += [norm1.weight.detach().requires_grad_(True), norm1.bias.detach().requires_grad_(True)]
+                    y = F.group_norm(y, norm1.num_groups, params[2], params[3], norm1.eps)
+                y = F.relu(y)
+                g = torch.autograd.grad(y, params, g_stem)
+            grads[id(conv1.weight)], grads[id(conv1.bias)] = g[0], g[1]
+            if norm1 is not None:
+                grads[id(norm1.weight)], grads[id(norm1.bias)] = g[2], g[3]
+        return grads
+
+    @staticmethod
+    def _param_grads(grads, rec, norm, ab, dbias):
+        pack = rec['pack']
+        if pack.bias_param is not None:
+            grads[id(pack.bias_param)] = dbias.to(torch.float32)
+        if norm is not None:
+            sums = ab.sum(0)
+            grads[id(norm.bias)] = sums[:, 0].to(torch.float32)
+            grads[id(norm.weight)] = sums[:, 1].to(torch.float32)
+
+
+class _FusedStep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, image, *params):
+        out, state = plan.forward(image)
+        ctx.plan, ctx.state, ctx.params = plan, state, params
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        grads = ctx.plan.backward(ctx.state, g_out)
+        ctx.state = None
+        return (None, None) + tuple(grads.get(id(p)) if ctx.needs_input_grad[2 + i] else None for i, p in enumerate(ctx.params))
+
+
+def forward_train(net, image):
+    """Differentiable forward of `net` through the fused plan (one autograd node for the whole network)."""
+    plan = getattr(net, '_train_plan', None)
+    if plan is None:
+        plan = net._train_plan = TrainPlan(net)
+    params = tuple(p for p in net.parameters())
+    return _FusedStep.apply(plan, image.contiguous().to(torch.float32), *params)

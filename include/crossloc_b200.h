@@ -129,6 +129,25 @@ int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const void* act, in
                      float out_scale, float* dw, void* cuda_stream);
 
 /*
+ * Backward of one "GroupNorm -> ReLU -> (residual merge -> ReLU)" stage on padded-flat tensors (training step):
+ * the autograd kernels behind nn.GroupNorm / F.relu / the residual adds (networks.py:231-254, 332-343;
+ * train_single_task.py:298).  pass 0 sums the `num_src` gradient sources (fp32 PF, each x two optional device
+ * scalars; `src_phased[i]` = 1 for the 4-phase result of a stride-2 data gradient), masks them with the sign of
+ * the stage's merged output (`mask_out`, fp16 hi plane, nullable), optionally stores the result in `g_out`, and
+ * accumulates ab[b][c] = (sum dy, sum dy * xhat) in fp64 plus the bits of max |dy * gamma| * rstd.  pass 1 reads
+ * src[0] only and writes d_raw = gradient of the raw convolution output as fp16 hi / lo PF planes x 2^k
+ * (scale_out = {2^k, 2^-k}, derived on the device), adding its per-channel sums to `dbias` (nullable).
+ * d_gamma = sum_b ab[b][c][1], d_beta = sum_b ab[b][c][0].  group_ch = 0: no normalisation (vanilla Network).
+ * Caller zeroes ab, gmax_bits, dbias; d_raw keeps zero border rows (only interior pixels are written).
+ */
+int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch, const float* raw, const double* stats,
+                   const float* gamma, const float* beta, float eps, int relu_inner, int num_src,
+                   const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
+                   const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out, double* ab,
+                   void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows, float* scale_out, double* dbias,
+                   void* cuda_stream);
+
+/*
  * Layout kernels of the training path (device pointers): NCHW fp32 tensors, as autograd hands them over, to and
  * from the operand layouts of cl_conv_igemm / cl_conv_wgrad, and filter packing.  `scale` arguments are device
  * scalars (power-of-two factors computed on the GPU, no host synchronisation), NULL = 1.

@@ -10,11 +10,14 @@ cuDNN/ATen.  `forward_reference` is the same network spelled with stock torch op
 definition the parity tests compare against and the autograd path of `train_single_task.py` until the
 backward kernels exist.  There is no CPU execution of the native path.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from crossloc_b200 import train as native_train
+from crossloc_b200 import train_plan
 from crossloc_b200.cnn import CoordNetEngine
 
 try:   # the reference logs through utils.io.safe_printout (networks.py:40); optional here
@@ -23,6 +26,7 @@ except Exception:   # pragma: no cover - reference utils not on the path
     def safe_printout(words):
         pass
 
+_FUSED_TRAIN = os.environ.get('CROSSLOC_B200_TRAIN', 'fused') != 'layerwise'
 _POS_CLAMP = (-16.10, 13.82)   # exp() range limiter of the uncertainty channel, networks.py:355-356
 
 
@@ -130,8 +134,14 @@ class Network(nn.Module):
         sc = conv(self.fc3, sc)
         return sc + self.mean.to(sc.device)[None, :, None, None]
 
-    def forward_train(self, inputs):
-        """Autograd path with the convolutions (forward, dgrad, wgrad) on the native tensor-core kernels."""
+    def forward_train(self, inputs, fused=None):
+        """Autograd path on the native kernels: the fused plan (crossloc_b200.train_plan: one autograd node, GroupNorm /
+        ReLU / residual backward and both convolution gradients on padded-flat tensors) or, with fused=False, the
+        per-layer path (conv forward / dgrad / wgrad as an autograd Function around stock pointwise ops)."""
+        if fused is None:
+            fused = _FUSED_TRAIN
+        if fused and inputs.is_cuda:
+            return train_plan.forward_train(self, inputs)
         return self.forward_reference(inputs, conv=native_train.conv2d)
 
     def forward(self, inputs):
@@ -418,10 +428,16 @@ class TransPoseNet(nn.Module):
             return self.decoder.forward_reference(res, up_height, up_width, conv)
         return self.decoder.forward_reference(res, conv=conv)
 
-    def forward_train(self, inputs):
-        """Autograd path: every eligible convolution runs its forward, dgrad and wgrad on the native tensor-core
-        kernels (crossloc_b200.train.NativeConv2d); GroupNorm, ReLU, the residual adds, the 3-channel stem and the
-        4-channel head stay stock torch ops in this round."""
+    def forward_train(self, inputs, fused=None):
+        """Autograd path on the native kernels.  Default: the fused plan (crossloc_b200.train_plan) -- the whole network
+        is one autograd node whose backward runs GroupNorm / ReLU / residual-merge backward, data and weight gradients
+        on padded-flat tensors; the 3-channel stem and the 4-channel head are differentiated with stock torch ops.
+        fused=False (or the MLR / full-size variants): every eligible convolution as crossloc_b200.train.NativeConv2d
+        between stock pointwise ops."""
+        if fused is None:
+            fused = _FUSED_TRAIN
+        if fused and inputs.is_cuda and train_plan.supported(self):
+            return train_plan.forward_train(self, inputs)
         return self.forward_reference(inputs, conv=native_train.conv2d)
 
     def forward(self, inputs):

@@ -51,8 +51,76 @@ def test_conv_forward_dgrad_wgrad_match_autograd(shape):
     assert rel(gb, gb_ref) < 1e-5
 
 
-def test_training_step_matches_reference_autograd():
-    """One TransPoseNet training step (coord MLE loss): loss and every gradient vs the stock-torch definition."""
+def _pf_rows(t):
+    """NCHW fp32 -> fp32 padded-flat matrix [B*(H+2)*(W+2)][C] with zero borders."""
+    return F.pad(t, (1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(-1, t.size(1)).contiguous()
+
+
+@pytest.mark.parametrize('case', [(64, 2, 9, 14, 'merge'), (256, 2, 7, 10, 'merge'), (512, 1, 6, 9, 'plain'),
+                                  (128, 2, 9, 13, 'phased'), (64, 1, 8, 8, 'nonorm')])
+def test_gn_backward_stage_matches_autograd(case):
+    """cl_gn_backward (both passes) vs autograd of out = relu(res + relu(GroupNorm(raw))) / relu(GroupNorm(raw))."""
+    from crossloc_b200 import layout
+    from crossloc_b200.cnn import _Geometry
+    from crossloc_b200.train_plan import TrainPlan, _Src
+    c, b, h, w, kind = case
+    torch.manual_seed(c + h)
+    norm = None if kind == 'nonorm' else torch.nn.GroupNorm(32, c).to(DEV)
+    if norm is not None:
+        with torch.no_grad():
+            norm.weight.uniform_(0.5, 1.5)
+            norm.bias.uniform_(-0.5, 0.5)
+    raw = (torch.randn(b, c, h, w, device=DEV) * 2 + 0.3).requires_grad_(True)
+    res = torch.rand(b, c, h, w, device=DEV) - 0.3
+    y = F.relu(raw if norm is None else norm(raw))
+    out = F.relu(res + y) if kind == 'merge' else y
+    g1, g2 = torch.randn_like(out) * 3e-4, torch.randn_like(out) * 1e-4
+    params = [raw] + ([] if norm is None else [norm.weight, norm.bias])
+    ref = torch.autograd.grad(out, params, g1 * 0.5 + g2 * 2.0)
+
+    geo = _Geometry(b, h, w)
+    raw_pf = _pf_rows(raw.detach())
+    groups = 32
+    stats = None
+    if norm is not None:
+        xr = raw.detach().double().reshape(b, groups, -1)
+        stats = torch.stack([xr.sum(-1), (xr * xr).sum(-1)], -1).contiguous()
+    half, two = torch.tensor([0.5], device=DEV), torch.tensor([2.0], device=DEV)
+    if kind == 'phased':   # gradient handed over as 4 parity phases at half resolution, 64 floats of row pitch more
+        hh, wh = (h + 1) // 2, (w + 1) // 2
+        ph = torch.zeros(4, b, c + 64, hh, wh, device=DEV)
+        for a in range(2):
+            for bb in range(2):
+                sub = (g1 * 0.5 + g2 * 2.0)[:, :, a::2, bb::2]
+                ph[a * 2 + bb, :, :c, :sub.size(2), :sub.size(3)] = sub
+        buf = torch.cat([_pf_rows(ph[i]) for i in range(4)], 0)
+        srcs = [_Src(buf, c + 64, None, None, phased=True)]
+    else:
+        srcs = [_Src(_pf_rows(g1), c, half, None), _Src(_pf_rows(g2), c, two, torch.ones(1, device=DEV))]
+    mask = layout.to_pf(out.detach(), 1, 2) if kind == 'merge' else None
+    plan = TrainPlan.__new__(TrainPlan)
+    plan._pool = {}
+    from crossloc_b200 import _lib
+    d_raw, scale_out, ab, dbias, g_buf = plan._gn_backward(
+        _lib.load(), torch.cuda.current_stream().cuda_stream, geo, c, {'raw': raw_pf, 'stats': stats}, norm, True, srcs, mask,
+        kind == 'merge' or len(srcs) > 1)
+    torch.cuda.synchronize()
+    got = layout.from_pf(d_raw, b, h, w, 2) * scale_out[1]
+    assert rel(got, ref[0]) < 2e-5
+    assert abs(float(scale_out[0] * scale_out[1]) - 1.0) < 1e-6
+    assert rel(dbias.float(), ref[0].sum((0, 2, 3))) < 1e-4 or float(ref[0].sum((0, 2, 3)).abs().max()) < 1e-7
+    if norm is not None:
+        assert rel(ab.sum(0)[:, 1].float(), ref[1]) < 1e-5
+        assert rel(ab.sum(0)[:, 0].float(), ref[2]) < 1e-5
+    if kind == 'merge':
+        g_ref = (g1 * 0.5 + g2 * 2.0) * (out.detach() > 0)
+        assert rel(layout.raw_to_nchw(g_buf, b, h, w), g_ref) < 1e-6
+
+
+@pytest.mark.parametrize('fused', [True, False])
+def test_training_step_matches_reference_autograd(fused):
+    """One TransPoseNet training step (coord MLE loss): loss and every gradient vs the stock-torch definition, through the
+    fused plan (crossloc_b200.train_plan) and through the per-layer path (crossloc_b200.train)."""
     import networks.networks as nets
     from loss.coord import scene_coords_regression_loss
     from tests.test_loss_cpu import pixel_grid
@@ -89,7 +157,7 @@ def test_training_step_matches_reference_autograd():
         return worst, errs[worst]
 
     loss_ref, g_ref = grads(net.forward_reference, 'probe')
-    loss_nat, g_nat = grads(net.forward_train, 'probe')
+    loss_nat, g_nat = grads(lambda t: net.forward_train(t, fused=fused), 'probe')
     assert abs(float(loss_nat) - float(loss_ref)) < 1e-4 * abs(float(loss_ref))
     # Every kernel agrees with autograd to ~1e-6 in isolation (test above), but this toy network has only 24k
     # activations per layer: a single ReLU whose pre-activation lies within the 1e-5 forward difference of zero
@@ -102,7 +170,7 @@ def test_training_step_matches_reference_autograd():
     # the reference's loss (train_single_task.py:279-283): same value; its gradient is piecewise (validity masks,
     # soft clamp) over only 192 cells here, so one cell changing side moves every gradient by ~0.5 %
     loss_ref, g_ref = grads(net.forward_reference, 'mle')
-    loss_nat, g_nat = grads(net.forward_train, 'mle')
+    loss_nat, g_nat = grads(lambda t: net.forward_train(t, fused=fused), 'mle')
     assert abs(float(loss_nat) - float(loss_ref)) < 1e-5 * abs(float(loss_ref))
     name, err = worst_error(g_nat, g_ref)
     assert err < 5e-2, (name, err)

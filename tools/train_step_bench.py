@@ -2,8 +2,8 @@
 """BASELINE config 4: one train_single_task.py-shaped step (coord MLE loss, forward + backward, Adam) at 480x720.
 
     python tools/train_step_bench.py [batch] [steps]
-Times the native path (tensor-core conv forward / dgrad / wgrad through crossloc_b200.train) and, for context,
-the same step through stock autograd (cuDNN) on the same GPU.
+Times the native fused plan (crossloc_b200.train_plan), the per-layer native path (crossloc_b200.train) and, for
+context, the same step through stock autograd (cuDNN, TF32 allowed as torch's default) on the same GPU.
 """
 import json
 import os
@@ -37,7 +37,10 @@ def main():
     cam[0, 2], cam[1, 2] = 360.0, 240.0
     grid = pixel_grid().to(dev)
     out = {}
-    for name, fwd in (('native', net.forward_train), ('torch_autograd_cudnn', net.forward_reference)):
+    variants = (('native_fused', lambda t: net.forward_train(t, fused=True)),
+                ('native_layerwise', lambda t: net.forward_train(t, fused=False)),
+                ('torch_autograd_cudnn', net.forward_reference))
+    for name, fwd in variants:
         times = []
         for i in range(steps + 1):
             torch.cuda.synchronize()
