@@ -26,11 +26,9 @@ SIGNATURES = {
         _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _i32p, _c.c_int,
         _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p,
         _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p]),
-    'cl_conv_wgrad': (_c.c_int, [
-        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _i32p, _i32p,
-        _c.c_int, _c.c_float, _c.c_void_p, _c.c_void_p]),
     'cl_conv_wgrad_pf': (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
-                                    _c.c_int, _i32p, _i32p, _c.c_int, _c.c_float, _c.c_void_p, _c.c_void_p]),
+                                    _c.c_int, _i32p, _i32p, _c.c_int, _c.c_float, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                    _c.c_void_p]),
     'cl_gn_backward': (_c.c_int, [
         _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
         _c.c_float, _c.c_int, _c.c_int, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _i32p,
@@ -40,8 +38,6 @@ SIGNATURES = {
                                  _c.c_void_p]),
     'cl_pf_to_nchw': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,
                                  _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
-    'cl_nchw_to_cm': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
-                                 _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _i32p, _i32p, _i32p, _c.c_void_p]),
     'cl_pow2_scale': (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_float, _c.c_void_p, _c.c_void_p]),
     'cl_pack_filter': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _i32p,
                                   _i32p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),

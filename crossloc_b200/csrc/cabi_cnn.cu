@@ -57,26 +57,6 @@ extern "C" int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo
     return finish(kFn, cl::conv_igemm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 
-extern "C" int cl_conv_wgrad(const void* grad, const void* act, int B, int Cout, int Cin, int plane, int plane_stride,
-                             int phases, int num_taps, const int32_t* tap_shift, const int32_t* tap_phase, int nterms,
-                             float out_scale, float* dw, void* cuda_stream)
-{
-    static const char* kFn = "cl_conv_wgrad";
-    NEED_DEV(grad); NEED_DEV(act); NEED_DEV(dw);
-    if (!tap_shift || !tap_phase) return cl::fail(-1, "%s: tap tables must not be NULL", kFn);
-    if (num_taps < 1 || num_taps > 9) return cl::fail(-1, "%s: num_taps=%d out of range", kFn, num_taps);
-    if (B <= 0 || plane <= 0 || phases < 1 || phases > 16) return cl::fail(-1, "%s: invalid sizes", kFn);
-    for (int i = 0; i < num_taps; i++)
-        if (tap_shift[i] % 8 != 0)   // TMA needs 16-byte aligned box starts along the pixel axis
-            return cl::fail(-1, "%s: tap_shift[%d]=%d is not a multiple of 8 pixels (use column-shifted copies)", kFn, i, tap_shift[i]);
-    cl::ConvWgradDesc d{};
-    d.grad = grad; d.act = act; d.B = B; d.Cout = Cout; d.Cin = Cin; d.plane = plane; d.plane_stride = plane_stride;
-    d.phases = phases; d.num_taps = num_taps;
-    for (int i = 0; i < num_taps; i++) { d.tap_shift[i] = tap_shift[i]; d.tap_phase[i] = tap_phase[i]; }
-    d.nterms = nterms; d.out_scale = out_scale; d.dw = dw;
-    return finish(kFn, cl::conv_wgrad_launch(d, static_cast<cudaStream_t>(cuda_stream)));
-}
-
 extern "C" int cl_nchw_to_pf(const float* x, const float* scale, void* out, int B, int C, int H, int W, int phases,
                              void* cuda_stream)
 {
@@ -97,22 +77,6 @@ extern "C" int cl_pf_to_nchw(const float* raw, int B, int H, int W, int Craw, fl
     if (step != 1 && step != 2) return cl::fail(-1, "%s: step must be 1 or 2", kFn);
     cl::PfToNchwDesc d{raw, B, H, W, Craw, out, C, Hout, Wout, step, off_y, off_x, scale, bias};
     return finish(kFn, cl::pf_to_nchw_launch(d, static_cast<cudaStream_t>(cuda_stream)));
-}
-
-extern "C" int cl_nchw_to_cm(const float* x, const float* scale, void* out, int B, int C, int H, int W, int hp, int wp,
-                             int rows, int cols, int step, int groups, const int32_t* pa, const int32_t* pb,
-                             const int32_t* col0, void* cuda_stream)
-{
-    static const char* kFn = "cl_nchw_to_cm";
-    NEED_DEV(x); NEED_DEV(out);
-    if (scale) NEED_DEV(scale);
-    if (!pa || !pb || !col0) return cl::fail(-1, "%s: group tables must not be NULL", kFn);
-    if (groups < 1 || groups > 8) return cl::fail(-1, "%s: groups=%d out of range", kFn, groups);
-    cl::NchwToCmDesc d{};
-    d.x = x; d.scale = scale; d.out = static_cast<__half*>(out); d.B = B; d.C = C; d.H = H; d.W = W; d.hp = hp; d.wp = wp;
-    d.rows = rows; d.cols = cols; d.step = step; d.groups = groups;
-    for (int g = 0; g < groups; g++) { d.pa[g] = pa[g]; d.pb[g] = pb[g]; d.col0[g] = col0[g]; }
-    return finish(kFn, cl::nchw_to_cm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 
 extern "C" int cl_pow2_scale(const float* x, int64_t n, float target, void* workspace, void* cuda_stream)
@@ -211,10 +175,12 @@ extern "C" int cl_duc_head_forward(const float* raw, int B, int Hc, int Wc, int 
 
 extern "C" int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const void* act, int64_t x_plane_rows, int Mp,
                                 int Cout, int Cin, int phases, int num_taps, const int32_t* tap_shift,
-                                const int32_t* tap_phase, int nterms, float out_scale, float* dw, void* cuda_stream)
+                                const int32_t* tap_phase, int nterms, float out_scale, const float* scale_dev, int oihw,
+                                float* dw, void* cuda_stream)
 {
     static const char* kFn = "cl_conv_wgrad_pf";
     NEED_DEV(grad); NEED_DEV(act); NEED_DEV(dw);
+    if (scale_dev) NEED_DEV(scale_dev);
     if (!tap_shift || !tap_phase) return cl::fail(-1, "%s: tap tables must not be NULL", kFn);
     if (num_taps < 1 || num_taps > 9) return cl::fail(-1, "%s: num_taps=%d out of range", kFn, num_taps);
     if (Mp <= 0 || phases < 1 || phases > 4) return cl::fail(-1, "%s: invalid sizes", kFn);
@@ -224,7 +190,7 @@ extern "C" int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const vo
     d.grad = grad; d.g_plane_rows = g_plane_rows; d.act = act; d.x_plane_rows = x_plane_rows; d.Mp = Mp; d.Cout = Cout;
     d.Cin = Cin; d.phases = phases; d.num_taps = num_taps;
     for (int i = 0; i < num_taps; i++) { d.tap_shift[i] = tap_shift[i]; d.tap_phase[i] = tap_phase[i]; }
-    d.nterms = nterms; d.out_scale = out_scale; d.dw = dw;
+    d.nterms = nterms; d.out_scale = out_scale; d.scale_dev = scale_dev; d.oihw = oihw; d.dw = dw;
     return finish(kFn, cl::conv_wgrad_pf_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 

@@ -60,35 +60,6 @@ struct ConvIgemmParams {
 // returns nullptr on success, else a static error string
 const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream);
 
-// ---------------------------------------------------------------- weight gradient (training path)
-// dW[tap][co][ci] = sum over images and pixels of dY[b][co][p] * X[b][ci][p + shift(tap)] on channel-major
-// ("CM") fp16 matrices [term][phase][image][channel][plane_stride] (zero-bordered planes, pixel index fastest).
-struct ConvWgradDesc {
-    const void* grad;       // dY, CM, terms x B x Cout planes
-    const void* act;        // X, CM, terms x phases x B x Cin planes
-    int B, Cout, Cin;
-    int plane;              // pixels per padded plane (H + 2) * (W + 2) at the OUTPUT resolution
-    int plane_stride;       // row pitch in elements (plane rounded up to a multiple of 8)
-    int phases;             // 1, or 4 for a stride-2 convolution
-    int num_taps;
-    int tap_shift[9];       // pixel shift of X for each tap
-    int tap_phase[9];       // phase plane of X for each tap
-    int nterms;             // 1 or 3
-    float out_scale;
-    float* dw;              // fp32 [tap][Cout][Cin], accumulated with atomics: caller zeroes it
-};
-const char* conv_wgrad_launch(const ConvWgradDesc& d, cudaStream_t stream);
-
-struct ConvWgradParams {
-    int num_taps;
-    int tap_shift[9], tap_phase[9];
-    int B, Cout, Cin, BN, tiles_co, tiles_ci, splits, images_per_split, plane_kblocks, phases, nterms;
-    float out_scale;
-    float* dw;
-    int num_stages, accum_stages;
-    uint32_t a_bytes, w_bytes, stage_bytes;
-};
-
 // ---------------------------------------------------------------- weight gradient on padded-flat operands
 // dW[tap][co][ci] += out_scale * sum over PF rows r of dY[r][co] * X[tap_phase][r + tap_shift][ci]; both operands
 // are the [pixel rows][channels] matrices of the forward / GroupNorm-backward kernels (MN-major tensor-core operands).
@@ -104,7 +75,9 @@ struct ConvWgradPfDesc {
     int tap_phase[9];       // phase plane of X for each tap
     int nterms;             // 1 or 3
     float out_scale;
-    float* dw;              // fp32 [tap][Cout][Cin], accumulated with atomics: caller zeroes it
+    const float* scale_dev; // nullable device scalar multiplied into the result (the 2^-k of a rescaled gradient)
+    int oihw;               // 0: dw is [tap][Cout][Cin];  1: [Cout][Cin][taps], i.e. torch's OIHW weight layout
+    float* dw;              // fp32, accumulated with atomics: caller zeroes it
 };
 const char* conv_wgrad_pf_launch(const ConvWgradPfDesc& d, cudaStream_t stream);
 
@@ -126,19 +99,6 @@ struct PfToNchwDesc {
     const float* bias;      // nullable [C]
 };
 const char* pf_to_nchw_launch(const PfToNchwDesc& d, cudaStream_t stream);
-
-struct NchwToCmDesc {
-    const float* x;         // NCHW fp32 [B][C][H][W]
-    const float* scale;     // nullable device scalar
-    __half* out;            // CM hi/lo [2][groups][B][C][hp*wp]
-    int B, C, H, W;
-    int hp, wp;             // padded plane; source pixel (r, q) of group g lands at row r + 1, column q + col0[g]
-    int rows, cols;         // valid source extent of a plane (output resolution of the convolution)
-    int step;               // 1, or 2: group g holds the parity phase (pa[g], pb[g]) of x
-    int groups;
-    int pa[8], pb[8], col0[8];
-};
-const char* nchw_to_cm_launch(const NchwToCmDesc& d, cudaStream_t stream);
 
 // {2^k, 2^-k} with k = floor(log2(target / max|x|)); scratch: two 32-bit words (zeroed by the launch), out: two floats
 const char* pow2_scale_launch(const float* x, size_t n, float target, unsigned* scratch, float* out, cudaStream_t stream);

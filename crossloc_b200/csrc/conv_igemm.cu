@@ -643,163 +643,6 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Weight gradient: D[co][ci] += sum_k dY[co][k] * X[ci][k + shift(tap)], k = pixel index inside the padded plane
-// of one image.  Both operands are channel-major, i.e. K-major for the tensor core, so the same shared-memory
-// descriptors as the forward kernel apply; the K loop runs over (image, 64-pixel block) and is split over CTAs,
-// partial tiles are accumulated into dW with fp32 atomics.  Border pixels of dY are zero, so garbage-free.
-template <int BK>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
-                  const ConvWgradParams p)
-{
-    constexpr int kSwizzle = BK * 2;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t tfull_bar[2];
-    __shared__ __align__(8) uint64_t tempty_bar[2];
-    __shared__ uint32_t tmem_base_s;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int nA = p.nterms == 3 ? 2 : 1;
-    const int items = p.num_taps * p.tiles_co * p.tiles_ci * p.splits;
-
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&tmG);
-        ptx::prefetch_tensormap(&tmX);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.num_stages; s++) {
-            ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
-            ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
-        }
-        for (int s = 0; s < 2; s++) {
-            ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
-            ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 4);
-        }
-        ptx::fence_mbar_init();
-    }
-    if (warp == 2) {
-        ptx::tmem_alloc(ptx::smem_u32(&tmem_base_s), kTmemCols);
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-
-    // item -> (tap, co tile, ci tile, split); split fastest so that CTAs working on one dW tile run together
-    auto decode = [&](int item, int& tap, int& co0, int& ci0, int& b0, int& b1) {
-        const int split = item % p.splits;
-        int r = item / p.splits;
-        const int tci = r % p.tiles_ci; r /= p.tiles_ci;
-        const int tco = r % p.tiles_co;
-        tap = r / p.tiles_co;
-        co0 = tco * kBlockM;
-        ci0 = tci * p.BN;
-        b0 = split * p.images_per_split;
-        b1 = b0 + p.images_per_split < p.B ? b0 + p.images_per_split : p.B;
-    };
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)nA * (p.a_bytes + p.w_bytes);
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                int tap, co0, ci0, b0, b1;
-                decode(item, tap, co0, ci0, b0, b1);
-                const int shift = p.tap_shift[tap];
-                for (int b = b0; b < b1; b++) {
-                    const int xplane = p.tap_phase[tap] * p.B + b;
-                    for (int kb = 0; kb < p.plane_kblocks; kb++) {
-                        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
-                        const uint32_t bar = ptx::smem_u32(&full_bar[stage]);
-                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
-                        const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
-                        ptx::mbar_expect_tx(bar, tx_bytes);
-                        ptx::tma_load_3d(sa, &tmG, bar, kb * BK, co0, b);
-                        ptx::tma_load_3d(sw, &tmX, bar, kb * BK + shift, ci0, xplane);
-                        if (nA == 2) {
-                            ptx::tma_load_3d(sa + p.a_bytes, &tmG, bar, kb * BK, co0, p.B + b);
-                            ptx::tma_load_3d(sw + p.w_bytes, &tmX, bar, kb * BK + shift, ci0, p.phases * p.B + xplane);
-                        }
-                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        const uint32_t idesc = ptx::make_idesc_f16(kBlockM, p.BN);
-        int stage = 0, local = 0;
-        uint32_t phase = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, local++) {
-            int tap, co0, ci0, b0, b1;
-            decode(item, tap, co0, ci0, b0, b1);
-            const int kblocks = (b1 - b0) * p.plane_kblocks;
-            const int as = local % p.accum_stages;
-            const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
-            ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aphase ^ 1u);
-            ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.BN);
-            for (int kbi = 0; kbi < kblocks; kbi++) {
-                ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
-                ptx::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
-                    const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
-                    for (int term = 0; term < p.nterms; term++) {
-                        const uint32_t a_addr = sa + (term == 1 ? p.a_bytes : 0u);
-                        const uint32_t w_addr = sw + (term == 2 ? p.w_bytes : 0u);
-#pragma unroll
-                        for (int k = 0; k < BK / 16; k++) {
-                            const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(a_addr + k * 32);
-                            const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(w_addr + k * 32);
-                            ptx::mma_f16_ss(tmem_d, da, db, idesc, (kbi | term | k) != 0 ? 1u : 0u);
-                        }
-                    }
-                    ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));
-                    if (kbi == kblocks - 1) ptx::mma_commit(ptx::smem_u32(&tfull_bar[as]));
-                }
-                __syncwarp();
-                if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
-            }
-        }
-    } else if (warp >= 4) {
-        const int q = warp & 3;
-        int local = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, local++) {
-            int tap, co0, ci0, b0, b1;
-            decode(item, tap, co0, ci0, b0, b1);
-            const int as = local % p.accum_stages;
-            const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
-            ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
-            const int co = co0 + q * 32 + lane;
-            float* dst = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + ci0;
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
-                uint32_t u[32];
-                ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
-                ptx::tmem_ld_wait();
-                if (co < p.Cout && b1 > b0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) atomicAdd(dst + c0 + j, __uint_as_float(u[j]) * p.out_scale);
-                }
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
-        }
-    }
-
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -950,73 +793,6 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
         e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<32>, tmA, tmW, tmO, tmA8, tmW8, p);
     }
     if (e != cudaSuccess) return cudaGetErrorString(e);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
-}
-
-// channel-major fp16 matrix [planes][channels][plane_stride]: 3-D map, box = 1 plane x box_ch channels x box_px pixels;
-// the innermost extent is the true plane size so that reads past the plane (and negative shifts) return zeros
-static bool make_cm_tensor_map(CUtensorMap* map, const void* base, uint64_t planes, uint64_t channels, uint64_t plane,
-                               uint64_t plane_stride, uint32_t box_ch, uint32_t box_px)
-{
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) return false;
-    const cuuint64_t dims[3] = {plane, channels, planes};
-    const cuuint64_t strides[2] = {plane_stride * 2, plane_stride * channels * 2};
-    const cuuint32_t box[3] = {box_px, box_ch, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-const char* conv_wgrad_launch(const ConvWgradDesc& d, cudaStream_t stream)
-{
-    if (d.Cout % 128 != 0 && d.Cout != 64) return "conv_wgrad: Cout must be 64 or a multiple of 128";
-    if (d.Cin % 32 != 0) return "conv_wgrad: Cin must be a multiple of 32";
-    if (d.nterms != 1 && d.nterms != 3) return "conv_wgrad: nterms must be 1 or 3";
-    if (d.plane_stride % 8 != 0 || d.plane_stride < d.plane) return "conv_wgrad: plane_stride must be a multiple of 8 >= plane";
-    constexpr int BK = 64;
-    const int BN = d.Cin % 256 == 0 ? 256 : (d.Cin % 128 == 0 ? 128 : (d.Cin % 64 == 0 ? 64 : 32));
-    const int nA = d.nterms == 3 ? 2 : 1;
-    ConvWgradParams p{};
-    p.num_taps = d.num_taps;
-    for (int i = 0; i < d.num_taps; i++) { p.tap_shift[i] = d.tap_shift[i]; p.tap_phase[i] = d.tap_phase[i]; }
-    p.B = d.B; p.Cout = d.Cout; p.Cin = d.Cin; p.BN = BN;
-    p.tiles_co = (d.Cout + kBlockM - 1) / kBlockM;
-    p.tiles_ci = d.Cin / BN;
-    p.phases = d.phases; p.nterms = d.nterms; p.out_scale = d.out_scale; p.dw = d.dw;
-    p.plane_kblocks = (d.plane + BK - 1) / BK;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int tiles = d.num_taps * p.tiles_co * p.tiles_ci;
-    int splits = (2 * sms + tiles - 1) / tiles;          // about two items per SM
-    if (splits > d.B) splits = d.B;
-    if (splits < 1) splits = 1;
-    p.images_per_split = (d.B + splits - 1) / splits;
-    p.splits = (d.B + p.images_per_split - 1) / p.images_per_split;
-    p.a_bytes = (uint32_t)(kBlockM * BK * 2);
-    p.w_bytes = (uint32_t)(BN * BK * 2);
-    p.stage_bytes = (uint32_t)nA * (p.a_bytes + p.w_bytes);
-    p.num_stages = (227 * 1024 - 2048) / (int)p.stage_bytes;
-    if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
-    if (p.num_stages < 2) return "conv_wgrad: tile does not fit two pipeline stages";
-    p.accum_stages = 2 * BN <= (int)kTmemCols ? 2 : 1;
-    const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024;
-
-    CUtensorMap tmG, tmX;
-    if (!make_cm_tensor_map(&tmG, d.grad, (uint64_t)nA * d.B, (uint64_t)d.Cout, (uint64_t)d.plane, (uint64_t)d.plane_stride,
-                            kBlockM, BK))   // rows past Cout are zero-filled: the box is always a full 128-row tile
-        return "conv_wgrad: cuTensorMapEncodeTiled failed for the gradient matrix";
-    if (!make_cm_tensor_map(&tmX, d.act, (uint64_t)nA * d.phases * d.B, (uint64_t)d.Cin, (uint64_t)d.plane,
-                            (uint64_t)d.plane_stride, BN, BK))
-        return "conv_wgrad: cuTensorMapEncodeTiled failed for the activation matrix";
-    const int items = tiles * p.splits;
-    const int grid = items < sms ? items : sms;
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    conv_wgrad_kernel<64><<<grid, kThreads, smem, stream>>>(tmG, tmX, p);
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

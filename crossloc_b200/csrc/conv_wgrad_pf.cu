@@ -35,6 +35,8 @@ struct WgradPfParams {
     int Cout, Cin, BN, tiles_co, tiles_ci, splits, kb_per_split, total_kb, phases, nterms;
     int inner_g, inner_x;            // channels per swizzle row (64, or 32 for 32-channel tensors)
     float out_scale;
+    const float* scale_dev;          // nullable device scalar multiplied into the result
+    int oihw;                        // 1: dw is [Cout][Cin][taps] (torch's OIHW weight layout), 0: [tap][Cout][Cin]
     float* dw;
     int num_stages, accum_stages;
     uint32_t a_bytes, w_bytes, stage_bytes;
@@ -187,14 +189,17 @@ conv_wgrad_pf_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
             const int co = co0 + q * 32 + lane;
-            float* dst = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + ci0;
+            const float scale = p.out_scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+            const size_t estride = p.oihw ? (size_t)p.num_taps : 1;
+            float* dst = p.oihw ? p.dw + ((size_t)co * p.Cin + ci0) * p.num_taps + tap
+                                : p.dw + ((size_t)tap * p.Cout + co) * p.Cin + ci0;
             for (int c0 = 0; c0 < p.BN; c0 += 32) {
                 uint32_t u[32];
                 ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
                 ptx::tmem_ld_wait();
                 if (co < p.Cout) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) atomicAdd(dst + c0 + j, __uint_as_float(u[j]) * p.out_scale);
+                    for (int j = 0; j < 32; j++) atomicAdd(dst + (size_t)(c0 + j) * estride, __uint_as_float(u[j]) * scale);
                 }
             }
             ptx::tc_fence_before();
@@ -260,6 +265,7 @@ const char* conv_wgrad_pf_launch(const ConvWgradPfDesc& d, cudaStream_t stream)
     p.tiles_co = (d.Cout + kBlockM - 1) / kBlockM;
     p.tiles_ci = d.Cin / BN;
     p.phases = d.phases; p.nterms = d.nterms; p.out_scale = d.out_scale; p.dw = d.dw;
+    p.scale_dev = d.scale_dev; p.oihw = d.oihw;
     p.inner_g = 64;
     p.inner_x = d.Cin >= 64 ? 64 : 32;
     p.total_kb = (d.Mp + kBK - 1) / kBK;

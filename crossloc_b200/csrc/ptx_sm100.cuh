@@ -70,14 +70,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
-// 3-D tiled load (c0 innermost): used for channel-major [image][channel][pixel] matrices.
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
-        ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
 // Same, multicast: the box lands at the same shared-memory offset of every CTA in cta_mask, and each of those
 // CTAs' mbarrier (same offset) receives the complete_tx.
 __device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,

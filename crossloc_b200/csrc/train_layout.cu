@@ -3,8 +3,6 @@
 //
 //   nchw_to_pf   activations or output gradients -> padded-flat pixel-major [term][phase][B*(H+2)*(W+2)][C]
 //                (operand of cl_conv_igemm: forward and data gradient)
-//   nchw_to_cm   -> channel-major planes [term][group][B][C][hp*wp] with per-group parity phase and column shift
-//                (operands of cl_conv_wgrad)
 //   pf_to_nchw   raw fp32 padded-flat result -> NCHW (optionally into one parity phase of a 2x larger tensor:
 //                the per-phase results of a stride-2 data gradient), x scale, + bias
 //   pack_filter  OIHW fp32 filter -> fp16 hi/lo [2][tap][N][K] for a tap subset, optionally transposed
@@ -95,31 +93,6 @@ __global__ void __launch_bounds__(256) pf_to_nchw_kernel(PfToNchwDesc d)
     }
 }
 
-// one block per (plane row, channel, group x image): threads run along the row, hi and lo planes written in full
-// (zero padding included), no per-element index arithmetic beyond one multiply-add
-__global__ void __launch_bounds__(128) nchw_to_cm_kernel(NchwToCmDesc d)
-{
-    const int row = blockIdx.x, c = blockIdx.y;
-    const int g = blockIdx.z / d.B, b = blockIdx.z % d.B;
-    const size_t plane = (size_t)d.hp * d.wp;
-    const size_t per_term = (size_t)d.groups * d.B * d.C * plane;
-    const size_t base = (((size_t)g * d.B + b) * d.C + c) * plane + (size_t)row * d.wp;
-    const float sc = d.scale ? __ldg(d.scale) : 1.f;
-    const int yy = (row - 1) * d.step + d.pa[g];
-    const bool row_ok = row >= 1 && row - 1 < d.rows && yy < d.H;
-    const float* src = d.x + (((size_t)b * d.C + c) * d.H + (row_ok ? yy : 0)) * d.W;
-    const int col0 = d.col0[g], pb = d.pb[g];
-    for (int col = threadIdx.x; col < d.wp; col += 128) {
-        const int q = col - col0, xx = q * d.step + pb;
-        float v = 0.f;
-        if (row_ok && q >= 0 && q < d.cols && xx < d.W) v = __ldg(src + xx) * sc;
-        __half hi, lo;
-        split2(v, hi, lo);
-        d.out[base + col] = hi;
-        d.out[base + col + per_term] = lo;
-    }
-}
-
 // amax -> power-of-two scale, one launch: every block folds its maximum into scratch[0] (float bits of a
 // non-negative value order like unsigned integers), the last block to finish writes {2^k, 2^-k} with
 // k = floor(log2(target / amax)).  scratch = two zeroed 32-bit words.
@@ -200,15 +173,6 @@ const char* pf_to_nchw_launch(const PfToNchwDesc& d, cudaStream_t stream)
     if ((long long)d.B * ((d.C + 31) / 32) > 65535 || d.H > 65535) return "pf_to_nchw: grid too large";
     if (d.B == 0) return nullptr;
     pf_to_nchw_kernel<<<dim3((d.W + 31) / 32, d.H, d.B * ((d.C + 31) / 32)), dim3(32, 8), 0, stream>>>(d);
-    return last_error();
-}
-
-const char* nchw_to_cm_launch(const NchwToCmDesc& d, cudaStream_t stream)
-{
-    if (d.groups < 1 || d.groups > 8) return "nchw_to_cm: 1..8 plane groups";
-    if (d.C > 65535 || (long long)d.groups * d.B > 65535) return "nchw_to_cm: grid too large";
-    if (d.B == 0 || d.C == 0) return nullptr;
-    nchw_to_cm_kernel<<<dim3(d.hp, d.C, d.groups * d.B), 128, 0, stream>>>(d);
     return last_error();
 }
 

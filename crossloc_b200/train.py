@@ -180,10 +180,11 @@ def conv_wgrad(gy, x, weight_shape, stride, operand=None, act=None):
         ph = (t + geo.Mp // 2) // geo.Mp if stride == 2 else 0
         tphase.append(ph)
         shifts.append(t - ph * geo.Mp)
-    dw = torch.zeros(k * k, cout, cin, dtype=torch.float32, device=g_pf.device)
+    dw = torch.zeros(cout, cin, k, k, dtype=torch.float32, device=g_pf.device)   # written in OIHW, x 2^-k, by the kernel
     _lib.check(lib.cl_conv_wgrad_pf(g_pf.data_ptr(), geo.Mp, act.data_ptr(), geo.Mp, geo.Mp, cout, cin, phases, k * k,
-                                    _i32(shifts), _i32(tphase), _NTERMS, 1.0, dw.data_ptr(), _stream(g_pf)))
-    return (dw * gs_inv).reshape(k, k, cout, cin).permute(2, 3, 0, 1).contiguous()
+                                    _i32(shifts), _i32(tphase), _NTERMS, 1.0, gs_inv.data_ptr(), 1, dw.data_ptr(),
+                                    _stream(g_pf)))
+    return dw
 
 
 class NativeConv2d(torch.autograd.Function):

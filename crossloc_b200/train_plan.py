@@ -17,6 +17,7 @@ with stock torch ops (0.2 % of the FLOPs).  Covers TransPoseNet / Network withou
 the other variants keep using the per-layer path.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -26,6 +27,9 @@ from .cnn import CoordNetEngine, _Geometry
 from .train import _forward_taps, _i32, _pack, _stream
 
 _NTERMS = 3
+# arithmetic of the data / weight gradient GEMMs: 'fp16x3' (default, fp32-grade like the forward) or 'fp16x1' (one
+# fp16 pass with fp32 accumulation: the 10-bit mantissa of the TF32 kernels stock PyTorch trains with by default)
+BACKWARD = os.environ.get('CROSSLOC_B200_TRAIN_BACKWARD', 'fp16x3')
 _RESCALE_EVERY = 64   # steps between host-side refreshes of the filters' power-of-two scales
 
 
@@ -59,8 +63,13 @@ def supported(net):
 
 
 class TrainPlan:
-    def __init__(self, net):
+    def __init__(self, net, backward=None):
         self.net = net
+        backward = backward or BACKWARD
+        if backward not in ('fp16x3', 'fp16x1'):
+            raise ValueError('unknown backward arithmetic %r (fp16x3 | fp16x1)' % (backward,))
+        self.bwd_terms = 3 if backward == 'fp16x3' else 1
+        self._zero_bias = {}
         self.engine = CoordNetEngine(precision='fp16x3')
         self.engine.packer = self._packer
         self._exps = {}
@@ -102,10 +111,12 @@ class TrainPlan:
     def _gn_backward(self, lib, stream, geo, channels, rec, norm, relu_inner, srcs, mask, want_g):
         """Both passes of cl_gn_backward for one stage; returns (d_raw, scale_out, ab, dbias, g_buf)."""
         dev = rec['raw'].device
-        ab = torch.zeros(geo.B, channels, 2, dtype=torch.float64, device=dev)
-        gmax = torch.zeros(1, dtype=torch.int32, device=dev)
-        dbias = torch.zeros(channels, dtype=torch.float64, device=dev)
-        scale_out = torch.empty(2, dtype=torch.float32, device=dev)
+        n_ab = geo.B * channels * 2
+        z = torch.zeros(n_ab + channels + 2, dtype=torch.float64, device=dev)   # one fill for all the accumulators
+        ab = z[:n_ab].view(geo.B, channels, 2)
+        dbias = z[n_ab:n_ab + channels]
+        gmax = z[n_ab + channels:n_ab + channels + 1].view(torch.int32)
+        scale_out = z[n_ab + channels + 1:].view(torch.float32)
         g_buf = torch.empty(geo.Mp, channels, dtype=torch.float32, device=dev) if want_g else None
         d_raw = self._zeros_pf(geo, channels, dev)
         group_ch = 0 if norm is None else channels // norm.num_groups
@@ -129,8 +140,8 @@ class TrainPlan:
         call(1, [_Src(g_buf, channels)] if want_g else srcs[:1])
         return d_raw, scale_out, ab, dbias, g_buf
 
-    def _conv_backward(self, lib, stream, rec, d_raw, scale_out, need_dgrad):
-        """Weight gradient (always) and data gradient (as a source for the producer of the conv's input)."""
+    def _conv_backward(self, lib, stream, rec, d_raw, scale_out, need_dgrad, gw):
+        """Weight gradient into `gw` (zeroed OIHW tensor) and data gradient (a source for the producer of the input)."""
         pack, geo, act = rec['pack'], rec['geo'], rec['act']
         k, stride, cin, cout = pack.ksize, pack.stride, pack.cin, pack.cout
         dev = d_raw.device
@@ -140,20 +151,21 @@ class TrainPlan:
             ph = (t + geo.Mp // 2) // geo.Mp if stride == 2 else 0
             tphase.append(ph)
             shifts.append(t - ph * geo.Mp)
-        dw = torch.zeros(k * k, cout, cin, dtype=torch.float32, device=dev)
         _lib.check(lib.cl_conv_wgrad_pf(d_raw.data_ptr(), geo.Mp, act.h16.data_ptr(), geo.Mp, geo.Mp, cout, cin, act.phases,
-                                        k * k, _i32(shifts), _i32(tphase), _NTERMS, 1.0, dw.data_ptr(), stream))
-        gw = (dw * scale_out[1:2]).reshape(k, k, cout, cin).permute(2, 3, 0, 1).contiguous()
+                                        k * k, _i32(shifts), _i32(tphase), self.bwd_terms, 1.0, scale_out[1:2].data_ptr(), 1,
+                                        gw.data_ptr(), stream))
         if not need_dgrad:
-            return gw, None
+            return None
         # ---- data gradient: transposed filter, negated tap shifts; one small problem per input parity for stride 2
         n_out = (cin + 63) // 64 * 64
-        zero_bias = torch.zeros(n_out, dtype=torch.float32, device=dev)
+        zero_bias = self._zero_bias.get((n_out, str(dev)))
+        if zero_bias is None:
+            zero_bias = self._zero_bias[(n_out, str(dev))] = torch.zeros(n_out, dtype=torch.float32, device=dev)
 
         def igemm(pairs, shifts, raw):
             packed = _pack(pack.weight, pack.scale, pairs, True, n_out, cout)
             _lib.check(lib.cl_conv_igemm(d_raw.data_ptr(), d_raw.size(0), geo.Mp, cout, packed.data_ptr(), n_out,
-                                         len(shifts), _i32(shifts), _NTERMS, geo.Mp, geo.Hp, geo.Wp, 0, 1.0,
+                                         len(shifts), _i32(shifts), self.bwd_terms, geo.Mp, geo.Hp, geo.Wp, 0, 1.0,
                                          raw.data_ptr(), zero_bias.data_ptr(), 0, 0, 0, 0, 0, stream))
 
         if stride == 1:
@@ -163,8 +175,8 @@ class TrainPlan:
             else:
                 pairs = [(kh, kw) for kh in range(3) for kw in range(3)]
                 igemm(pairs, [(1 - kh) * geo.Wp + (1 - kw) for kh, kw in pairs], raw)
-            return gw, _Src(raw, n_out, scale_out[1:2], pack.inv_scale, phased=False)
-        raw = torch.zeros(4 * geo.Mp, n_out, dtype=torch.float32, device=dev)
+            return _Src(raw, n_out, scale_out[1:2], pack.inv_scale, phased=False)
+        raw = (torch.empty if k == 3 else torch.zeros)(4 * geo.Mp, n_out, dtype=torch.float32, device=dev)
         per_parity = {0: [(1, 0)], 1: [(0, 1), (2, 0)]} if k == 3 else {0: [(0, 0)], 1: []}
         for a in (0, 1):
             for bb in (0, 1):
@@ -172,7 +184,7 @@ class TrainPlan:
                 if pairs:
                     shifts = [dy * geo.Wp + dx for _, dy in per_parity[a] for _, dx in per_parity[bb]]
                     igemm(pairs, shifts, raw[(a * 2 + bb) * geo.Mp:(a * 2 + bb + 1) * geo.Mp])
-        return gw, _Src(raw, n_out, scale_out[1:2], pack.inv_scale, phased=True)
+        return _Src(raw, n_out, scale_out[1:2], pack.inv_scale, phased=True)
 
     # ------------------------------------------------------------------ backward
     def backward(self, state, g_out):
@@ -206,6 +218,15 @@ class TrainPlan:
         g_pf = F.pad(gx, (1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(geo3.Mp, -1).contiguous()
         sources = {id(res): [_Src(g_pf, g_pf.size(1))]}
 
+        # one zeroed buffer for every convolution's weight gradient (the kernels accumulate into OIHW views of it)
+        recs = [e['conv'] for e in state['tape']] + [e['skip'] for e in state['tape'] if e['skip'] is not None]
+        flat = torch.zeros(sum(r['pack'].weight.numel() for r in recs), dtype=torch.float32, device=dev)
+        offset = 0
+        for r in recs:
+            n = r['pack'].weight.numel()
+            r['gw'] = flat[offset:offset + n].view(r['pack'].weight.shape)
+            offset += n
+
         stem_out = state['stem_out']
         for e in reversed(state['tape']):
             rec, out = e['conv'], e['out']
@@ -220,8 +241,8 @@ class TrainPlan:
             if e['add_kind'] == 1:
                 sources.setdefault(id(e['res']), []).append(_Src(g_buf, channels))
             act = rec['act']
-            gw, src = self._conv_backward(lib, stream, rec, d_raw, scale_out, True)
-            grads[id(rec['pack'].weight_param)] = gw
+            src = self._conv_backward(lib, stream, rec, d_raw, scale_out, True, rec['gw'])
+            grads[id(rec['pack'].weight_param)] = rec['gw']
             sources.setdefault(id(act), []).append(src)
             if e['add_kind'] == 2:
                 # skip branch: out = [relu](GroupNorm(skip_conv(res)) + main): its gradient is the merged gradient g_buf
@@ -229,8 +250,8 @@ class TrainPlan:
                 d_raw_s, scale_s, ab_s, dbias_s, _ = self._gn_backward(lib, stream, geo, channels, srec, e['norm2'], False,
                                                                        [_Src(g_buf, channels)], None, False)
                 self._param_grads(grads, srec, e['norm2'], ab_s, dbias_s)
-                gw, src = self._conv_backward(lib, stream, srec, d_raw_s, scale_s, True)
-                grads[id(srec['pack'].weight_param)] = gw
+                src = self._conv_backward(lib, stream, srec, d_raw_s, scale_s, True, srec['gw'])
+                grads[id(srec['pack'].weight_param)] = srec['gw']
                 sources.setdefault(id(srec['act']), []).append(src)
 
         # ---- stem (conv1 + norm1 + relu on the 3-channel frame): stock torch ops, recomputed
@@ -288,10 +309,11 @@ class _FusedStep(torch.autograd.Function):
         return (None, None) + tuple(grads.get(id(p)) if ctx.needs_input_grad[2 + i] else None for i, p in enumerate(ctx.params))
 
 
-def forward_train(net, image):
+def forward_train(net, image, backward=None):
     """Differentiable forward of `net` through the fused plan (one autograd node for the whole network)."""
     plan = getattr(net, '_train_plan', None)
-    if plan is None:
-        plan = net._train_plan = TrainPlan(net)
+    if plan is None or (backward is not None and plan.bwd_terms != (3 if backward == 'fp16x3' else 1)):
+        plan = TrainPlan(net, backward)
+        object.__setattr__(net, '_train_plan', plan)
     params = tuple(p for p in net.parameters())
     return _FusedStep.apply(plan, image.contiguous().to(torch.float32), *params)

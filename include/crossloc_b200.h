@@ -98,35 +98,21 @@ int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int 
                   int64_t a8_total_rows, int64_t a8_lo_rows, const void* weights8, void* cuda_stream);
 
 /*
- * Convolution weight gradient (training step):
- *   dw[tap][co][ci] += out_scale * sum_{b, p} grad[b][co][p] * act[b][ci][p + tap_shift[tap]]
- * on channel-major fp16 hi/lo matrices [term][phase][image][channel][plane_stride] whose planes are the
- * zero-bordered images at the convolution's OUTPUT resolution (pixel index fastest, row pitch a multiple of 8).
- * `act` holds `phases` plane groups; tap_phase[tap] selects the group a tap reads and tap_shift[tap] the pixel
- * shift inside it.  TMA needs 16-byte aligned box starts, so tap_shift must be a multiple of 8: horizontal
- * neighbours are provided as column-shifted copies (3 groups for a 3x3 stride-1 convolution, 4 parity phases x 2
- * copies for stride 2) and only whole rows are shifted by the kernel.
- * Replaces the cuDNN wgrad kernels autograd launches for nn.Conv2d (train_single_task.py:298).
- *   grad   terms x B x Cout planes;  act  terms x phases x B x Cin planes;  nterms 1 | 3 (fp16x3)
- *   dw     fp32 [num_taps][Cout][Cin], accumulated with atomics: the caller zeroes it
- */
-int cl_conv_wgrad(const void* grad, const void* act, int B, int Cout, int Cin, int plane, int plane_stride, int phases,
-                  int num_taps, const int32_t* tap_shift, const int32_t* tap_phase, int nterms, float out_scale,
-                  float* dw, void* cuda_stream);
-
-/*
- * Convolution weight gradient on padded-flat operands (the layout of cl_conv_igemm / cl_gn_backward):
+ * Convolution weight gradient (training step) on padded-flat operands, the layout
+ * of cl_conv_igemm / cl_gn_backward:
  *   dw[tap][co][ci] += out_scale * sum over rows r < Mp of grad[r][co] * act[tap_phase[tap]][r + tap_shift[tap]][ci]
  * Both operands are fp16 hi/lo PF matrices [planes][rows][C] read as MN-major tensor-core operands (64-row x
  * 64-channel TMA boxes, SWIZZLE_128B): no channel-major copies.  grad: plane 0 = hi, 1 = lo, g_plane_rows apart,
  * zero border rows.  act: plane term * phases + phase, x_plane_rows apart; rows outside a plane read as zero.
  * tap_shift / tap_phase are the forward convolution's tap table (phase and in-plane row shift kept apart).
  * Replaces the cuDNN wgrad kernels autograd launches for nn.Conv2d (train_single_task.py:298).
- *   Cout % 64 == 0, Cin = 32 or a multiple of 64, nterms 1 | 3 (fp16x3); dw fp32 [num_taps][Cout][Cin], atomics.
+ *   Cout % 64 == 0, Cin = 32 or a multiple of 64, nterms 1 | 3 (fp16x3).  dw fp32, accumulated with atomics (caller
+ *   zeroes it): [num_taps][Cout][Cin], or with oihw = 1 [Cout][Cin][num_taps] = torch's OIHW weight layout.
+ *   scale_dev: nullable device scalar multiplied into the result (the 2^-k of a device-rescaled gradient).
  */
 int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const void* act, int64_t x_plane_rows, int Mp, int Cout,
                      int Cin, int phases, int num_taps, const int32_t* tap_shift, const int32_t* tap_phase, int nterms,
-                     float out_scale, float* dw, void* cuda_stream);
+                     float out_scale, const float* scale_dev, int oihw, float* dw, void* cuda_stream);
 
 /*
  * Backward of one "GroupNorm -> ReLU -> (residual merge -> ReLU)" stage on padded-flat tensors (training step):
@@ -149,22 +135,17 @@ int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch, const flo
 
 /*
  * Layout kernels of the training path (device pointers): NCHW fp32 tensors, as autograd hands them over, to and
- * from the operand layouts of cl_conv_igemm / cl_conv_wgrad, and filter packing.  `scale` arguments are device
+ * from the operand layouts of cl_conv_igemm / cl_conv_wgrad_pf, and filter packing.  `scale` arguments are device
  * scalars (power-of-two factors computed on the GPU, no host synchronisation), NULL = 1.
  *   cl_nchw_to_pf   x [B][C][H][W] -> fp16 hi/lo PF [2][phases][B*(H'+2)*(W'+2)][C] (interior; caller zero-fills)
  *   cl_pf_to_nchw   raw fp32 PF [B*(H+2)*(W+2)][Craw] -> out [B][C][Hout][Wout] at (y*step+off_y, x*step+off_x),
  *                   x scale, + bias (the per-phase results of a stride-2 data gradient use step 2)
- *   cl_nchw_to_cm   x -> fp16 hi/lo channel-major planes [2][groups][B][C][hp*wp]; group g holds parity phase
- *                   (pa[g], pb[g]) of x (step 2) or x itself (step 1) shifted to column col0[g], rows from 1
  *   cl_pack_filter  w OIHW -> fp16 hi/lo [2][num_taps][N][K] for taps (tap_kh, tap_kw), transposed for dgrad
  */
 int cl_nchw_to_pf(const float* x, const float* scale, void* out, int B, int C, int H, int W, int phases,
                   void* cuda_stream);
 int cl_pf_to_nchw(const float* raw, int B, int H, int W, int Craw, float* out, int C, int Hout, int Wout, int step,
                   int off_y, int off_x, const float* scale, const float* bias, void* cuda_stream);
-int cl_nchw_to_cm(const float* x, const float* scale, void* out, int B, int C, int H, int W, int hp, int wp, int rows,
-                  int cols, int step, int groups, const int32_t* pa, const int32_t* pb, const int32_t* col0,
-                  void* cuda_stream);
 /* workspace: 4 x 32-bit device words; on completion workspace[0] = 2^k, workspace[1] = 2^-k (floats) with
  * k = floor(log2(target / max|x|)) -- the power-of-two operand scales, computed without a host round trip */
 int cl_pow2_scale(const float* x, int64_t n, float target, void* workspace, void* cuda_stream);

@@ -37,7 +37,9 @@ def main():
     cam[0, 2], cam[1, 2] = 360.0, 240.0
     grid = pixel_grid().to(dev)
     out = {}
-    variants = (('native_fused', lambda t: net.forward_train(t, fused=True)),
+    from crossloc_b200 import train_plan
+    variants = (('native_fused', lambda t: train_plan.forward_train(net, t, backward='fp16x3')),
+                ('native_fused_bwd_fp16x1', lambda t: train_plan.forward_train(net, t, backward='fp16x1')),
                 ('native_layerwise', lambda t: net.forward_train(t, fused=False)),
                 ('torch_autograd_cudnn', net.forward_reference))
     for name, fwd in variants:
