@@ -287,7 +287,8 @@ class CoordNetEngine:
         def planes_for(consumers, also_lo=False):
             """Which operand planes the consumers of an activation need: (fp16 lo plane, e4m3 planes)."""
             want8 = any(packs[c].nterms == 2 for c in consumers)
-            want_lo = also_lo or any(packs[c].nterms == 3 for c in consumers)
+            # training: the weight gradient reads the fp16 lo plane of every operand, whatever the forward scheme
+            want_lo = also_lo or self.tape is not None or any(packs[c].nterms == 3 for c in consumers)
             return want_lo, want8
 
         duc = spec.get('head', {}).get('duc') if spec.get('output', 'head') == 'head' else None

@@ -16,6 +16,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "conv.h"
 
 namespace cl {
@@ -24,18 +26,31 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// UNI: the 8 channels of a thread share one GroupNorm group (group size a multiple of 8, or no normalisation):
+// mean / rstd are then scalars (entry 0) and the kernel needs ~14 registers less.
+template <bool UNI>
 struct Lane {
     int c;                      // first of the 8 channels of this thread
-    float ga[8], be[8], mean[8], rstd[8];
+    float ga[8], be[8], mean[UNI ? 1 : 8], rstd[UNI ? 1 : 8];
 };
 
-__device__ __forceinline__ void load_lane(const GnBwdDesc& d, int b, int c, Lane& t)
+template <bool UNI>
+__device__ __forceinline__ void load_lane(const GnBwdDesc& d, int b, int c, Lane<UNI>& t)
 {
     t.c = c;
     const int groups = d.group_ch ? d.C / d.group_ch : 0;
     const double count = (double)d.group_ch * d.H * d.W;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
+        if (d.group_ch) {
+            t.ga[j] = d.gamma[c + j];
+            t.be[j] = d.beta[c + j];
+        } else {
+            t.ga[j] = 1.f; t.be[j] = 0.f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < (UNI ? 1 : 8); j++) {
         if (d.group_ch) {
             const int g = (c + j) / d.group_ch;
             const double s = d.stats[((size_t)b * groups + g) * 2], ss = d.stats[((size_t)b * groups + g) * 2 + 1];
@@ -44,10 +59,8 @@ __device__ __forceinline__ void load_lane(const GnBwdDesc& d, int b, int c, Lane
             var = var > 0 ? var : 0;
             t.mean[j] = (float)m;
             t.rstd[j] = (float)(1.0 / sqrt(var + (double)d.eps));   // same expression as the forward (cnn_pointwise.cu)
-            t.ga[j] = d.gamma[c + j];
-            t.be[j] = d.beta[c + j];
         } else {
-            t.mean[j] = 0.f; t.rstd[j] = 1.f; t.ga[j] = 1.f; t.be[j] = 0.f;
+            t.mean[j] = 0.f; t.rstd[j] = 1.f;
         }
     }
 }
@@ -90,8 +103,8 @@ __device__ __forceinline__ void gather_grad(const GnBwdDesc& d, int nsrc, const 
     }
 }
 
-template <bool APPLY>
-__global__ void __launch_bounds__(kThreads) gn_bwd_kernel(GnBwdDesc d)
+template <bool APPLY, bool UNI>
+__global__ void __launch_bounds__(kThreads, APPLY ? 4 : 3) gn_bwd_kernel(GnBwdDesc d)
 {
     __shared__ float red[kThreads][17];
     __shared__ float2 group_means[256];     // APPLY: (mean_group(dy*gamma), mean_group(dy*gamma*xhat)) of this image
@@ -102,8 +115,8 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_kernel(GnBwdDesc d)
     const int c = chunk * 8;
     const int Wp = d.W + 2;
     const size_t plane = (size_t)(d.H + 2) * Wp;
-    Lane t;
-    load_lane(d, b, c, t);
+    Lane<UNI> t;
+    load_lane<UNI>(d, b, c, t);
     const int nsrc = APPLY ? 1 : d.num_src;
     float scale[3] = {1.f, 1.f, 1.f};
     for (int s = 0; s < nsrc; s++) scale[s] = src_scale(d.src[s]);
@@ -162,18 +175,19 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_kernel(GnBwdDesc d)
         float dr[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const float xhat = (r[j] - t.mean[j]) * t.rstd[j];
-            const float v = (r[j] - t.mean[j]) * (t.rstd[j] * t.ga[j]) + t.be[j];   // the forward's expression
+            const float mean = t.mean[UNI ? 0 : j], rstd = t.rstd[UNI ? 0 : j];
+            const float xhat = (r[j] - mean) * rstd;
+            const float v = (r[j] - mean) * (rstd * t.ga[j]) + t.be[j];   // the forward's expression
             const float dy = (d.relu_inner && !(v > 0.f)) ? 0.f : g[j];
             if (!APPLY) {
                 a1[j] += dy;
                 a2[j] += dy * xhat;
-                gmax = fmaxf(gmax, fabsf(dy * t.ga[j]) * t.rstd[j]);
+                gmax = fmaxf(gmax, fabsf(dy * t.ga[j]) * rstd);
             } else {
                 float val = dy;
                 if (d.group_ch) {
-                    const float2 gm = group_means[(c + j) / d.group_ch];
-                    val = t.rstd[j] * (dy * t.ga[j] - gm.x - xhat * gm.y);
+                    const float2 gm = group_means[(c + (UNI ? 0 : j)) / d.group_ch];
+                    val = rstd * (dy * t.ga[j] - gm.x - xhat * gm.y);
                 }
                 dr[j] = val;
                 a1[j] += val;
@@ -239,14 +253,18 @@ const char* check(const GnBwdDesc& d)
     return nullptr;
 }
 
-int grid_x(const GnBwdDesc& d)
+// one resident wave of blocks (the launch bounds allow 3 / 4 blocks per SM): every extra block adds 16 fp64 atomics per
+// channel chunk to the tail, measured 0.17 ms (one wave) vs 0.22 ms (four waves) for a 512-channel stage of 12 frames
+int grid_x(const GnBwdDesc& d, int blocks_per_sm)
 {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int pslots = kThreads / (d.C / 8);
     int bx = (d.H * d.W + pslots * 4 - 1) / (pslots * 4);     // >= 4 pixels per thread: the reduction tail stays small
-    const int cap = (sms * 8 + d.B - 1) / d.B;
+    const char* env = getenv("CL_GNBWD_CAP");
+    const int per_sm = env ? atoi(env) : blocks_per_sm;
+    const int cap = (sms * per_sm) / d.B;
     if (bx > cap) bx = cap;
     return bx < 1 ? 1 : bx;
 }
@@ -257,7 +275,8 @@ const char* gn_bwd_reduce_launch(const GnBwdDesc& d, cudaStream_t stream)
 {
     if (const char* e = check(d)) return e;
     if (!d.ab || !d.gmax_bits) return "gn_backward: the reduce pass needs the ab and gmax buffers";
-    gn_bwd_kernel<false><<<dim3(grid_x(d), d.B), kThreads, 0, stream>>>(d);
+    if (d.group_ch % 8 == 0) gn_bwd_kernel<false, true><<<dim3(grid_x(d, 3), d.B), kThreads, 0, stream>>>(d);
+    else gn_bwd_kernel<false, false><<<dim3(grid_x(d, 3), d.B), kThreads, 0, stream>>>(d);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -266,7 +285,8 @@ const char* gn_bwd_apply_launch(const GnBwdDesc& d, cudaStream_t stream)
 {
     if (const char* e = check(d)) return e;
     if (!d.ab || !d.gmax_bits || !d.d_raw || !d.scale_out) return "gn_backward: the apply pass needs ab, gmax, d_raw and scale_out";
-    gn_bwd_kernel<true><<<dim3(grid_x(d), d.B), kThreads, 0, stream>>>(d);
+    if (d.group_ch % 8 == 0) gn_bwd_kernel<true, true><<<dim3(grid_x(d, 4), d.B), kThreads, 0, stream>>>(d);
+    else gn_bwd_kernel<true, false><<<dim3(grid_x(d, 4), d.B), kThreads, 0, stream>>>(d);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

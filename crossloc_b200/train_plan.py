@@ -4,8 +4,8 @@ The reference trains through stock autograd (/root/reference/train_single_task.p
 nn.GroupNorm / F.relu / residual add contributes its own forward and backward library kernels on NCHW fp32 tensors.
 Here the whole network is ONE autograd node:
 
-  forward   the inference plan of crossloc_b200.cnn in fp16x3 arithmetic with every raw convolution output,
-            GroupNorm statistic and operand kept (the engine's `tape`);
+  forward   the inference plan of crossloc_b200.cnn (fp16 + fp8 scheme by default) with every raw convolution
+            output, GroupNorm statistic and operand kept (the engine's `tape`);
   backward  walks the tape in reverse.  Per stage: cl_gn_backward pass 0 (sum of the incoming gradients, residual
             mask, GroupNorm / ReLU reductions) and pass 1 (gradient of the raw convolution output as fp16 hi / lo
             padded-flat planes, power-of-two scaled on the device), then the data gradient (cl_conv_igemm with the
@@ -23,13 +23,16 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib, layout
-from .cnn import CoordNetEngine, _Geometry
+from .cnn import CoordNetEngine, _Geometry, _nterms_for, _W8_LO_SCALE
 from .train import _forward_taps, _i32, _pack, _stream
 
 _NTERMS = 3
 # arithmetic of the data / weight gradient GEMMs: 'fp16x3' (default, fp32-grade like the forward) or 'fp16x1' (one
 # fp16 pass with fp32 accumulation: the 10-bit mantissa of the TF32 kernels stock PyTorch trains with by default)
 BACKWARD = os.environ.get('CROSSLOC_B200_TRAIN_BACKWARD', 'fp16x3')
+# arithmetic of the forward convolutions: the inference default ('fp16+fp8': e4m3 correction terms on the large layers,
+# 3e-5 relative on the coordinate map) or 'fp16x3'
+FORWARD = os.environ.get('CROSSLOC_B200_TRAIN_FORWARD', 'fp16+fp8')
 _RESCALE_EVERY = 64   # steps between host-side refreshes of the filters' power-of-two scales
 
 
@@ -43,10 +46,10 @@ class _Src:
 class _TrainPack:
     """Filter of one convolution in the tensor-core layout, packed on the device (no host synchronisation)."""
 
-    def __init__(self, conv, exp):
+    def __init__(self, conv, exp, nterms=_NTERMS):
         w = conv.weight.detach().contiguous()
         cout, cin, k, _ = w.shape
-        self.cin, self.cout, self.ksize, self.stride, self.nterms = cin, cout, k, conv.stride[0], _NTERMS
+        self.cin, self.cout, self.ksize, self.stride, self.nterms = cin, cout, k, conv.stride[0], nterms
         self.out_scale = float(2.0 ** (-exp))
         self.scale = torch.full((1,), float(2.0 ** exp), dtype=torch.float32, device=w.device)
         self.inv_scale = torch.full((1,), self.out_scale, dtype=torch.float32, device=w.device)
@@ -54,6 +57,9 @@ class _TrainPack:
         self.weight_param, self.bias_param = conv.weight, conv.bias
         self.weights = _pack(w, self.scale, [(kh, kw) for kh in range(k) for kw in range(k)], False, cout, cin)
         self.weights8 = None
+        if nterms == 2:   # forward in the fp16 + fp8 scheme: e4m3 planes fp8(w_hi), fp8(w_lo * 2^12)
+            self.weights8 = torch.stack([self.weights[0].to(torch.float32).to(torch.float8_e4m3fn),
+                                         (self.weights[1].to(torch.float32) * _W8_LO_SCALE).to(torch.float8_e4m3fn)], 0).contiguous()
         self.bias = (conv.bias.detach().to(torch.float32) if conv.bias is not None
                      else torch.zeros(cout, dtype=torch.float32, device=w.device)).contiguous()
 
@@ -63,14 +69,15 @@ def supported(net):
 
 
 class TrainPlan:
-    def __init__(self, net, backward=None):
+    def __init__(self, net, backward=None, forward=None):
         self.net = net
+        forward = forward or FORWARD
         backward = backward or BACKWARD
         if backward not in ('fp16x3', 'fp16x1'):
             raise ValueError('unknown backward arithmetic %r (fp16x3 | fp16x1)' % (backward,))
         self.bwd_terms = 3 if backward == 'fp16x3' else 1
         self._zero_bias = {}
-        self.engine = CoordNetEngine(precision='fp16x3')
+        self.engine = CoordNetEngine(precision=forward)
         self.engine.packer = self._packer
         self._exps = {}
         self._step = 0
@@ -83,7 +90,8 @@ class TrainPlan:
             import math
             exp = 0 if amax == 0.0 or not math.isfinite(amax) else int(math.floor(math.log2(128.0 / amax)))
             self._exps[name] = max(-24, min(24, exp))
-        return _TrainPack(conv, self._exps[name])
+        nterms = _nterms_for(self.engine.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0])
+        return _TrainPack(conv, self._exps[name], nterms)
 
     # ------------------------------------------------------------------ forward
     def forward(self, image):
@@ -309,11 +317,12 @@ class _FusedStep(torch.autograd.Function):
         return (None, None) + tuple(grads.get(id(p)) if ctx.needs_input_grad[2 + i] else None for i, p in enumerate(ctx.params))
 
 
-def forward_train(net, image, backward=None):
+def forward_train(net, image, backward=None, forward=None):
     """Differentiable forward of `net` through the fused plan (one autograd node for the whole network)."""
     plan = getattr(net, '_train_plan', None)
-    if plan is None or (backward is not None and plan.bwd_terms != (3 if backward == 'fp16x3' else 1)):
-        plan = TrainPlan(net, backward)
+    if (plan is None or (backward is not None and plan.bwd_terms != (3 if backward == 'fp16x3' else 1))
+            or (forward is not None and plan.engine.precision != forward)):
+        plan = TrainPlan(net, backward, forward)
         object.__setattr__(net, '_train_plan', plan)
     params = tuple(p for p in net.parameters())
     return _FusedStep.apply(plan, image.contiguous().to(torch.float32), *params)

@@ -38,26 +38,37 @@ def main():
     grid = pixel_grid().to(dev)
     out = {}
     from crossloc_b200 import train_plan
-    variants = (('native_fused', lambda t: train_plan.forward_train(net, t, backward='fp16x3')),
-                ('native_fused_bwd_fp16x1', lambda t: train_plan.forward_train(net, t, backward='fp16x1')),
+    variants = (('native_fused', lambda t: train_plan.forward_train(net, t, backward='fp16x3', forward='fp16+fp8')),
+                ('native_fused_fwd_fp16x3', lambda t: train_plan.forward_train(net, t, backward='fp16x3', forward='fp16x3')),
+                ('native_fused_bwd_fp16x1', lambda t: train_plan.forward_train(net, t, backward='fp16x1', forward='fp16+fp8')),
                 ('native_layerwise', lambda t: net.forward_train(t, fused=False)),
                 ('torch_autograd_cudnn', net.forward_reference))
     for name, fwd in variants:
         times = []
+        phases = [0.0, 0.0, 0.0, 0.0]
         for i in range(steps + 1):
             torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             t0 = time.perf_counter()
+            ev[0].record()
             opt.zero_grad()
             pred = fwd(images)
+            ev[1].record()
             c, u = torch.split(pred, [3, 1], dim=1)
             loss, rate = scene_coords_regression_loss(0.1, 100.0, 1000.0, 50.0, 'MLE', grid, -1, cam, c, u, poses, gt)
+            ev[2].record()
             loss.backward()
+            ev[3].record()
             opt.step()
+            ev[4].record()
             torch.cuda.synchronize()
             if i > 0:
                 times.append(time.perf_counter() - t0)
+                for j in range(4):
+                    phases[j] += ev[j].elapsed_time(ev[j + 1])
         out[name] = {'ms_per_step': 1e3 * sum(times) / len(times), 'images_per_s': batch * len(times) / sum(times),
-                     'loss': float(loss)}
+                     'loss': float(loss),
+                     'device_ms': dict(zip(('forward', 'loss', 'backward', 'adam'), [p / len(times) for p in phases]))}
     out['batch'] = batch
     out['peak_mem_gb'] = torch.cuda.max_memory_allocated() / 1e9
     print(json.dumps(out))
