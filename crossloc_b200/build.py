@@ -26,6 +26,7 @@ UNITS = {
     'conv_igemm.cu': [],
     'conv_wgrad_pf.cu': [],
     'cnn_pointwise.cu': [],
+    'stem_tc.cu': [],
     'gn_backward.cu': [],
     'train_layout.cu': [],
 }

@@ -139,9 +139,15 @@ extern "C" int cl_stem_forward(const float* image, int B, int Cin, int H, int W,
     d.stats = stats; d.gamma = gamma; d.beta = beta; d.eps = eps; d.out = static_cast<__half*>(out);
     d.out_terms = out_terms;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const char* env = getenv("CROSSLOC_B200_STEM");
+    if (env && env[0] == 'c') {   // "cuda": the CUDA-core kernels, kept for comparison
+        if (has_gn)
+            if (int rc = finish(kFn, cl::stem_stats_launch(d, s))) return rc;
+        return finish(kFn, cl::stem_apply_launch(d, s));
+    }
     if (has_gn)
-        if (int rc = finish(kFn, cl::stem_stats_launch(d, s))) return rc;
-    return finish(kFn, cl::stem_apply_launch(d, s));
+        if (int rc = finish(kFn, cl::stem_tc_launch(d, true, s))) return rc;
+    return finish(kFn, cl::stem_tc_launch(d, false, s));
 }
 
 extern "C" int cl_head_forward(const void* act, int64_t act_lo_rows, int in_terms, int B, int H, int W, int C,

@@ -185,6 +185,9 @@ struct StemDesc {
     __half* out;            // PF, 4 phases at (ceil(H/2), ceil(W/2)), C = 32
     int out_terms;
 };
+// tensor-core version (stem_tc.cu): im2col rows built in shared memory, tcgen05 fp16x3; same two passes
+const char* stem_tc_launch(const StemDesc& d, bool stats_pass, cudaStream_t stream);
+// CUDA-core version (cnn_pointwise.cu), CROSSLOC_B200_STEM=cuda
 const char* stem_stats_launch(const StemDesc& d, cudaStream_t stream);   // pass 1: statistics only
 const char* stem_apply_launch(const StemDesc& d, cudaStream_t stream);   // pass 2: recompute, normalise, ReLU, store
 
