@@ -282,7 +282,7 @@ def run_native(args):
         nterms = engine.nterms
         # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (same shape and mode)
         traffic = None
-        prof = os.path.join(ROOT, 'profiles', 'r1s2_conv3x3_pair_ncu_full.json')
+        prof = os.path.join(ROOT, 'profiles', 'r1s3_conv3x3_pair_ncu_full.json')
         if os.path.exists(prof) and B == BATCH and engine.precision == 'fp16+fp8':
             traffic = json.load(open(prof)).get('dram_bytes_per_launch')
         roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel<64> 3x3 512->512 @60x90 x%d images' % B,

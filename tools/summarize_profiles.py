@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn raw ncu captures (gpurun_out/) into the tracked summaries under profiles/.
 
-    python tools/summarize_profiles.py launches <launches.csv> <warmup+steps> <out.md> [title]
+    python tools/summarize_profiles.py launches <launches.csv> <warmup+steps> <out.md> [title] [marker kernel]
     python tools/summarize_profiles.py full <report.ncu-rep> <out.json> <kernel description> <command>
 
 `launches`: per-kernel totals of an `ncu --metrics gpu__time_duration.sum` launch list; the capture covers the
@@ -42,13 +42,20 @@ def short(name):
     return name[:60]
 
 
-def launches(path, steps, out, title):
+def launches(path, steps, out, title, marker=None):
     rows = []
     with open(path) as fh:
         lines = [l for l in fh if l.startswith('"')]
     for r in csv.DictReader(io.StringIO(''.join(lines))):
         if r['Metric Name'] == 'gpu__time_duration.sum':
             rows.append((short(r['Kernel Name']), float(r['Metric Value']) * (1e-6 if r['Metric Unit'] == 'ns' else 1.0)))
+    if marker:
+        # steady state only: the launches between the first and the last launch of `marker` (one per step), i.e. whole
+        # steps without the allocation / filter-packing launches of the first one
+        idx = [i for i, (k, _) in enumerate(rows) if marker in k]
+        if len(idx) >= 2:
+            rows = rows[idx[0] + 1:idx[-1] + 1]
+            steps = len(idx) - 1
     agg = {}
     for k, ms in rows:
         a = agg.setdefault(k, [0, 0.0])
@@ -94,7 +101,8 @@ def full(report, out, kernel, command):
 
 if __name__ == '__main__':
     if sys.argv[1] == 'launches':
-        launches(sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else 'ncu launch list')
+        launches(sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else 'ncu launch list',
+                 sys.argv[6] if len(sys.argv) > 6 else None)
     elif sys.argv[1] == 'full':
         full(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
     else:
