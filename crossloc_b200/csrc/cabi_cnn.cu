@@ -229,3 +229,13 @@ extern "C" int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch
     NEED_DEV(d_raw); NEED_DEV(scale_out);
     return finish(kFn, cl::gn_bwd_apply_launch(d, s));
 }
+
+extern "C" int cl_frames_to_nchw(const uint8_t* frames, int B, int H, int W, int C, const float* mean, const float* stdv,
+                                 float* out, void* cuda_stream)
+{
+    static const char* kFn = "cl_frames_to_nchw";
+    NEED_DEV(frames); NEED_DEV(out);
+    if (mean) NEED_DEV(mean);
+    if (stdv) NEED_DEV(stdv);
+    return finish(kFn, cl::frames_to_nchw_launch(frames, B, H, W, C, mean, stdv, out, static_cast<cudaStream_t>(cuda_stream)));
+}

@@ -517,6 +517,25 @@ __global__ void __launch_bounds__(kDucThreads) duc_head_kernel(DucHeadDesc d)
     }
 }
 
+// Input frames: uint8 HWC (what PIL / the decoders deliver) -> fp32 NCHW, x / 255 [then (v - mean[c]) / std[c]] with the
+// same fp32 operations as torchvision's ToTensor / Normalize (dataloader/dataloader.py:189-212), so the result is
+// bit-identical to the host transform it replaces while the host-to-device copy moves a quarter of the bytes.
+__global__ void __launch_bounds__(256) frames_to_nchw_kernel(const uint8_t* __restrict__ frames, int B, int H, int W, int C,
+                                                            const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                            float* __restrict__ out)
+{
+    const long long total = (long long)B * H * W;
+    const long long hw = (long long)H * W;
+    for (long long pix = blockIdx.x * 256ll + threadIdx.x; pix < total; pix += (long long)gridDim.x * 256) {
+        const long long b = pix / hw, r = pix - b * hw;
+        for (int c = 0; c < C; c++) {
+            float v = __fdiv_rn((float)frames[pix * C + c], 255.f);
+            if (mean) v = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+            out[(b * C + c) * hw + r] = v;
+        }
+    }
+}
+
 int sm_count()
 {
     int dev = 0, sms = 148;
@@ -611,6 +630,20 @@ const char* duc_head_launch(const DucHeadDesc& d, cudaStream_t stream)
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     duc_head_kernel<<<(unsigned)blocks, kDucThreads, smem, stream>>>(d);
+    return last_error();
+}
+
+const char* frames_to_nchw_launch(const uint8_t* frames, int B, int H, int W, int C, const float* mean, const float* stdv,
+                                  float* out, cudaStream_t stream)
+{
+    if (C < 1 || C > 4) return "frames_to_nchw: 1..4 channels";
+    if ((mean == nullptr) != (stdv == nullptr)) return "frames_to_nchw: mean and std come together";
+    const long long total = (long long)B * H * W;
+    if (total <= 0) return "frames_to_nchw: empty batch";
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    frames_to_nchw_kernel<<<(unsigned)blocks, 256, 0, stream>>>(frames, B, H, W, C, mean, stdv, out);
     return last_error();
 }
 

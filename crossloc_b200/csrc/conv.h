@@ -225,4 +225,8 @@ struct DucHeadDesc {
 };
 const char* duc_head_launch(const DucHeadDesc& d, cudaStream_t stream);
 
+// ---------------------------------------------------------------- input frames: uint8 HWC -> fp32 NCHW (ToTensor [+ Normalize])
+const char* frames_to_nchw_launch(const uint8_t* frames, int B, int H, int W, int C, const float* mean, const float* stdv,
+                                  float* out, cudaStream_t stream);
+
 }  // namespace cl

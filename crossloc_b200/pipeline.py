@@ -11,7 +11,25 @@ the next batch overlaps the kernels of the current one.
 """
 import torch
 
-from . import dsac
+from . import _lib, dsac
+
+
+def frames_to_network_input(frames_u8, mean=None, std=None, out=None):
+    """uint8 HWC frames [B,H,W,C] on the device -> fp32 NCHW network input: x / 255 (torchvision ToTensor) and, with
+    mean / std, (v - mean) / std (Normalize) -- bit-identical to the host transform of dataloader/dataloader.py:189-212."""
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or not frames_u8.is_cuda:
+        raise RuntimeError('frames must be a CUDA uint8 tensor [B, H, W, C]')
+    frames_u8 = frames_u8.contiguous()
+    b, h, w, c = frames_u8.shape
+    if out is None:
+        out = torch.empty(b, c, h, w, dtype=torch.float32, device=frames_u8.device)
+    dev = frames_u8.device
+    mean_t = None if mean is None else torch.as_tensor(mean, dtype=torch.float32, device=dev).contiguous()
+    std_t = None if std is None else torch.as_tensor(std, dtype=torch.float32, device=dev).contiguous()
+    _lib.check(_lib.load().cl_frames_to_nchw(frames_u8.data_ptr(), b, h, w, c, None if mean_t is None else mean_t.data_ptr(),
+                                             None if std_t is None else std_t.data_ptr(), out.data_ptr(),
+                                             torch.cuda.current_stream(dev).cuda_stream))
+    return out
 
 
 class Localizer:
@@ -72,14 +90,16 @@ class Localizer:
 
     # ------------------------------------------------------------------ host entry, pipelined
     def submit(self, images_host, focal, coord_offset=None, image_base=0):
-        """Queue one batch: async H2D on the copy stream, compute on the current stream, async D2H of the poses."""
+        """Queue one batch: async H2D on the copy stream, compute on the current stream, async D2H of the poses.
+        `images_host`: pinned fp32 NCHW frames, or pinned uint8 HWC frames [B,H,W,C] (a quarter of the copy; converted on
+        the device by cl_frames_to_nchw exactly as torchvision's ToTensor does on the host)."""
         slot = self._turn
         self._turn ^= 1
         b = images_host.size(0)
         st = self._slots[slot]
-        if st is None or st['images'].shape != images_host.shape:
+        if st is None or st['images'].shape != images_host.shape or st['images'].dtype != images_host.dtype:
             st = {
-                'images': torch.empty(images_host.shape, dtype=torch.float32, device=self.device),
+                'images': torch.empty(images_host.shape, dtype=images_host.dtype, device=self.device),
                 'pose_dev': torch.empty(b, 4, 4, dtype=torch.float32, device=self.device),
                 'pose_host': torch.empty(b, 4, 4, dtype=torch.float32).pin_memory(),
                 'done': torch.cuda.Event(),
@@ -94,7 +114,10 @@ class Localizer:
             st['images'].copy_(images_host, non_blocking=True)
             st['copied'].record(self._copy_stream)
         compute.wait_event(st['copied'])
-        self.localize_device(st['images'], focal, coord_offset, image_base, out_pose=st['pose_dev'], overlap=True)
+        frames = st['images']
+        if frames.dtype == torch.uint8:
+            st['frames_f32'] = frames = frames_to_network_input(frames, out=st.get('frames_f32'))
+        self.localize_device(frames, focal, coord_offset, image_base, out_pose=st['pose_dev'], overlap=True)
         st['free'] = torch.cuda.Event()
         st['free'].record(compute)          # the network has consumed the device frames
         with torch.cuda.stream(self.solver_stream):   # poses leave on the solver stream, behind the solve

@@ -198,6 +198,16 @@ int cl_duc_head_forward(const float* raw, int B, int Hc, int Wc, int C, int Co, 
                         const float* bias, const float* mean, int num_task, float clamp_lo, float clamp_hi,
                         float* out, int Ho, int Wo, void* cuda_stream);
 
+/*
+ * Input frames on the device: uint8 HWC [B][H][W][C] (decoder / PIL layout) -> fp32 NCHW [B][C][H][W] as
+ * x / 255, then (v - mean[c]) / std[c] when mean / std (device, [C]) are given -- the fp32 operations of
+ * torchvision's ToTensor and Normalize (dataloader/dataloader.py:189-212), bit for bit.  The host-to-device copy of
+ * a frame shrinks from 4 bytes to 1 byte per sample.  Frames must already have the network resolution (the
+ * reference's Resize(480) is the identity for its 480 x 720 datasets).
+ */
+int cl_frames_to_nchw(const uint8_t* frames, int B, int H, int W, int C, const float* mean, const float* stdv, float* out,
+                      void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

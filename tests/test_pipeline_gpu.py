@@ -73,3 +73,38 @@ def test_localizer_host_pipeline_equals_device_entry():
         direct = loc.localize_device(f.to(dev), focal_d, offsets, image_base=100 * k)
         torch.cuda.synchronize()
         assert torch.equal(direct.cpu(), host[k])
+
+
+def test_uint8_frames_match_torchvision_transforms():
+    """cl_frames_to_nchw vs the host transform of the reference's dataloader (ToPILImage -> Resize(480) -> ToTensor
+    [-> Normalize], dataloader/dataloader.py:189-212) on frames that already have the network height: bit for bit."""
+    from torchvision import transforms
+    from crossloc_b200.pipeline import frames_to_network_input
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (3, 48, 72, 3), dtype=torch.uint8, generator=g)
+    mean, std = [0.4245, 0.4375, 0.3836], [0.1823, 0.1701, 0.1854]
+    raw = transforms.Compose([transforms.ToPILImage(), transforms.Resize(48), transforms.ToTensor()])
+    norm = transforms.Compose([transforms.ToPILImage(), transforms.Resize(48), transforms.ToTensor(),
+                               transforms.Normalize(mean=mean, std=std)])
+    ref_raw = torch.stack([raw(f.numpy()) for f in frames])
+    ref_norm = torch.stack([norm(f.numpy()) for f in frames])
+    assert torch.equal(frames_to_network_input(frames.cuda()).cpu(), ref_raw)
+    assert torch.equal(frames_to_network_input(frames.cuda(), mean, std).cpu(), ref_norm)
+
+
+def test_localizer_accepts_uint8_host_frames():
+    """submit() with pinned uint8 HWC frames gives the poses of the fp32 frames ToTensor would have produced."""
+    import networks.networks as nets
+    from crossloc_b200.pipeline import Localizer
+    torch.manual_seed(4)
+    net = nets.TransPoseNet(torch.zeros(3), False, False, 0, 0, 3, 1).eval().cuda()
+    dev = torch.device('cuda', 0)
+    height, width, batch = 64, 96, 2
+    coords, _, _, focal = synth.make_batch(20, batch, height=height, width=width, focal=100.0)
+    offsets, focal_d = torch.from_numpy(coords).to(dev), torch.from_numpy(focal).to(dev)
+    frames = torch.randint(0, 256, (batch, height, width, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(6))
+    loc = Localizer(net, hyps=32, device=dev)
+    from_u8 = loc.localize(frames.pin_memory(), focal_d, offsets, image_base=7).clone()
+    as_f32 = (frames.permute(0, 3, 1, 2).float() / 255).contiguous().pin_memory()
+    from_f32 = loc.localize(as_f32, focal_d, offsets, image_base=7).clone()
+    assert torch.equal(from_u8, from_f32)
