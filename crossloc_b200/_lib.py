@@ -44,7 +44,10 @@ SIGNATURES = {
     'cl_gn_apply': (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
         _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,
-        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
+    'cl_pf_groupnorm': (_c.c_int, [
+        _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_float,
+        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
     'cl_stem_forward': (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,
         _c.c_void_p, _c.c_void_p, _c.c_float, _c.c_void_p, _c.c_int, _c.c_void_p]),

@@ -125,6 +125,7 @@ class CoordNetEngine:
         self.head_in = None
         self._conv_rec = {}
         self._keep_i = 0
+        self._shared = {}
 
     # ------------------------------------------------------------------ parameters
     def _pack(self, name, conv, force_split=False):
@@ -211,7 +212,7 @@ class CoordNetEngine:
                                        'stats': stats, 'group_ch': group_ch}
 
     def _apply(self, stream, raw, geo, channels, norm, stats, out, relu_inner=True, res=None, raw2=None, norm2=None,
-               stats2=None, relu_outer=False, want_lo=True, want8=False):
+               stats2=None, relu_outer=False, want_lo=True, want8=False, out_c0=None):
         group_ch = 0 if norm is None else channels // norm.num_groups
         add_kind = 1 if res is not None else (2 if raw2 is not None else 0)
         e0 = self._tick()
@@ -224,7 +225,7 @@ class CoordNetEngine:
             0 if raw2 is None else raw2.data_ptr(), 0 if stats2 is None else stats2.data_ptr(),
             0 if norm2 is None else norm2.weight.data_ptr(), 0 if norm2 is None else norm2.bias.data_ptr(),
             1 if relu_outer else 0, out.h16.data_ptr(), out.phases, 2 if (want_lo and self.terms == 2) else 1,
-            out.f8.data_ptr() if want8 else 0, stream))
+            out.f8.data_ptr() if want8 else 0, out.channels if out_c0 is not None else 0, out_c0 or 0, stream))
         self._tock(e0, 'gn_apply', ('gn_apply', channels, out.phases, add_kind), 0.0)
         self.launches += 1
         if self.tape is not None:
@@ -232,29 +233,52 @@ class CoordNetEngine:
                               'add_kind': add_kind, 'res': res, 'relu_outer': relu_outer,
                               'skip': None if raw2 is None else self._conv_rec[id(raw2)], 'norm2': norm2})
 
+    def shared_pf(self, key, device, batch, h, w, channels):
+        """A padded-flat activation at the output resolution of an (h, w) frame that outlives single forward() calls
+        (the concatenated encoder outputs of the MLR model)."""
+        for _ in range(3):
+            h, w = (h + 1) // 2, (w + 1) // 2
+        k = (key, str(device), batch, h, w, channels, self.terms)
+        buf = self._shared.get(k)
+        if buf is None:
+            if len(self._shared) >= 4:
+                self._shared.pop(next(iter(self._shared)))
+            buf = self._shared[k] = _PF(_Geometry(batch, h, w), channels, 1, self.terms, device)
+        return buf
+
+    def nterms_of(self, conv):
+        return _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0])
+
     # ------------------------------------------------------------------ plans
     def forward(self, spec, image):
         """spec: dict produced by networks.networks (layer modules + head description). image: NCHW fp32 CUDA.
 
         Optional spec keys: 'roles' maps conv1..conv4 to layer names (several encoders can share one engine);
         'input': 'image' (default) | 'activation' (`image` is an NCHW fp32 activation at the output resolution: the
-        stem and the strided ladder are skipped); 'output': 'head' (default) | 'activation' (returns the final
-        residual stream as an NCHW fp32 tensor instead of running a head)."""
-        if not image.is_cuda:
-            raise RuntimeError('crossloc_b200: the coordinate network runs on a CUDA device only (no CPU fallback)')
+        stem and the strided ladder are skipped) | 'pf' (spec['in_pf'] is a padded-flat activation produced by an earlier
+        plan; `image` is ignored); 'output': 'head' (default) | 'activation' (returns the final residual stream as an
+        NCHW fp32 tensor instead of running a head) | 'pf' (returns it as a padded-flat activation; with
+        spec['out_pf'] = (buffer, first channel, want e4m3 planes) the last stage writes into that channel slice)."""
         self._lib = _lib.load()
-        image = image.contiguous().to(torch.float32)
-        batch, cin, h, w = image.shape
+        in_pf = spec.get('in_pf') if spec.get('input') == 'pf' else None
+        if in_pf is not None:
+            dev = in_pf.h16.device
+            batch, cin, h, w = in_pf.geo.B, in_pf.channels, in_pf.geo.H, in_pf.geo.W
+        else:
+            if not image.is_cuda:
+                raise RuntimeError('crossloc_b200: the coordinate network runs on a CUDA device only (no CPU fallback)')
+            image = image.contiguous().to(torch.float32)
+            batch, cin, h, w = image.shape
+            dev = image.device
         if batch == 0:
             raise RuntimeError('crossloc_b200: empty batch')
-        dev = image.device
         torch.cuda.set_device(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        from_activation = spec.get('input', 'image') == 'activation'
+        from_activation = spec.get('input', 'image') in ('activation', 'pf')
         ws = self._workspace(dev, batch, h, w, {'cin': cin, 'act': int(from_activation)})
         geo = ws['geo']
         if from_activation:
-            geo[3] = _Geometry(batch, h, w)
+            geo[3] = in_pf.geo if in_pf is not None else _Geometry(batch, h, w)
         roles = spec.get('roles', {'conv1': 'conv1', 'conv2': 'conv2', 'conv3': 'conv3', 'conv4': 'conv4'})
         gn = spec['group_norm']
         layers = spec['layers']          # ordered list of (name, conv, norm or None)
@@ -277,7 +301,7 @@ class CoordNetEngine:
         convs = {name: (conv, norm) for name, conv, norm in layers}
         blocks = spec['blocks']
         entry = set()
-        if from_activation and blocks:   # convolutions reading the externally supplied activation
+        if from_activation and in_pf is None and blocks:   # convolutions reading the externally supplied activation
             entry = {blocks[0]['convs'][0]} | ({blocks[0]['skip']} if blocks[0]['kind'] == 'residual_skip' else set())
         packs = {name: self._pack(name, conv, name in entry) for name, conv, _ in layers if name != roles.get('conv1')}
 
@@ -301,7 +325,10 @@ class CoordNetEngine:
             return [blk['convs'][0]] + ([blk['skip']] if blk['kind'] == 'residual_skip' else [])
 
         g3 = geo[3]
-        if from_activation:
+        out_pf = spec.get('out_pf') if spec.get('output') == 'pf' else None
+        if in_pf is not None:
+            res = in_pf
+        elif from_activation:
             # externally produced activation (e.g. the MLR merge): NCHW fp32 -> fp16 hi/lo padded-flat planes
             res = ws['act'].get('ext')
             if res is None:   # cl_nchw_to_pf always writes both planes, whatever the precision mode
@@ -357,7 +384,7 @@ class CoordNetEngine:
                     return buf
             raise AssertionError
 
-        def chain(names, x, res_in, outer_relu, next_readers, merge_raw2=None):
+        def chain(names, x, res_in, outer_relu, next_readers, merge_raw2=None, target=None):
             """conv -> [GN] -> relu per layer; the last layer merges the residual stream:
             out = [relu](res + relu(gn(conv)))  or, with merge_raw2 = (raw, norm, stats), the GroupNorm'ed skip path."""
             for i, name in enumerate(names):
@@ -373,13 +400,17 @@ class CoordNetEngine:
                     self._apply(stream, raw, g3, pack.cout, norm, st, out, want_lo=want_lo, want8=want8)
                 else:
                     want_lo, want8 = planes_for(next_readers, also_lo=True)
+                    c0 = None
+                    if target is not None:   # the plan's result goes into a channel slice of a caller-owned activation
+                        out, c0, want8 = target
+                        want_lo = True
                     if merge_raw2 is None:
                         self._apply(stream, raw, g3, pack.cout, norm, st, out, res=res_in, relu_outer=outer_relu,
-                                    want_lo=want_lo, want8=want8)
+                                    want_lo=want_lo, want8=want8, out_c0=c0)
                     else:
                         raw_s, snorm, st_s = merge_raw2
                         self._apply(stream, raw, g3, pack.cout, norm, st, out, raw2=raw_s, norm2=snorm, stats2=st_s,
-                                    relu_outer=outer_relu, want_lo=want_lo, want8=want8)
+                                    relu_outer=outer_relu, want_lo=want_lo, want8=want8, out_c0=c0)
                 x = out
             return x
 
@@ -387,8 +418,34 @@ class CoordNetEngine:
         for bi, block in enumerate(blocks):
             kind = block['kind']
             readers = first_conv_of(bi + 1)
+            target = out_pf if bi == len(blocks) - 1 else None
+            if target is not None and (kind not in ('residual', 'residual_skip') or not gn):
+                raise RuntimeError('crossloc_b200: a sliced plan output needs a final residual block')
             if kind == 'residual':
-                res = chain(block['convs'], res, res, outer, readers)
+                res = chain(block['convs'], res, res, outer, readers, target=target)
+            elif kind == 'mlr_merge':
+                # networks.py:491-494: res = mlr_skip(cat); mlr = mlr_forward(mlr_norm(cat)); res = relu(res + mlr)
+                sconv, snorm = convs[block['skip']]
+                spack = packs[block['skip']]
+                raw_s = self._raw(ws, 'rs', 3, spack.cout, block['skip'])
+                st_s = next_stats()
+                self._conv(stream, spack, res, g3, raw_s, st_s, groups_of(snorm, spack.cout), block['skip'])
+                nin = block['norm_in']
+                normed = self._act(ws, 'mlr_normed', 3, res.channels, 1)
+                want_lo, want8 = planes_for([block['convs'][0]])
+                st_n = ws.get('pfgn_stats')
+                if st_n is None or st_n.shape != (batch, nin.num_groups, 2):
+                    st_n = ws['pfgn_stats'] = torch.zeros(batch, nin.num_groups, 2, dtype=torch.float64, device=dev)
+                else:
+                    st_n.zero_()
+                e0 = self._tick()
+                _lib.check(self._lib.cl_pf_groupnorm(
+                    res.h16.data_ptr(), g3.Mp, batch, g3.H, g3.W, res.channels, res.channels // nin.num_groups,
+                    nin.weight.data_ptr(), nin.bias.data_ptr(), float(nin.eps), st_n.data_ptr(), normed.h16.data_ptr(),
+                    2 if want_lo else 1, normed.f8.data_ptr() if want8 else 0, stream))
+                self._tock(e0, 'pf_groupnorm', ('pf_groupnorm', res.channels), 0.0)
+                self.launches += 2
+                res = chain(block['convs'], normed, normed, outer, readers, merge_raw2=(raw_s, snorm, st_s))
             elif kind == 'residual_skip':
                 # x = chain(res); res = skip_norm(skip(res)); res = [relu](res + x)   (networks.py:242-249)
                 sconv, snorm = convs[block['skip']]
@@ -397,7 +454,7 @@ class CoordNetEngine:
                 st_s = next_stats() if snorm is not None else None
                 self._conv(stream, spack, res, g3, raw_s, st_s, groups_of(snorm, spack.cout), block['skip'])
                 if gn:
-                    res = chain(block['convs'], res, res, outer, readers, merge_raw2=(raw_s, snorm, st_s))
+                    res = chain(block['convs'], res, res, outer, readers, merge_raw2=(raw_s, snorm, st_s), target=target)
                 else:
                     # vanilla Network: res = skip(res) + relu(conv(x)), no normalisation anywhere
                     skip_pf = scratch(spack.cout, (res,))
@@ -420,6 +477,8 @@ class CoordNetEngine:
             else:
                 raise AssertionError(kind)
 
+        if spec.get('output', 'head') == 'pf':
+            return res
         if spec.get('output', 'head') == 'activation':
             from . import layout
             return layout.from_pf(res.h16, batch, g3.H, g3.W, self.terms)

@@ -108,7 +108,7 @@ extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int gro
                            const float* gamma, const float* beta, float eps, int relu_inner, int add_kind,
                            const void* res, int64_t res_lo_rows, const float* raw2, const double* stats2,
                            const float* gamma2, const float* beta2, int relu_outer, void* out, int out_phases,
-                           int out_terms, void* out8, void* cuda_stream)
+                           int out_terms, void* out8, int out_C, int out_c0, void* cuda_stream)
 {
     static const char* kFn = "cl_gn_apply";
     NEED_DEV(raw); NEED_DEV(out);
@@ -123,6 +123,7 @@ extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int gro
     d.res = static_cast<const __half*>(res); d.res_lo_rows = res_lo_rows; d.raw2 = raw2; d.stats2 = stats2;
     d.gamma2 = gamma2; d.beta2 = beta2; d.relu_outer = relu_outer; d.out = static_cast<__half*>(out);
     d.out_phases = out_phases; d.out_terms = out_terms; d.out8 = static_cast<uint8_t*>(out8);
+    d.out_C = out_C; d.out_c0 = out_c0;
     if (out8) NEED_DEV(out8);
     return finish(kFn, cl::gn_apply_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
@@ -238,4 +239,18 @@ extern "C" int cl_frames_to_nchw(const uint8_t* frames, int B, int H, int W, int
     if (mean) NEED_DEV(mean);
     if (stdv) NEED_DEV(stdv);
     return finish(kFn, cl::frames_to_nchw_launch(frames, B, H, W, C, mean, stdv, out, static_cast<cudaStream_t>(cuda_stream)));
+}
+
+extern "C" int cl_pf_groupnorm(const void* in, int64_t in_lo_rows, int B, int H, int W, int C, int group_ch,
+                               const float* gamma, const float* beta, float eps, double* stats, void* out, int out_terms,
+                               void* out8, void* cuda_stream)
+{
+    static const char* kFn = "cl_pf_groupnorm";
+    NEED_DEV(in); NEED_DEV(gamma); NEED_DEV(beta); NEED_DEV(stats); NEED_DEV(out);
+    if (out8) NEED_DEV(out8);
+    cl::PfGroupNormDesc d{};
+    d.in = static_cast<const __half*>(in); d.in_lo_rows = in_lo_rows; d.B = B; d.H = H; d.W = W; d.C = C;
+    d.group_ch = group_ch; d.gamma = gamma; d.beta = beta; d.eps = eps; d.stats = stats;
+    d.out = static_cast<__half*>(out); d.out_terms = out_terms; d.out8 = static_cast<uint8_t*>(out8);
+    return finish(kFn, cl::pf_groupnorm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }

@@ -165,8 +165,11 @@ __device__ __forceinline__ void gn_finish(const GnApplyDesc& d, const GnLane& t,
         orow = ((size_t)ph * d.B + it.b) * oplane + (size_t)(it.y / 2 + 1) * Wop + (it.x / 2 + 1);
         olo = (size_t)4 * d.B * oplane;
     }
-    split_store8(d.out + orow * d.C + c, d.out + (orow + olo) * d.C + c, v, d.out_terms == 2);
-    if (d.out8) fp8_store8(d.out8 + orow * d.C + c, d.out8 + (orow + olo) * d.C + c, v);
+    // out_C / out_c0: the destination may be a channel slice of a wider matrix (encoder outputs of the MLR model are
+    // written side by side into one concatenated activation)
+    const size_t oc = (size_t)d.out_C, o0 = (size_t)d.out_c0 + c;
+    split_store8(d.out + orow * oc + o0, d.out + (orow + olo) * oc + o0, v, d.out_terms == 2);
+    if (d.out8) fp8_store8(d.out8 + orow * oc + o0, d.out8 + (orow + olo) * oc + o0, v);
 }
 
 template <int ADD_KIND>
@@ -536,6 +539,88 @@ __global__ void __launch_bounds__(256) frames_to_nchw_kernel(const uint8_t* __re
     }
 }
 
+// GroupNorm of a padded-flat fp16 hi/lo activation (no ReLU): mlr_norm of the MLR model normalises the CONCATENATED
+// encoder outputs (networks.py:421-439, 491-494), i.e. a tensor that is not the raw output of a convolution.  Pass 1
+// accumulates sum / sum of squares per (image, group) in fp64, pass 2 writes the normalised hi / lo (+ e4m3) planes.
+// Any group size (the 384-channel tiny model has 12 channels per group): the group of every channel is looked up.
+constexpr int kPfGnMaxThreads = 256;
+
+// blockDim = chunks * pslots (chunks = C / 8 <= 256): a thread keeps the same 8 channels for every pixel it visits.
+// Statistics: per-channel fp32 partial sums in registers, a fixed-order block reduction per group in fp64, one fp64
+// atomic per (block, group, moment) -- the result does not depend on thread scheduling beyond fp64 round-off.
+template <bool APPLY>
+__global__ void __launch_bounds__(kPfGnMaxThreads) pf_groupnorm_kernel(PfGroupNormDesc d)
+{
+    __shared__ float red[kPfGnMaxThreads][17];
+    __shared__ float2 tab[512];             // APPLY: (mean, rstd) per group of this image
+    const int b = blockIdx.y;
+    const int groups = d.C / d.group_ch;
+    const int chunks = d.C / 8;
+    const int pslots = blockDim.x / chunks;
+    const int chunk = threadIdx.x % chunks, pslot = threadIdx.x / chunks;
+    const int c = chunk * 8;
+    const int Wp = d.W + 2;
+    const size_t plane = (size_t)(d.H + 2) * Wp;
+    float be[8], mu[8], rs[8];
+    if (APPLY) {
+        const double count = (double)d.group_ch * d.H * d.W;
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+            float m, r;
+            mean_rstd(d.stats, b, groups, g, count, d.eps, m, r);
+            tab[g] = make_float2(m, r);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float2 mr = tab[(c + j) / d.group_ch];
+            mu[j] = mr.x;
+            rs[j] = mr.y * __ldg(d.gamma + c + j);
+            be[j] = __ldg(d.beta + c + j);
+        }
+    }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { s1[j] = 0.f; s2[j] = 0.f; }
+    const int total = d.H * d.W;
+    const size_t olo = (size_t)d.B * plane;
+    for (int pix = blockIdx.x * pslots + pslot; pix < total; pix += gridDim.x * pslots) {
+        const int y = pix / d.W, x = pix - y * d.W;
+        const size_t row = (size_t)b * plane + (size_t)(y + 1) * Wp + (x + 1);
+        const uint4 hq = __ldg(reinterpret_cast<const uint4*>(d.in + row * d.C + c));
+        const uint4 lq = __ldg(reinterpret_cast<const uint4*>(d.in + (row + (size_t)d.in_lo_rows) * d.C + c));
+        const __half* hh = reinterpret_cast<const __half*>(&hq);
+        const __half* ll = reinterpret_cast<const __half*>(&lq);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __half2float(hh[j]) + __half2float(ll[j]);
+        if (!APPLY) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = (v[j] - mu[j]) * rs[j] + be[j];
+            split_store8(d.out + row * d.C + c, d.out + (row + olo) * d.C + c, v, d.out_terms == 2);
+            if (d.out8) fp8_store8(d.out8 + row * d.C + c, d.out8 + (row + olo) * d.C + c, v);
+        }
+    }
+    if (!APPLY) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j]; }
+        __syncthreads();
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+            double t1 = 0, t2 = 0;
+            for (int ch = g * d.group_ch; ch < (g + 1) * d.group_ch; ch++) {
+                for (int p = 0; p < pslots; p++) {
+                    t1 += (double)red[p * chunks + (ch >> 3)][ch & 7];
+                    t2 += (double)red[p * chunks + (ch >> 3)][8 + (ch & 7)];
+                }
+            }
+            atomicAdd(d.stats + ((size_t)b * groups + g) * 2, t1);
+            atomicAdd(d.stats + ((size_t)b * groups + g) * 2 + 1, t2);
+        }
+    }
+}
+
 int sm_count()
 {
     int dev = 0, sms = 148;
@@ -552,8 +637,13 @@ const char* last_error()
 
 }  // namespace
 
-const char* gn_apply_launch(const GnApplyDesc& d, cudaStream_t stream)
+const char* gn_apply_launch(const GnApplyDesc& desc, cudaStream_t stream)
 {
+    GnApplyDesc d = desc;
+    if (d.out_C == 0) d.out_C = d.C;
+    if (d.out_C < d.C || d.out_c0 < 0 || d.out_c0 + d.C > d.out_C || d.out_C % 8 != 0 || d.out_c0 % 8 != 0)
+        return "gn_apply: invalid destination channel slice";
+    if (d.out_C != d.C && d.out_phases != 1) return "gn_apply: a channel slice needs a same-resolution output";
     if (d.C % 8 != 0) return "gn_apply: C must be a multiple of 8";
     if (d.out_phases != 1 && d.out_phases != 4) return "gn_apply: out_phases must be 1 or 4";
     if (d.add_kind == 1 && d.out_phases != 1) return "gn_apply: residual add needs a same-resolution output";
@@ -644,6 +734,25 @@ const char* frames_to_nchw_launch(const uint8_t* frames, int B, int H, int W, in
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     frames_to_nchw_kernel<<<(unsigned)blocks, 256, 0, stream>>>(frames, B, H, W, C, mean, stdv, out);
+    return last_error();
+}
+
+const char* pf_groupnorm_launch(const PfGroupNormDesc& d, cudaStream_t stream)
+{
+    if (d.C % 8 != 0 || d.group_ch < 1 || d.C % d.group_ch != 0) return "pf_groupnorm: C must be a multiple of 8 and of the group size";
+    if (d.C / 8 > kPfGnMaxThreads) return "pf_groupnorm: at most 2048 channels";
+    if (d.C / d.group_ch > 512) return "pf_groupnorm: at most 512 groups";
+    if (d.B <= 0 || d.B > 65535 || d.H <= 0 || d.W <= 0) return "pf_groupnorm: invalid sizes";
+    const int chunks = d.C / 8;
+    const int pslots = kPfGnMaxThreads / chunks;
+    const int threads = chunks * pslots;
+    long long bx = ((long long)d.H * d.W + pslots * 8 - 1) / (pslots * 8);
+    const long long cap = ((long long)sm_count() * 6) / d.B;     // about one resident wave
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    pf_groupnorm_kernel<false><<<dim3((unsigned)bx, d.B), threads, 0, stream>>>(d);
+    if (const char* e = last_error()) return e;
+    pf_groupnorm_kernel<true><<<dim3((unsigned)bx, d.B), threads, 0, stream>>>(d);
     return last_error();
 }
 

@@ -137,6 +137,8 @@ struct GnApplyDesc {
     int out_phases;
     int out_terms;          // 2: write hi and lo, 1: hi only
     uint8_t* out8;          // nullable: e4m3 planes [2][B*(H+2)*(W+2)][C] for a consumer in fp16 + fp8 mode
+    int out_C;              // channels of the destination matrices (>= C: the output may be a channel slice), 0 = C
+    int out_c0;             // first destination channel
 };
 const char* gn_apply_launch(const GnApplyDesc& d, cudaStream_t stream);
 
@@ -228,5 +230,21 @@ const char* duc_head_launch(const DucHeadDesc& d, cudaStream_t stream);
 // ---------------------------------------------------------------- input frames: uint8 HWC -> fp32 NCHW (ToTensor [+ Normalize])
 const char* frames_to_nchw_launch(const uint8_t* frames, int B, int H, int W, int C, const float* mean, const float* stdv,
                                   float* out, cudaStream_t stream);
+
+// ---------------------------------------------------------------- GroupNorm of a padded-flat activation (MLR merge)
+struct PfGroupNormDesc {
+    const __half* in;       // fp16 PF [2][B*(H+2)*(W+2)][C] hi / lo planes (P = 1)
+    int64_t in_lo_rows;
+    int B, H, W, C;
+    int group_ch;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    double* stats;          // [B][C/group_ch][2], zeroed by the caller
+    __half* out;            // same geometry, normalised (no ReLU)
+    int out_terms;
+    uint8_t* out8;          // nullable e4m3 planes
+};
+const char* pf_groupnorm_launch(const PfGroupNormDesc& d, cudaStream_t stream);
 
 }  // namespace cl

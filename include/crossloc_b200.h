@@ -159,11 +159,24 @@ int cl_pack_filter(const float* w, const float* scale, void* out, int Cout, int 
  *   res_lo_rows: row distance of the residual's lo plane, 0 when it has none (single-pass mode)
  *   out_phases 1: same geometry;  4: the four parity phases at (ceil(H/2), ceil(W/2)).
  *   out8: nullable e4m3 planes [2][B*(H+2)*(W+2)][C] written alongside (input of an nterms == 2 convolution).
+ *   out_C / out_c0: the destination matrices have out_C channels per row (0 = C) and the result goes to channels
+ *   out_c0 .. out_c0 + C - 1: the encoders of the MLR model write side by side into one concatenated activation
+ *   (torch.cat(..., dim=1), networks.py:488).
  */
 int cl_gn_apply(const float* raw, int B, int H, int W, int C, int group_ch, const double* stats, const float* gamma,
                 const float* beta, float eps, int relu_inner, int add_kind, const void* res, int64_t res_lo_rows,
                 const float* raw2, const double* stats2, const float* gamma2, const float* beta2, int relu_outer,
-                void* out, int out_phases, int out_terms, void* out8, void* cuda_stream);
+                void* out, int out_phases, int out_terms, void* out8, int out_C, int out_c0, void* cuda_stream);
+
+/*
+ * GroupNorm (no ReLU) of a padded-flat fp16 hi/lo activation [2][B*(H+2)*(W+2)][C]: mlr_norm of the MLR model
+ * normalises the concatenated encoder outputs (networks.py:421-439, 491-494), which are not the raw output of a
+ * convolution.  Two launches: fp64 sums per (image, group) into `stats` ([B][C/group_ch][2], zeroed by the caller),
+ * then the normalised hi / lo (out_terms 2) and optional e4m3 planes.  Any group size that divides C.
+ */
+int cl_pf_groupnorm(const void* in, int64_t in_lo_rows, int B, int H, int W, int C, int group_ch, const float* gamma,
+                    const float* beta, float eps, double* stats, void* out, int out_terms, void* out8,
+                    void* cuda_stream);
 
 /*
  * Stem: conv3x3 s1 (Cin = 1 or 3 -> 32) + per-channel GroupNorm(32, 32) + ReLU, written as the

@@ -398,9 +398,31 @@ class TransPoseNet(nn.Module):
                 'roles': roles}
 
     def _forward_mlr(self, inputs):
-        """MLR model (networks.py:482-494): every encoder and the decoder run their fused plans; the merge in between
-        (1536-channel GroupNorm, mlr_skip, mlr_forward) runs its convolutions on the tensor-core kernels with stock
-        GroupNorm -- 89 % of the FLOPs are in the fused parts."""
+        """MLR model (networks.py:482-494), fully on the fused plans: every encoder writes its output into a channel
+        slice of one concatenated padded-flat activation (torch.cat, :488); the merge -- mlr_skip, mlr_norm over the
+        concatenation (cl_pf_groupnorm), mlr_forward, relu(res + mlr) -- and the decoder run as one more plan on it."""
+        eng = self._engine
+        if eng.terms != 2:   # single-pass speed mode: no lo planes to normalise from
+            return self._forward_mlr_unfused(inputs)
+        width = _width(self.tiny)
+        batch, _, h, w = inputs.shape
+        concat = eng.shared_pf('mlr_concat', inputs.device, batch, h, w, width * self.num_mlr)
+        skip_conv = self.mlr_skip[0]
+        need8 = eng.nterms_of(skip_conv) == 2
+        for i, enc in enumerate(self.mlr_encoder_ls):
+            layers, blocks, roles = enc.plan('mlr_encoder_%d.' % (i + 1))
+            eng.forward({'group_norm': True, 'layers': layers, 'blocks': blocks, 'roles': roles, 'output': 'pf',
+                         'out_pf': (concat, i * width, need8)}, inputs)
+        names = ['mlr_forward.%d' % j for j in (0, 3, 6)]
+        merge_layers = [('mlr_skip.0', skip_conv, self.mlr_skip[1])]
+        merge_layers += [(names[k], self.mlr_forward[3 * k], self.mlr_forward[3 * k + 1]) for k in range(3)]
+        merge = {'kind': 'mlr_merge', 'skip': 'mlr_skip.0', 'convs': names, 'norm_in': self.mlr_norm}
+        dec_layers, dec_blocks, head = self._decoder_plan(inputs)
+        return eng.forward({'group_norm': True, 'layers': merge_layers + dec_layers, 'blocks': [merge] + dec_blocks,
+                            'head': head, 'input': 'pf', 'in_pf': concat}, None)
+
+    def _forward_mlr_unfused(self, inputs):
+        """Encoders and decoder as fused plans, the merge on the native convolutions with stock GroupNorm."""
         acts = []
         for i, enc in enumerate(self.mlr_encoder_ls):
             layers, blocks, roles = enc.plan('mlr_encoder_%d.' % (i + 1))

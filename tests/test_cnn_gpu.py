@@ -141,7 +141,7 @@ def test_gn_apply_variants():
         _lib.check(lib.cl_gn_apply(r1.data_ptr(), b, h, w, c, c // 32, s1.data_ptr(), gn.weight.data_ptr(),
                                    gn.bias.data_ptr(), 1e-5, 1, add_kind, res_pf.data_ptr(), geo.Mp, r2.data_ptr(),
                                    s2.data_ptr(), gn2.weight.data_ptr(), gn2.bias.data_ptr(), relu_outer,
-                                   out.data_ptr(), phases, 2, out8.data_ptr() if phases == 1 else 0,
+                                   out.data_ptr(), phases, 2, out8.data_ptr() if phases == 1 else 0, 0, 0,
                                    torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         if phases == 1:
@@ -298,6 +298,9 @@ def test_mlr_fused_plan_matches_reference_math():
     assert rel_l2(out[:, :3], ref[:, :3]) < 2e-4
     assert rel_l2(out[:, 3:], ref[:, 3:]) < 1e-3
     assert rel_l2(out[:, :3], via_train[:, :3]) < 2e-4
+    with torch.no_grad():
+        unfused = net._forward_mlr_unfused(x)
+    assert rel_l2(out, unfused) < 2e-4   # fused merge (cl_pf_groupnorm, sliced encoder outputs) vs stock GroupNorm + torch.cat
     launches = net._engine.launches
     with torch.no_grad():
         out2 = net(x)
