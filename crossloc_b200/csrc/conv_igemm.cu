@@ -478,9 +478,17 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
+    if (warp == 0 || warp == 3) {
+        // ------------------------------------------------------------------ TMA producers (both CTAs)
+        // Layers with one k-block per tap (conv2, conv3) use two producer threads per CTA: warp 0 loads the activation
+        // boxes (and arms the barrier), warp 3 the weight boxes.  One thread needs ~250 instructions per stage for four
+        // loads; with short stages that is on the critical path (conv2: producer and MMA issuer are both
+        // instruction bound, ncu: tensor pipe 18 %; 1.06 -> 0.98 ms stand-alone).
+        // Only for layers with a single k-block per tap: with longer K loops the MMAs hide the producer anyway and the
+        // second thread costs ~1 % (measured on the 512-channel layers).
+        const bool split = p.kblocks_per_tap == 1 && !f8c;
+        const bool load_a = warp == 0, load_w = split ? warp == 3 : warp == 0;
+        if (lane == 0 && (load_a || load_w)) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_pair = 2u * (uint32_t)nA * (p.a_bytes + w_half);
@@ -500,7 +508,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             const uint32_t bar = ptx::smem_u32(&full_bar[stage]);   // resolved to the leader's copy by the load
                             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                             const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
-                            if (leader) ptx::mbar_expect_tx(bar, tx_pair);
+                            if (leader && load_a) ptx::mbar_expect_tx(bar, tx_pair);
                             if (pass == 0) {
                                 ptx::tma_load_2d_pair(sa, &tmA8, bar, kb * BK, p.a8_lo_rows + a_row);           // a_lo8
                                 ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA8, bar, kb * BK, a_row);              // a_hi8
@@ -512,11 +520,13 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                 ptx::tma_load_2d_pair(sw, &tmW, bar, kb * BK, w_row);
                                 ptx::tma_load_2d_pair(sw + w_half, &tmW, bar, (kb + 1) * BK, w_row);
                             } else {
-                                ptx::tma_load_2d_pair(sa, &tmA, bar, kb * BK, a_row);
-                                ptx::tma_load_2d_pair(sw, &tmW, bar, kb * BK, w_row);
-                                if (nA == 2) {
-                                    ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA, bar, kb * BK, p.a_lo_rows + a_row);
-                                    ptx::tma_load_2d_pair(sw + w_half, &tmW, bar, kb * BK, p.w_lo_rows + w_row);
+                                if (load_a) {
+                                    ptx::tma_load_2d_pair(sa, &tmA, bar, kb * BK, a_row);
+                                    if (nA == 2) ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA, bar, kb * BK, p.a_lo_rows + a_row);
+                                }
+                                if (load_w) {
+                                    ptx::tma_load_2d_pair(sw, &tmW, bar, kb * BK, w_row);
+                                    if (nA == 2) ptx::tma_load_2d_pair(sw + w_half, &tmW, bar, kb * BK, p.w_lo_rows + w_row);
                                 }
                             }
                             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }

@@ -99,8 +99,9 @@ class TrainPlan:
         eng.tape = []
         spec = self.net._spec()
         out = eng.forward(spec, image)
+        # the tape points into workspace buffers the next forward overwrites: remember which forward a state belongs to
         state = {'tape': eng.tape, 'head_in': eng.head_in, 'stem_out': eng.stem_out, 'spec': spec, 'image': image,
-                 'geo3': eng.head_in.geo}
+                 'geo3': eng.head_in.geo, 'generation': self._step + 1}
         eng.tape = None
         self._step += 1
         return out, state
@@ -197,6 +198,10 @@ class TrainPlan:
     # ------------------------------------------------------------------ backward
     def backward(self, state, g_out):
         """Gradients of every parameter given dL/d(output); returns {parameter: gradient}."""
+        if state['generation'] != self._step:
+            raise RuntimeError('crossloc_b200: backward through a forward whose activations have been overwritten -- the '
+                               'fused training plan keeps ONE forward per network (call backward before the next forward, '
+                               'or use forward_train(x, fused=False))')
         lib = _lib.load()
         image = state['image']
         dev = image.device

@@ -177,3 +177,16 @@ def test_training_step_matches_reference_autograd(fused):
     # and it is what forward() itself runs when autograd is on
     out = net(x)
     assert out.requires_grad
+
+
+def test_fused_plan_refuses_stale_backward():
+    """Two forwards before a backward would silently differentiate through overwritten activations: it raises instead."""
+    import networks.networks as nets
+    torch.manual_seed(1)
+    net = nets.TransPoseNet(torch.zeros(3), True, False, 0, 0, 3, 1).to(DEV).train()
+    x = torch.rand(1, 3, 32, 48, device=DEV)
+    first = net.forward_train(x, fused=True)
+    second = net.forward_train(x, fused=True)
+    second.sum().backward()          # the latest forward is fine
+    with pytest.raises(RuntimeError, match='ONE forward'):
+        first.sum().backward()
