@@ -29,7 +29,8 @@ constexpr int kThreads = 288;                  // 4 builder warps, 4 epilogue wa
 constexpr uint32_t kPlaneBytes = kTile * 64;   // one fp16 plane of the A tile: 128 rows x 32 K
 constexpr uint32_t kABytes = 2 * kPlaneBytes;  // hi + lo
 constexpr uint32_t kBPlaneBytes = kCo * 64;
-constexpr uint32_t kSmemBytes = 2 * kABytes + 2 * kBPlaneBytes + 1024;
+constexpr uint32_t kStageBytes = 4096;          // per epilogue warp: [plane hi/lo][x parity][16 rows][64 B]
+constexpr uint32_t kSmemBytes = 2 * kABytes + 2 * kBPlaneBytes + 4 * kStageBytes + 1024;
 constexpr uint32_t kTmemCols = 64;             // two 32-column accumulators
 
 // byte offset of 16-byte chunk c (8 K-elements) of row r in a K-major tile with 64-byte rows, SWIZZLE_64B
@@ -246,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_tc_kernel(StemDesc d)
         // ------------------------------------------------------------------ epilogue
         const int q = warp - 4;
         const float inv_scale = wscale_s[1];
+        const uint32_t stage_base = b_base + 2 * kBPlaneBytes;
         const int Ho = (d.H + 1) / 2, Wo = (d.W + 1) / 2, Wop = Wo + 2;
         const size_t oplane = (size_t)(Ho + 2) * Wop;
         const size_t olo = (size_t)4 * d.B * oplane;
@@ -275,22 +277,54 @@ __global__ void __launch_bounds__(kThreads, 2) stem_tc_kernel(StemDesc d)
                         tot[(2 * co + 1) % (STATS ? 2 * kCo : 1)] = fmaf(a, a, tot[(2 * co + 1) % (STATS ? 2 * kCo : 1)]);
                     }
                 }
-            } else if (inside) {
-                const int ph = (y & 1) * 2 + (x & 1);
-                const size_t orow = ((size_t)ph * d.B + b) * oplane + (size_t)(y / 2 + 1) * Wop + (x / 2 + 1);
+            } else {
+                // Stores through a per-warp staging tile: lane = pixel holds 64 B per plane, but neighbouring pixels
+                // alternate between two parity phases, so direct stores touch 32 half-used sectors per instruction.
+                // Staged, every instruction writes 512 contiguous bytes (eight 64-byte rows of one phase plane).
+                const uint32_t st = stage_base + (uint32_t)q * kStageBytes;
+                const int px = lane & 1, rrow = lane >> 1;
+                const uint32_t key = (uint32_t)(((rrow >> 1) & 1) | (px << 1));
+                if (inside) {
 #pragma unroll
-                for (int c0 = 0; c0 < kCo; c0 += 8) {
-                    float v[8];
+                    for (int c0 = 0; c0 < kCo; c0 += 8) {
+                        float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float2 af = affine_s[c0 + j];
-                        v[j] = fmaxf(fmaf(fmaf(__uint_as_float(u[c0 + j]), inv_scale, bias_s[c0 + j]), af.x, af.y), 0.f);
+                        for (int j = 0; j < 8; j++) {
+                            const float2 af = affine_s[c0 + j];
+                            v[j] = fmaxf(fmaf(fmaf(__uint_as_float(u[c0 + j]), inv_scale, bias_s[c0 + j]), af.x, af.y), 0.f);
+                        }
+                        uint4 hi, lo;
+                        split8(v, hi, lo);
+                        const uint32_t off = (uint32_t)(px * 16 + rrow) * 64u + ((((uint32_t)c0 >> 3) ^ key) << 4);
+                        st_shared_v4(st + off, hi);
+                        st_shared_v4(st + 2048u + off, lo);
                     }
-                    uint4 hi, lo;
-                    split8(v, hi, lo);
-                    *reinterpret_cast<uint4*>(d.out + orow * kCo + c0) = hi;
-                    if (d.out_terms == 2) *reinterpret_cast<uint4*>(d.out + (orow + olo) * kCo + c0) = lo;
                 }
+                __syncwarp();
+                const int xw = (t - y * tiles_x) * kTile + q * 32;   // first pixel of this warp (even)
+#pragma unroll
+                for (int plane_i = 0; plane_i < 2; plane_i++) {
+                    if (plane_i == 1 && d.out_terms != 2) break;
+#pragma unroll
+                    for (int ppx = 0; ppx < 2; ppx++) {
+                        const int ph = (y & 1) * 2 + ppx;
+                        const size_t orow0 = ((size_t)ph * d.B + b) * oplane + (size_t)(y / 2 + 1) * Wop + (xw / 2 + 1) +
+                                             (plane_i ? olo : 0);
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const int j = lane + 32 * k, rr = j >> 2, cc = j & 3;
+                            if (xw + 2 * rr + ppx < d.W) {
+                                const uint32_t kk = (uint32_t)(((rr >> 1) & 1) | (ppx << 1));
+                                uint4 val;
+                                const uint32_t addr = st + (uint32_t)plane_i * 2048u + (uint32_t)(ppx * 16 + rr) * 64u + ((((uint32_t)cc) ^ kk) << 4);
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                                             : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(addr));
+                                *reinterpret_cast<uint4*>(d.out + (orow0 + rr) * kCo + cc * 8) = val;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
         if (STATS) {
