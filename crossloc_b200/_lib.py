@@ -33,7 +33,7 @@ SIGNATURES = {
         _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
         _c.c_float, _c.c_int, _c.c_int, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _i32p,
         _i32p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p,
-        _c.c_void_p]),
+        _c.c_void_p, _c.c_void_p]),
     'cl_nchw_to_pf': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                  _c.c_void_p]),
     'cl_pf_to_nchw': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,
@@ -50,7 +50,7 @@ SIGNATURES = {
         _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
     'cl_stem_forward': (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,
-        _c.c_void_p, _c.c_void_p, _c.c_float, _c.c_void_p, _c.c_int, _c.c_void_p]),
+        _c.c_void_p, _c.c_void_p, _c.c_float, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
     'cl_head_forward': (_c.c_int, [
         _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
         _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p]),

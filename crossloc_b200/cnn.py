@@ -342,16 +342,21 @@ class CoordNetEngine:
                 raise RuntimeError('crossloc_b200: the stem kernel is built for 32 channels / 32 groups')
             a = self._act(ws, 'stem', 1, 32, 4)
             st = next_stats() if norm1 is not None else None
+            stem_raw = None
+            if self.tape is not None:   # training: keep the raw conv1 output for the GroupNorm / ReLU backward
+                stem_raw = self._raw(ws, 'stem', 0, 32, 'stem')
             e0 = self._tick()
             _lib.check(self._lib.cl_stem_forward(
                 image.data_ptr(), batch, cin, h, w, conv1.weight.detach().contiguous().data_ptr(),
                 conv1.bias.detach().contiguous().data_ptr(), 1 if norm1 is not None else 0,
                 0 if st is None else st.data_ptr(), 0 if norm1 is None else norm1.weight.data_ptr(),
                 0 if norm1 is None else norm1.bias.data_ptr(), 1e-5 if norm1 is None else float(norm1.eps),
-                a.h16.data_ptr(), self.terms, stream))
+                a.h16.data_ptr(), self.terms, 0 if stem_raw is None else stem_raw.data_ptr(), stream))
             self._tock(e0, 'stem', ('stem',), 2.0 * batch * h * w * 32 * cin * 9)
             self.launches += 2 if norm1 is not None else 1
             self.stem_out = a if self.tape is not None else None
+            self.stem_rec = None if self.tape is None else {'raw': stem_raw, 'stats': st, 'norm': norm1, 'geo': geo[0],
+                                                            'conv': conv1}
 
             # ---- strided ladder conv2..conv4
             for level, role in ((1, 'conv2'), (2, 'conv3'), (3, 'conv4')):

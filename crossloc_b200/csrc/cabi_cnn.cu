@@ -130,18 +130,19 @@ extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int gro
 
 extern "C" int cl_stem_forward(const float* image, int B, int Cin, int H, int W, const float* weight,
                                const float* bias, int has_gn, double* stats, const float* gamma, const float* beta,
-                               float eps, void* out, int out_terms, void* cuda_stream)
+                               float eps, void* out, int out_terms, float* raw_out, void* cuda_stream)
 {
     static const char* kFn = "cl_stem_forward";
+    if (raw_out) NEED_DEV(raw_out);
     NEED_DEV(image); NEED_DEV(weight); NEED_DEV(bias); NEED_DEV(out);
     if (has_gn) { NEED_DEV(stats); NEED_DEV(gamma); NEED_DEV(beta); }
     cl::StemDesc d{};
     d.image = image; d.B = B; d.Cin = Cin; d.H = H; d.W = W; d.weight = weight; d.bias = bias; d.has_gn = has_gn;
     d.stats = stats; d.gamma = gamma; d.beta = beta; d.eps = eps; d.out = static_cast<__half*>(out);
-    d.out_terms = out_terms;
+    d.out_terms = out_terms; d.raw_out = raw_out;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     const char* env = getenv("CROSSLOC_B200_STEM");
-    if (env && env[0] == 'c') {   // "cuda": the CUDA-core kernels, kept for comparison
+    if (env && env[0] == 'c' && !raw_out) {   // "cuda": the CUDA-core kernels, kept for comparison (inference only)
         if (has_gn)
             if (int rc = finish(kFn, cl::stem_stats_launch(d, s))) return rc;
         return finish(kFn, cl::stem_apply_launch(d, s));
@@ -206,7 +207,7 @@ extern "C" int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch
                               const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
                               const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out,
                               double* ab, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows, float* scale_out,
-                              double* dbias, void* cuda_stream)
+                              double* dbias, float* d_raw_f32, void* cuda_stream)
 {
     static const char* kFn = "cl_gn_backward";
     NEED_DEV(raw); NEED_DEV(ab); NEED_DEV(gmax_bits);
@@ -224,7 +225,8 @@ extern "C" int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch
     }
     d.mask_out = static_cast<const __half*>(mask_out); d.g_out = g_out; d.ab = ab;
     d.gmax_bits = static_cast<unsigned*>(gmax_bits); d.d_raw = static_cast<__half*>(d_raw); d.d_raw_lo_rows = d_raw_lo_rows;
-    d.scale_out = scale_out; d.dbias = dbias;
+    d.scale_out = scale_out; d.dbias = dbias; d.d_raw_f32 = d_raw_f32;
+    if (d_raw_f32) NEED_DEV(d_raw_f32);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (pass == 0) return finish(kFn, cl::gn_bwd_reduce_launch(d, s));
     NEED_DEV(d_raw); NEED_DEV(scale_out);

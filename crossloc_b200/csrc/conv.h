@@ -169,6 +169,7 @@ struct GnBwdDesc {
     int64_t d_raw_lo_rows;
     float* scale_out;       // pass 2: {2^k, 2^-k}
     double* dbias;          // pass 2, nullable: [C] += sum d_raw (gradient of the convolution bias)
+    float* d_raw_f32;       // pass 2, nullable: the same gradient unscaled in fp32 PF [rows][C] (stem: weight gradient in torch)
 };
 const char* gn_bwd_reduce_launch(const GnBwdDesc& d, cudaStream_t stream);
 const char* gn_bwd_apply_launch(const GnBwdDesc& d, cudaStream_t stream);
@@ -186,6 +187,7 @@ struct StemDesc {
     float eps;
     __half* out;            // PF, 4 phases at (ceil(H/2), ceil(W/2)), C = 32
     int out_terms;
+    float* raw_out;         // nullable (tensor-core version only): raw conv1 output, fp32 PF [B*(H+2)*(W+2)][32], for training
 };
 // tensor-core version (stem_tc.cu): im2col rows built in shared memory, tcgen05 fp16x3; same two passes
 const char* stem_tc_launch(const StemDesc& d, bool stats_pass, cudaStream_t stream);

@@ -193,6 +193,11 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 4 : 3) gn_bwd_kernel(GnBwdDe
                 a1[j] += val;
             }
         }
+        if (APPLY && d.d_raw_f32) {
+            float4* o = reinterpret_cast<float4*>(d.d_raw_f32 + row * d.C + c);
+            o[0] = make_float4(dr[0], dr[1], dr[2], dr[3]);
+            o[1] = make_float4(dr[4], dr[5], dr[6], dr[7]);
+        }
         if (APPLY) {
             __align__(16) __half h[8];
             __align__(16) __half l[8];

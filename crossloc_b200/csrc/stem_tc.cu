@@ -281,6 +281,16 @@ __global__ void __launch_bounds__(kThreads, 2) stem_tc_kernel(StemDesc d)
                 // Stores through a per-warp staging tile: lane = pixel holds 64 B per plane, but neighbouring pixels
                 // alternate between two parity phases, so direct stores touch 32 half-used sectors per instruction.
                 // Staged, every instruction writes 512 contiguous bytes (eight 64-byte rows of one phase plane).
+                if (d.raw_out && inside) {   // training: keep the raw convolution output (fp32 PF at the input resolution)
+                    float4* ro = reinterpret_cast<float4*>(
+                        d.raw_out + (((size_t)b * (d.H + 2) + (y + 1)) * (d.W + 2) + (x + 1)) * kCo);
+#pragma unroll
+                    for (int c0 = 0; c0 < kCo; c0 += 4)
+                        ro[c0 >> 2] = make_float4(fmaf(__uint_as_float(u[c0]), inv_scale, bias_s[c0]),
+                                                  fmaf(__uint_as_float(u[c0 + 1]), inv_scale, bias_s[c0 + 1]),
+                                                  fmaf(__uint_as_float(u[c0 + 2]), inv_scale, bias_s[c0 + 2]),
+                                                  fmaf(__uint_as_float(u[c0 + 3]), inv_scale, bias_s[c0 + 3]));
+                }
                 const uint32_t st = stage_base + (uint32_t)q * kStageBytes;
                 const int px = lane & 1, rrow = lane >> 1;
                 const uint32_t key = (uint32_t)(((rrow >> 1) & 1) | (px << 1));

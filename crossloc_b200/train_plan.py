@@ -12,8 +12,8 @@ Here the whole network is ONE autograd node:
             transposed filter) and the weight gradient (cl_conv_wgrad_pf) read those planes directly.
 
 Activations and gradients never leave the padded-flat layout between layers, so the NCHW <-> operand conversions of
-the per-layer path (crossloc_b200.train) disappear.  The 3-channel stem and the 4-channel head are differentiated
-with stock torch ops (0.2 % of the FLOPs).  Covers TransPoseNet / Network without MLR encoders or the full-size head;
+the per-layer path (crossloc_b200.train) disappear.  The stem's GroupNorm / ReLU backward runs on the same kernels from the
+raw conv1 output the forward keeps; its 864-entry weight gradient and the 4-channel head are left to stock torch ops.  Covers TransPoseNet / Network without MLR encoders or the full-size head;
 the other variants keep using the per-layer path.
 """
 import ctypes
@@ -23,8 +23,8 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib, layout
-from .cnn import CoordNetEngine, _Geometry, _nterms_for, _W8_LO_SCALE
-from .train import _forward_taps, _i32, _pack, _stream
+from .cnn import CoordNetEngine, _nterms_for, _W8_LO_SCALE
+from .train import _i32, _pack
 
 _NTERMS = 3
 # arithmetic of the data / weight gradient GEMMs: 'fp16x3' (default, fp32-grade like the forward) or 'fp16x1' (one
@@ -100,7 +100,8 @@ class TrainPlan:
         spec = self.net._spec()
         out = eng.forward(spec, image)
         # the tape points into workspace buffers the next forward overwrites: remember which forward a state belongs to
-        state = {'tape': eng.tape, 'head_in': eng.head_in, 'stem_out': eng.stem_out, 'spec': spec, 'image': image,
+        state = {'tape': eng.tape, 'head_in': eng.head_in, 'stem_out': eng.stem_out, 'stem_rec': eng.stem_rec, 'spec': spec,
+                 'image': image,
                  'geo3': eng.head_in.geo, 'generation': self._step + 1}
         eng.tape = None
         self._step += 1
@@ -117,7 +118,7 @@ class TrainPlan:
             buf = self._pool[key] = torch.zeros(2 * geo.Mp, channels, dtype=torch.float16, device=device)
         return buf
 
-    def _gn_backward(self, lib, stream, geo, channels, rec, norm, relu_inner, srcs, mask, want_g):
+    def _gn_backward(self, lib, stream, geo, channels, rec, norm, relu_inner, srcs, mask, want_g, d_raw_f32=None):
         """Both passes of cl_gn_backward for one stage; returns (d_raw, scale_out, ab, dbias, g_buf)."""
         dev = rec['raw'].device
         n_ab = geo.B * channels * 2
@@ -143,7 +144,8 @@ class TrainPlan:
                 _i32([1 if s.phased else 0 for s in sources] + [0] * (3 - n)),
                 None if (mask is None or pass_id == 1) else mask.data_ptr(),
                 None if (g_buf is None or pass_id == 1) else g_buf.data_ptr(), ab.data_ptr(), gmax.data_ptr(),
-                d_raw.data_ptr(), geo.Mp, scale_out.data_ptr(), dbias.data_ptr(), stream))
+                d_raw.data_ptr(), geo.Mp, scale_out.data_ptr(), dbias.data_ptr(),
+                None if (d_raw_f32 is None or pass_id == 0) else d_raw_f32.data_ptr(), stream))
 
         call(0, srcs)
         call(1, [_Src(g_buf, channels)] if want_g else srcs[:1])
@@ -267,34 +269,24 @@ class TrainPlan:
                 grads[id(srec['pack'].weight_param)] = srec['gw']
                 sources.setdefault(id(srec['act']), []).append(src)
 
-        # ---- stem (conv1 + norm1 + relu on the 3-channel frame): stock torch ops, recomputed
+        # ---- stem (conv1 + norm1 + relu on the 1- or 3-channel frame): GroupNorm / ReLU backward on the native kernels from
+        # the raw conv1 output the forward kept (the four-phase data gradient of conv2 is read in place); the 864-entry
+        # weight gradient is left to torch (cuDNN wgrad on the fp32 NCHW copy of the result)
         if stem_out is not None:
-            (src,) = sources.pop(id(stem_out))
-            h, w_ = image.shape[2:]
-            g_stem = torch.empty(image.size(0), 32, h, w_, dtype=torch.float32, device=dev)
-            if h % 2 or w_ % 2:
-                g_stem.zero_()
-            geo1 = _Geometry(image.size(0), (h + 1) // 2, (w_ + 1) // 2)
-            scale = src.scale_a * src.scale_b
-            for a in (0, 1):
-                for bb in (0, 1):
-                    ph = a * 2 + bb
-                    _lib.check(lib.cl_pf_to_nchw(src.g[ph * geo1.Mp:(ph + 1) * geo1.Mp].data_ptr(), geo1.B, geo1.H, geo1.W,
-                                                 src.stride, g_stem.data_ptr(), 32, h, w_, 2, a, bb, scale.data_ptr(), None,
-                                                 stream))
-            convs = {name: (conv, norm) for name, conv, norm in spec['layers']}
-            conv1, norm1 = convs[spec.get('roles', {'conv1': 'conv1'})['conv1']]
-            with torch.enable_grad():
-                params = [conv1.weight.detach().requires_grad_(True), conv1.bias.detach().requires_grad_(True)]
-                y = F.conv2d(image, params[0], params[1], padding=1)
-                if norm1 is not None:
-                    params += [norm1.weight.detach().requires_grad_(True), norm1.bias.detach().requires_grad_(True)]
-                    y = F.group_norm(y, norm1.num_groups, params[2], params[3], norm1.eps)
-                y = F.relu(y)
-                g = torch.autograd.grad(y, params, g_stem)
-            grads[id(conv1.weight)], grads[id(conv1.bias)] = g[0], g[1]
+            srcs = sources.pop(id(stem_out))
+            rec = state['stem_rec']
+            conv1, norm1, geo0 = rec['conv'], rec['norm'], rec['geo']
+            d_f32 = torch.empty(geo0.Mp, 32, dtype=torch.float32, device=dev)
+            _, _, ab, dbias, _ = self._gn_backward(lib, stream, geo0, 32, rec, norm1, True, srcs, None, False, d_raw_f32=d_f32)
+            g_conv = torch.empty(geo0.B, 32, geo0.H, geo0.W, dtype=torch.float32, device=dev)
+            _lib.check(lib.cl_pf_to_nchw(d_f32.data_ptr(), geo0.B, geo0.H, geo0.W, 32, g_conv.data_ptr(), 32, geo0.H, geo0.W, 1, 0,
+                                         0, None, None, stream))
+            grads[id(conv1.weight)] = torch.nn.grad.conv2d_weight(image, conv1.weight.shape, g_conv, padding=1)
+            grads[id(conv1.bias)] = dbias.to(torch.float32)
             if norm1 is not None:
-                grads[id(norm1.weight)], grads[id(norm1.bias)] = g[2], g[3]
+                sums = ab.sum(0)
+                grads[id(norm1.bias)] = sums[:, 0].to(torch.float32)
+                grads[id(norm1.weight)] = sums[:, 1].to(torch.float32)
         return grads
 
     @staticmethod

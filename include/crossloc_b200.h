@@ -125,13 +125,14 @@ int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const void* act, in
  * (scale_out = {2^k, 2^-k}, derived on the device), adding its per-channel sums to `dbias` (nullable).
  * d_gamma = sum_b ab[b][c][1], d_beta = sum_b ab[b][c][0].  group_ch = 0: no normalisation (vanilla Network).
  * Caller zeroes ab, gmax_bits, dbias; d_raw keeps zero border rows (only interior pixels are written).
+ * d_raw_f32 (nullable): the same gradient, unscaled, as fp32 PF [rows][C] (the stem's weight gradient is left to torch).
  */
 int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch, const float* raw, const double* stats,
                    const float* gamma, const float* beta, float eps, int relu_inner, int num_src,
                    const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
                    const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out, double* ab,
                    void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows, float* scale_out, double* dbias,
-                   void* cuda_stream);
+                   float* d_raw_f32, void* cuda_stream);
 
 /*
  * Layout kernels of the training path (device pointers): NCHW fp32 tensors, as autograd hands them over, to and
@@ -184,10 +185,11 @@ int cl_pf_groupnorm(const void* in, int64_t in_lo_rows, int B, int H, int W, int
  * the 32-channel full-resolution fp32 tensor the reference materialises is never written.
  * Replaces encoder.conv1 / norm1 (networks.py:186-190, 231) and Network.conv1 (:59, 96; has_gn = 0).
  *   image NCHW fp32 [B][Cin][H][W]; weight OIHW fp32 [32][Cin][3][3]; stats fp64 [B][32][2] zeroed by caller.
+ *   raw_out (nullable, training): the raw conv1 output incl. bias as fp32 PF [B*(H+2)*(W+2)][32], interior rows.
  */
 int cl_stem_forward(const float* image, int B, int Cin, int H, int W, const float* weight, const float* bias,
                     int has_gn, double* stats, const float* gamma, const float* beta, float eps, void* out,
-                    int out_terms, void* cuda_stream);
+                    int out_terms, float* raw_out, void* cuda_stream);
 
 /*
  * Output head: 1x1 convolution C -> Co (Co <= 8) + mean offset on the task channels +

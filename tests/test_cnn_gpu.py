@@ -183,7 +183,7 @@ def test_stem_matches_torch(cin, has_gn):
     out = torch.zeros(2 * 4 * b * (ho + 2) * (wo + 2), 32, dtype=torch.float16, device=DEV)
     stats = torch.zeros(b, 32, 2, dtype=torch.float64, device=DEV)
     _lib.check(lib.cl_stem_forward(x.data_ptr(), b, cin, h, w, conv.weight.data_ptr(), conv.bias.data_ptr(), has_gn,
-                                   stats.data_ptr(), gn.weight.data_ptr(), gn.bias.data_ptr(), 1e-5, out.data_ptr(), 2,
+                                   stats.data_ptr(), gn.weight.data_ptr(), gn.bias.data_ptr(), 1e-5, out.data_ptr(), 2, 0,
                                    torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     with torch.no_grad():
