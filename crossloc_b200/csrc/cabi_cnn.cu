@@ -256,3 +256,14 @@ extern "C" int cl_pf_groupnorm(const void* in, int64_t in_lo_rows, int B, int H,
     d.out = static_cast<__half*>(out); d.out_terms = out_terms; d.out8 = static_cast<uint8_t*>(out8);
     return finish(kFn, cl::pf_groupnorm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
+
+extern "C" int cl_head_backward(const void* act, int64_t act_lo_rows, int B, int H, int W, int C, int Co,
+                                const float* weight, const float* g_sc, float* g_x, float* g_w, void* cuda_stream)
+{
+    static const char* kFn = "cl_head_backward";
+    NEED_DEV(act); NEED_DEV(weight); NEED_DEV(g_sc); NEED_DEV(g_x); NEED_DEV(g_w);
+    cl::HeadBwdDesc d{};
+    d.act = static_cast<const __half*>(act); d.act_lo_rows = act_lo_rows; d.B = B; d.H = H; d.W = W; d.C = C; d.Co = Co;
+    d.weight = weight; d.g_sc = g_sc; d.g_x = g_x; d.g_w = g_w;
+    return finish(kFn, cl::head_bwd_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}

@@ -172,6 +172,18 @@ struct GnBwdDesc {
     float* d_raw_f32;       // pass 2, nullable: the same gradient unscaled in fp32 PF [rows][C] (stem: weight gradient in torch)
 };
 const char* gn_bwd_reduce_launch(const GnBwdDesc& d, cudaStream_t stream);
+
+// backward of the 1x1 output head on the padded-flat activation it read
+struct HeadBwdDesc {
+    const __half* act;      // PF fp16 hi / lo [2][B*(H+2)*(W+2)][C] input of the head
+    int64_t act_lo_rows;
+    int B, H, W, C, Co;
+    const float* weight;    // fp32 [Co][C]
+    const float* g_sc;      // gradient of the head's pre-activation output, NCHW fp32 [B][Co][H][W]
+    float* g_x;             // out: fp32 PF [B*(H+2)*(W+2)][C] (interior rows)
+    float* g_w;             // out: fp32 [Co][C], accumulated with atomics (caller zeroes)
+};
+const char* head_bwd_launch(const HeadBwdDesc& d, cudaStream_t stream);
 const char* gn_bwd_apply_launch(const GnBwdDesc& d, cudaStream_t stream);
 
 // ---------------------------------------------------------------- stem convolution (3x3, stride 1, Cin in {1, 3}, Cout = 32)

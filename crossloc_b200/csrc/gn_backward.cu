@@ -246,6 +246,80 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 4 : 3) gn_bwd_kernel(GnBwdDe
     }
 }
 
+// Backward of the 1x1 output head (fc3: C -> Co <= 8; networks.py:349) on the padded-flat activation it read:
+//   g_x[row][c] = sum_o g_sc[b][o][y][x] * W[o][c]          (fp32 PF source for the last stage's cl_gn_backward)
+//   g_W[o][c]  += sum over pixels of g_sc[b][o][y][x] * (x_hi + x_lo)[row][c]
+// One thread owns 8 channels (C / 8 divides the block); g_sc is the gradient of the pre-activation map, NCHW fp32.
+constexpr int kHeadBwdMaxCo = 8;
+
+template <int CO>
+__global__ void __launch_bounds__(kThreads) head_bwd_kernel(HeadBwdDesc d)
+{
+    __shared__ float red[kThreads][8 * 4 + 1];   // one (o-slice of 4) x 8 channels per pass
+    const int b = blockIdx.y;
+    const int chunks = d.C / 8;
+    const int chunk = threadIdx.x % chunks, pslot = threadIdx.x / chunks, pslots = kThreads / chunks;
+    const int c = chunk * 8;
+    const int Wp = d.W + 2;
+    const size_t plane = (size_t)(d.H + 2) * Wp;
+    const int hw = d.H * d.W;
+    float w[CO][8];
+    float acc[CO][8];
+#pragma unroll
+    for (int o = 0; o < CO; o++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            w[o][j] = o < d.Co ? d.weight[o * d.C + c + j] : 0.f;
+            acc[o][j] = 0.f;
+        }
+    for (int pix = blockIdx.x * pslots + pslot; pix < hw; pix += gridDim.x * pslots) {
+        const int y = pix / d.W, x = pix - y * d.W;
+        const size_t row = (size_t)b * plane + (size_t)(y + 1) * Wp + (x + 1);
+        const uint4 hq = __ldg(reinterpret_cast<const uint4*>(d.act + row * d.C + c));
+        const uint4 lq = __ldg(reinterpret_cast<const uint4*>(d.act + (row + (size_t)d.act_lo_rows) * d.C + c));
+        const __half* hh = reinterpret_cast<const __half*>(&hq);
+        const __half* ll = reinterpret_cast<const __half*>(&lq);
+        float xv[8], gx[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { xv[j] = __half2float(hh[j]) + __half2float(ll[j]); gx[j] = 0.f; }
+#pragma unroll
+        for (int o = 0; o < CO; o++) {
+            if (o < d.Co) {
+                const float g = __ldg(d.g_sc + ((size_t)b * d.Co + o) * hw + pix);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    gx[j] = fmaf(g, w[o][j], gx[j]);
+                    acc[o][j] = fmaf(g, xv[j], acc[o][j]);
+                }
+            }
+        }
+        float4* out = reinterpret_cast<float4*>(d.g_x + row * d.C + c);
+        out[0] = make_float4(gx[0], gx[1], gx[2], gx[3]);
+        out[1] = make_float4(gx[4], gx[5], gx[6], gx[7]);
+    }
+    // block reduction of the weight-gradient partials, four output channels per pass
+#pragma unroll
+    for (int o0 = 0; o0 < CO; o0 += 4) {
+        if (o0 >= d.Co) break;   // uniform across the block
+        __syncthreads();
+#pragma unroll
+        for (int oo = 0; oo < 4; oo++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) red[threadIdx.x][oo * 8 + j] = acc[o0 + oo][j];
+        __syncthreads();
+        if (pslot == 0) {
+            for (int oo = 0; oo < 4 && o0 + oo < d.Co; oo++) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float t = 0.f;
+                    for (int p = 0; p < pslots; p++) t += red[p * chunks + chunk][oo * 8 + j];
+                    atomicAdd(d.g_w + (size_t)(o0 + oo) * d.C + c + j, t);
+                }
+            }
+        }
+    }
+}
+
 const char* check(const GnBwdDesc& d)
 {
     if (d.C % 8 != 0 || d.C > 2048) return "gn_backward: C must be a multiple of 8 and at most 2048";
@@ -275,6 +349,24 @@ int grid_x(const GnBwdDesc& d, int blocks_per_sm)
 }
 
 }  // namespace
+
+const char* head_bwd_launch(const HeadBwdDesc& d, cudaStream_t stream)
+{
+    if (d.Co < 1 || d.Co > kHeadBwdMaxCo) return "head_backward: 1..8 output channels";
+    if (d.C % 8 != 0 || kThreads % (d.C / 8) != 0) return "head_backward: C / 8 must divide 256";
+    if (d.B <= 0 || d.B > 65535 || d.H <= 0 || d.W <= 0) return "head_backward: invalid sizes";
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int pslots = kThreads / (d.C / 8);
+    int bx = (d.H * d.W + pslots * 4 - 1) / (pslots * 4);
+    const int cap = (sms * 2) / d.B > 0 ? (sms * 2) / d.B : 1;     // one resident wave: every block ends with atomics
+    if (bx > cap) bx = cap;
+    if (d.Co <= 4) head_bwd_kernel<4><<<dim3(bx, d.B), kThreads, 0, stream>>>(d);
+    else head_bwd_kernel<8><<<dim3(bx, d.B), kThreads, 0, stream>>>(d);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
 
 const char* gn_bwd_reduce_launch(const GnBwdDesc& d, cudaStream_t stream)
 {

@@ -13,16 +13,16 @@ Here the whole network is ONE autograd node:
 
 Activations and gradients never leave the padded-flat layout between layers, so the NCHW <-> operand conversions of
 the per-layer path (crossloc_b200.train) disappear.  The stem's GroupNorm / ReLU backward runs on the same kernels from the
-raw conv1 output the forward keeps; its 864-entry weight gradient and the 4-channel head are left to stock torch ops.  Covers TransPoseNet / Network without MLR encoders or the full-size head;
+raw conv1 output the forward keeps (its 864-entry weight gradient is one cuDNN wgrad call), the 4-channel head has its own
+backward kernel (cl_head_backward).  Covers TransPoseNet / Network without MLR encoders or the full-size head;
 the other variants keep using the per-layer path.
 """
 import ctypes
 import os
 
 import torch
-import torch.nn.functional as F
 
-from . import _lib, layout
+from . import _lib
 from .cnn import CoordNetEngine, _nterms_for, _W8_LO_SCALE
 from .train import _i32, _pack
 
@@ -101,7 +101,7 @@ class TrainPlan:
         out = eng.forward(spec, image)
         # the tape points into workspace buffers the next forward overwrites: remember which forward a state belongs to
         state = {'tape': eng.tape, 'head_in': eng.head_in, 'stem_out': eng.stem_out, 'stem_rec': eng.stem_rec, 'spec': spec,
-                 'image': image,
+                 'image': image, 'out': out.detach(),
                  'geo3': eng.head_in.geo, 'generation': self._step + 1}
         eng.tape = None
         self._step += 1
@@ -214,23 +214,23 @@ class TrainPlan:
         geo3 = state['geo3']
         res = state['head_in']
 
-        # ---- head (1x1 C -> Co, mean offset, exp(clamp)): stock torch ops on the NCHW view of the last activation
+        # ---- head (1x1 C -> Co, mean offset, exp(clamp)): the derivative of the output maps on the small [B,Co,Hc,Wc] tensor
+        # in torch (d exp(clamp(s)) = out where the clamp is inactive), then cl_head_backward on the padded-flat activation
         hconv = head['conv']
         co, k_task = hconv.out_channels, head['num_task']
-        x = layout.from_pf(res.h16, geo3.B, geo3.H, geo3.W, 2)
-        with torch.enable_grad():
-            x.requires_grad_(True)
-            w = hconv.weight.detach().reshape(co, -1).requires_grad_(True)
-            b = hconv.bias.detach().requires_grad_(True)
-            sc = torch.einsum('bchw,oc->bohw', x, w) + b[None, :, None, None]
-            task = sc[:, :k_task] + head['mean'].to(dev)[None, :, None, None]
-            if co > k_task:
-                pos = torch.exp(F.hardtanh(sc[:, k_task:], min_val=head['clamp'][0], max_val=head['clamp'][1]))
-                task = torch.cat([task, pos], 1)
-            gx, gw, gb = torch.autograd.grad(task, (x, w, b), g_out.contiguous())
-        grads[id(hconv.weight)] = gw.reshape(hconv.weight.shape)
-        grads[id(hconv.bias)] = gb
-        g_pf = F.pad(gx, (1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(geo3.Mp, -1).contiguous()
+        g_sc = g_out.to(torch.float32).contiguous().clone()
+        if co > k_task:
+            pos = state['out'][:, k_task:]
+            lo = torch.exp(torch.tensor(head['clamp'][0], dtype=torch.float32, device=dev))
+            hi = torch.exp(torch.tensor(head['clamp'][1], dtype=torch.float32, device=dev))
+            g_sc[:, k_task:] = g_sc[:, k_task:] * pos * ((pos > lo) & (pos < hi))
+        w2d = hconv.weight.detach().reshape(co, -1).to(torch.float32).contiguous()
+        g_w = torch.zeros_like(w2d)
+        g_pf = torch.empty(geo3.Mp, w2d.size(1), dtype=torch.float32, device=dev)
+        _lib.check(lib.cl_head_backward(res.h16.data_ptr(), geo3.Mp, geo3.B, geo3.H, geo3.W, w2d.size(1), co, w2d.data_ptr(),
+                                        g_sc.data_ptr(), g_pf.data_ptr(), g_w.data_ptr(), stream))
+        grads[id(hconv.weight)] = g_w.reshape(hconv.weight.shape)
+        grads[id(hconv.bias)] = g_sc.sum((0, 2, 3))
         sources = {id(res): [_Src(g_pf, g_pf.size(1))]}
 
         # one zeroed buffer for every convolution's weight gradient (the kernels accumulate into OIHW views of it)

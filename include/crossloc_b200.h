@@ -135,6 +135,17 @@ int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch, const flo
                    float* d_raw_f32, void* cuda_stream);
 
 /*
+ * Backward of the 1x1 output head (fc3, networks.py:349) on the padded-flat activation it read (training step):
+ *   g_x[row][c] = sum_o g_sc[b][o][y][x] * weight[o][c]      fp32 PF [B*(H+2)*(W+2)][C], interior rows -- the gradient
+ *                                                             source of the last stage's cl_gn_backward
+ *   g_w[o][c]  += sum over pixels g_sc[b][o][y][x] * act[row][c]   (fp32 atomics, caller zeroes)
+ * g_sc is the gradient of the head's pre-activation output (NCHW fp32; the mean offset and exp(clamp) derivatives
+ * are applied by the caller on the small output map).  act: fp16 hi / lo planes act_lo_rows apart.  Co <= 8.
+ */
+int cl_head_backward(const void* act, int64_t act_lo_rows, int B, int H, int W, int C, int Co, const float* weight,
+                     const float* g_sc, float* g_x, float* g_w, void* cuda_stream);
+
+/*
  * Layout kernels of the training path (device pointers): NCHW fp32 tensors, as autograd hands them over, to and
  * from the operand layouts of cl_conv_igemm / cl_conv_wgrad_pf, and filter packing.  `scale` arguments are device
  * scalars (power-of-two factors computed on the GPU, no host synchronisation), NULL = 1.
