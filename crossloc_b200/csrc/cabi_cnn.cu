@@ -206,8 +206,8 @@ extern "C" int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch
                               const float* gamma, const float* beta, float eps, int relu_inner, int num_src,
                               const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
                               const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out,
-                              double* ab, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows, float* scale_out,
-                              double* dbias, float* d_raw_f32, void* cuda_stream)
+                              double* ab, int ab_C, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows,
+                              float* scale_out, double* dbias, float* d_raw_f32, void* cuda_stream)
 {
     static const char* kFn = "cl_gn_backward";
     NEED_DEV(raw); NEED_DEV(ab); NEED_DEV(gmax_bits);
@@ -223,7 +223,8 @@ extern "C" int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch
         d.src[i].stride = src_stride[i]; d.src[i].phased = src_phased[i];
         if (int rc = need_device(kFn, "src[i]", src[i])) return rc;
     }
-    d.mask_out = static_cast<const __half*>(mask_out); d.g_out = g_out; d.ab = ab;
+    d.mask_out = static_cast<const __half*>(mask_out); d.g_out = g_out; d.ab = ab; d.ab_C = ab_C;
+    if (ab_C && ab_C < C) return cl::fail(-1, "%s: ab_C=%d smaller than C=%d", kFn, ab_C, C);
     d.gmax_bits = static_cast<unsigned*>(gmax_bits); d.d_raw = static_cast<__half*>(d_raw); d.d_raw_lo_rows = d_raw_lo_rows;
     d.scale_out = scale_out; d.dbias = dbias; d.d_raw_f32 = d_raw_f32;
     if (d_raw_f32) NEED_DEV(d_raw_f32);

@@ -163,7 +163,8 @@ struct GnBwdDesc {
     GnBwdSrc src[3];
     const __half* mask_out; // pass 1, nullable: hi plane of the stage's merged output; the gradient passes where it is > 0
     float* g_out;           // pass 1, nullable: summed / masked gradient, fp32 PF [rows][C]
-    double* ab;             // [B][C][2]: sum dy, sum dy * xhat (pass 1 accumulates, pass 2 reads); caller zeroes
+    double* ab;             // [B][ab_C][2]: sum dy, sum dy * xhat (pass 1 accumulates, pass 2 reads); caller zeroes
+    int ab_C;               // channels per image in `ab` (0 = C): several stages can share one buffer, each at its own offset
     unsigned* gmax_bits;    // float bits of max |dy * gamma| * rstd (pass 1 atomicMax, pass 2 reads); caller zeroes
     __half* d_raw;          // pass 2: gradient of the raw convolution output, fp16 hi / lo PF planes x 2^k
     int64_t d_raw_lo_rows;

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 4 : 3) gn_bwd_kernel(GnBwdDe
     const int c = chunk * 8;
     const int Wp = d.W + 2;
     const size_t plane = (size_t)(d.H + 2) * Wp;
+    const int ab_C = d.ab_C ? d.ab_C : d.C;   // channels per image in the ab buffer (it may hold several stages side by side)
     Lane<UNI> t;
     load_lane<UNI>(d, b, c, t);
     const int nsrc = APPLY ? 1 : d.num_src;
@@ -130,8 +131,8 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 4 : 3) gn_bwd_kernel(GnBwdDe
             for (int j = 0; j < d.group_ch; j++) {
                 const int ch = g * d.group_ch + j;
                 const double ga = d.gamma[ch];
-                s1 += ga * d.ab[((size_t)b * d.C + ch) * 2];
-                s2 += ga * d.ab[((size_t)b * d.C + ch) * 2 + 1];
+                s1 += ga * d.ab[((size_t)b * ab_C + ch) * 2];
+                s2 += ga * d.ab[((size_t)b * ab_C + ch) * 2 + 1];
             }
             group_means[g] = make_float2((float)(s1 * inv_n), (float)(s2 * inv_n));
         }
@@ -228,8 +229,8 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 4 : 3) gn_bwd_kernel(GnBwdDe
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             if (!APPLY) {
-                atomicAdd(d.ab + ((size_t)b * d.C + c + j) * 2, (double)s1[j]);
-                atomicAdd(d.ab + ((size_t)b * d.C + c + j) * 2 + 1, (double)s2[j]);
+                atomicAdd(d.ab + ((size_t)b * ab_C + c + j) * 2, (double)s1[j]);
+                atomicAdd(d.ab + ((size_t)b * ab_C + c + j) * 2 + 1, (double)s2[j]);
             } else if (d.dbias) {
                 atomicAdd(d.dbias + c + j, (double)s1[j]);
             }

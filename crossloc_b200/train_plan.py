@@ -118,15 +118,22 @@ class TrainPlan:
             buf = self._pool[key] = torch.zeros(2 * geo.Mp, channels, dtype=torch.float16, device=device)
         return buf
 
-    def _gn_backward(self, lib, stream, geo, channels, rec, norm, relu_inner, srcs, mask, want_g, d_raw_f32=None):
-        """Both passes of cl_gn_backward for one stage; returns (d_raw, scale_out, ab, dbias, g_buf)."""
+    def _gn_backward(self, lib, stream, geo, channels, rec, norm, relu_inner, srcs, mask, want_g, d_raw_f32=None, acc=None):
+        """Both passes of cl_gn_backward for one stage; returns (d_raw, scale_out, ab, dbias, g_buf).
+        `acc` = (ab pointer, channels per image of the shared ab buffer, dbias view, two-double scratch view) places the
+        accumulators of this stage inside buffers shared by the whole backward pass (one fill, one reduction at the end)."""
         dev = rec['raw'].device
-        n_ab = geo.B * channels * 2
-        z = torch.zeros(n_ab + channels + 2, dtype=torch.float64, device=dev)   # one fill for all the accumulators
-        ab = z[:n_ab].view(geo.B, channels, 2)
-        dbias = z[n_ab:n_ab + channels]
-        gmax = z[n_ab + channels:n_ab + channels + 1].view(torch.int32)
-        scale_out = z[n_ab + channels + 1:].view(torch.float32)
+        if acc is None:
+            n_ab = geo.B * channels * 2
+            z = torch.zeros(n_ab + channels + 2, dtype=torch.float64, device=dev)   # one fill for all the accumulators
+            ab, ab_ptr, ab_C = z[:n_ab].view(geo.B, channels, 2), z.data_ptr(), 0
+            dbias = z[n_ab:n_ab + channels]
+            misc = z[n_ab + channels:]
+        else:
+            ab_ptr, ab_C, dbias, misc = acc
+            ab = None
+        gmax = misc[0:1].view(torch.int32)
+        scale_out = misc[1:2].view(torch.float32)
         g_buf = torch.empty(geo.Mp, channels, dtype=torch.float32, device=dev) if want_g else None
         d_raw = self._zeros_pf(geo, channels, dev)
         group_ch = 0 if norm is None else channels // norm.num_groups
@@ -143,7 +150,7 @@ class TrainPlan:
                 1 if relu_inner else 0, n, ptrs, sa, sb, _i32([s.stride for s in sources] + [0] * (3 - n)),
                 _i32([1 if s.phased else 0 for s in sources] + [0] * (3 - n)),
                 None if (mask is None or pass_id == 1) else mask.data_ptr(),
-                None if (g_buf is None or pass_id == 1) else g_buf.data_ptr(), ab.data_ptr(), gmax.data_ptr(),
+                None if (g_buf is None or pass_id == 1) else g_buf.data_ptr(), ab_ptr, ab_C, gmax.data_ptr(),
                 d_raw.data_ptr(), geo.Mp, scale_out.data_ptr(), dbias.data_ptr(),
                 None if (d_raw_f32 is None or pass_id == 0) else d_raw_f32.data_ptr(), stream))
 
@@ -242,6 +249,22 @@ class TrainPlan:
             r['gw'] = flat[offset:offset + n].view(r['pack'].weight.shape)
             offset += n
 
+        # shared accumulators of all stages: ab [B][sumC][2], dbias [sumC], two scratch doubles per stage -- one fill now, one
+        # reduction over the batch and one fp32 cast at the end instead of three small launches per stage
+        stages = [(e['conv'], e['norm']) for e in state['tape']] + \
+                 [(e['skip'], e['norm2']) for e in state['tape'] if e['skip'] is not None]
+        if state['stem_out'] is not None:
+            stages.append((state['stem_rec'], state['stem_rec']['norm']))
+        batch = geo3.B
+        sum_c = sum(32 if 'pack' not in r else r['pack'].cout for r, _ in stages)
+        zall = torch.zeros(batch * sum_c * 2 + sum_c + 2 * len(stages), dtype=torch.float64, device=dev)
+        z_ab, z_db, z_misc = zall[:batch * sum_c * 2], zall[batch * sum_c * 2:batch * sum_c * 2 + sum_c], zall[batch * sum_c * 2 + sum_c:]
+        offs, c_off = {}, 0
+        for i, (r, _) in enumerate(stages):
+            ch = 32 if 'pack' not in r else r['pack'].cout
+            offs[id(r)] = (z_ab.data_ptr() + c_off * 16, sum_c, z_db[c_off:c_off + ch], z_misc[2 * i:2 * i + 2], c_off, ch)
+            c_off += ch
+
         stem_out = state['stem_out']
         for e in reversed(state['tape']):
             rec, out = e['conv'], e['out']
@@ -250,9 +273,8 @@ class TrainPlan:
             merge = e['add_kind'] != 0
             mask = out.h16 if (merge and e['relu_outer']) else None
             want_g = merge or len(srcs) > 1
-            d_raw, scale_out, ab, dbias, g_buf = self._gn_backward(lib, stream, geo, channels, rec, e['norm'],
-                                                                   e['relu_inner'], srcs, mask, want_g)
-            self._param_grads(grads, rec, e['norm'], ab, dbias)
+            d_raw, scale_out, _, _, g_buf = self._gn_backward(lib, stream, geo, channels, rec, e['norm'], e['relu_inner'], srcs,
+                                                              mask, want_g, acc=offs[id(rec)][:4])
             if e['add_kind'] == 1:
                 sources.setdefault(id(e['res']), []).append(_Src(g_buf, channels))
             act = rec['act']
@@ -262,9 +284,8 @@ class TrainPlan:
             if e['add_kind'] == 2:
                 # skip branch: out = [relu](GroupNorm(skip_conv(res)) + main): its gradient is the merged gradient g_buf
                 srec = e['skip']
-                d_raw_s, scale_s, ab_s, dbias_s, _ = self._gn_backward(lib, stream, geo, channels, srec, e['norm2'], False,
-                                                                       [_Src(g_buf, channels)], None, False)
-                self._param_grads(grads, srec, e['norm2'], ab_s, dbias_s)
+                d_raw_s, scale_s, _, _, _ = self._gn_backward(lib, stream, geo, channels, srec, e['norm2'], False,
+                                                              [_Src(g_buf, channels)], None, False, acc=offs[id(srec)][:4])
                 src = self._conv_backward(lib, stream, srec, d_raw_s, scale_s, True, srec['gw'])
                 grads[id(srec['pack'].weight_param)] = srec['gw']
                 sources.setdefault(id(srec['act']), []).append(src)
@@ -277,27 +298,25 @@ class TrainPlan:
             rec = state['stem_rec']
             conv1, norm1, geo0 = rec['conv'], rec['norm'], rec['geo']
             d_f32 = torch.empty(geo0.Mp, 32, dtype=torch.float32, device=dev)
-            _, _, ab, dbias, _ = self._gn_backward(lib, stream, geo0, 32, rec, norm1, True, srcs, None, False, d_raw_f32=d_f32)
+            self._gn_backward(lib, stream, geo0, 32, rec, norm1, True, srcs, None, False, d_raw_f32=d_f32, acc=offs[id(rec)][:4])
             g_conv = torch.empty(geo0.B, 32, geo0.H, geo0.W, dtype=torch.float32, device=dev)
             _lib.check(lib.cl_pf_to_nchw(d_f32.data_ptr(), geo0.B, geo0.H, geo0.W, 32, g_conv.data_ptr(), 32, geo0.H, geo0.W, 1, 0,
                                          0, None, None, stream))
             grads[id(conv1.weight)] = torch.nn.grad.conv2d_weight(image, conv1.weight.shape, g_conv, padding=1)
-            grads[id(conv1.bias)] = dbias.to(torch.float32)
-            if norm1 is not None:
-                sums = ab.sum(0)
-                grads[id(norm1.bias)] = sums[:, 0].to(torch.float32)
-                grads[id(norm1.weight)] = sums[:, 1].to(torch.float32)
-        return grads
 
-    @staticmethod
-    def _param_grads(grads, rec, norm, ab, dbias):
-        pack = rec['pack']
-        if pack.bias_param is not None:
-            grads[id(pack.bias_param)] = dbias.to(torch.float32)
-        if norm is not None:
-            sums = ab.sum(0)
-            grads[id(norm.bias)] = sums[:, 0].to(torch.float32)
-            grads[id(norm.weight)] = sums[:, 1].to(torch.float32)
+        # ---- per-channel parameter gradients of every stage from the shared accumulators
+        ab_sum = z_ab.view(batch, sum_c, 2).sum(0).to(torch.float32)   # [sumC][2]: (d_beta, d_gamma)
+        db = z_db.to(torch.float32)
+        for r, norm in stages:
+            _, _, _, _, c0, ch = offs[id(r)]
+            conv = r['conv'] if 'pack' not in r else None
+            bias_param = conv.bias if conv is not None else r['pack'].bias_param
+            if bias_param is not None:
+                grads[id(bias_param)] = db[c0:c0 + ch]
+            if norm is not None:
+                grads[id(norm.bias)] = ab_sum[c0:c0 + ch, 0]
+                grads[id(norm.weight)] = ab_sum[c0:c0 + ch, 1]
+        return grads
 
 
 class _FusedStep(torch.autograd.Function):

@@ -124,6 +124,7 @@ int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const void* act, in
  * src[0] only and writes d_raw = gradient of the raw convolution output as fp16 hi / lo PF planes x 2^k
  * (scale_out = {2^k, 2^-k}, derived on the device), adding its per-channel sums to `dbias` (nullable).
  * d_gamma = sum_b ab[b][c][1], d_beta = sum_b ab[b][c][0].  group_ch = 0: no normalisation (vanilla Network).
+ * ab is indexed [b][ab_C][2] (ab_C = 0 means C): the stages of one backward pass can share a buffer, each at its offset.
  * Caller zeroes ab, gmax_bits, dbias; d_raw keeps zero border rows (only interior pixels are written).
  * d_raw_f32 (nullable): the same gradient, unscaled, as fp32 PF [rows][C] (the stem's weight gradient is left to torch).
  */
@@ -131,7 +132,7 @@ int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch, const flo
                    const float* gamma, const float* beta, float eps, int relu_inner, int num_src,
                    const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
                    const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out, double* ab,
-                   void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows, float* scale_out, double* dbias,
+                   int ab_C, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows, float* scale_out, double* dbias,
                    float* d_raw_f32, void* cuda_stream);
 
 /*
