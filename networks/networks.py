@@ -6,9 +6,10 @@ Same classes, constructor signatures, attributes and state-dict keys as
 checkpoints and the unchanged callers (utils/evaluation.py:106-116, test_single_task.py:347-366) keep working.
 What differs is what `forward` launches: on a CUDA tensor without autograd it runs the hand-written sm_100a
 kernels of crossloc_b200 (TMA + tcgen05 implicit-GEMM convolutions, fused GroupNorm statistics) instead of
-cuDNN/ATen.  `forward_reference` is the same network spelled with stock torch ops in fp32: it is the
-definition the parity tests compare against and the autograd path of `train_single_task.py` until the
-backward kernels exist.  There is no CPU execution of the native path.
+cuDNN/ATen; with autograd enabled (`train_single_task.py:262-299`) it runs the fused training plan
+(`crossloc_b200.train_plan`: one autograd node whose backward is GroupNorm / ReLU backward, data and weight
+gradient kernels).  `forward_reference` is the same network spelled with stock torch ops in fp32: the definition
+the parity tests compare against.  There is no CPU execution of the native path.
 """
 import os
 

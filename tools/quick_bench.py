@@ -1,5 +1,5 @@
-import sys, time, torch
-sys.path.insert(0, '/root/repo')
+import os, sys, time, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import networks.networks as nets
 from crossloc_b200.cnn import CoordNetEngine
 torch.manual_seed(2021)
