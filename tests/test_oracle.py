@@ -108,6 +108,26 @@ def test_tier1_reproduces_golden():
     _check_against(ref, out)
 
 
+@pytest.mark.parametrize('idx,kw', [
+    (100, {}), (101, {'outlier_ratio': 0.5}), (102, {'noise_sigma': 2.0}), (103, {'height': 200, 'width': 312}),
+    (104, {'outlier_ratio': 0.1, 'noise_sigma': 0.1}), (105, {'subsample': 16}), (106, {}), (107, {'outlier_ratio': 0.7}),
+])
+def test_tier2_matches_tier1_on_scenes_outside_the_fixture(idx, kw):
+    """The C restatement against the cv2-based one, live, on scenes the committed fixture does not contain: same winner,
+    same number of tries per hypothesis, same refinement inlier counts, same pose."""
+    s = synth.make_scene(idx, **kw)
+    h, w, sub = kw.get('height', 480), kw.get('width', 720), kw.get('subsample', 8)
+    args = (s['coords'], 24, 10., s['focal'], w / 2, h / 2, 100., 100., sub)
+    ref = tier1.forward_rgb(*args, seed=1305, image=idx)
+    out = tier2.forward_rgb(*args, seed=1305, image=idx)
+    assert int(ref['best']) == out['best']
+    assert (np.asarray(ref['tries']) == np.asarray(out['tries'])).all()
+    bad = score_mismatch(ref['scores'], out['scores'])
+    assert bad.sum() <= 2 and not bad[int(ref['best'])]
+    assert list(ref['refine_counts']) == list(out['refine_counts'])
+    assert np.abs(ref['pose'] - out['pose']).max() < 1e-4 * max(1.0, np.abs(ref['pose']).max())
+
+
 def test_ground_truth_map_gives_zero_error():
     """The authors' debug hook (test_single_task.py:361): GT coordinates in, ~0 pose error out."""
     s = synth.make_scene(7, noise_sigma=0.0, outlier_ratio=0.0)
