@@ -23,3 +23,17 @@ def test_reference_arm_prints_one_contract_line():
     base = line['cpu_baseline']
     assert base['kind'] == 'port' and base['cores'] >= 1 and base['value'] == line['value'] and 'frames' in base['sample']
     assert line['config']['workload'] == 'batch32_480x720_forward+dsac256'
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """The driver launches the reference arm like the native one (torchrun, N ranks): rank 0 alone works and prints."""
+    env = dict(os.environ, OMP_NUM_THREADS='2')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29631', os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
+           '--warmup', '0']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith('{')]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference' and line['n_gpus'] == 2 and line['value'] > 0
