@@ -92,3 +92,17 @@ def test_profile_summariser_steady_state(tmp_path):
                     'title', 'head_kernel'], check=True)
     text = out.read_text()
     assert '| **total** | 5 | 2.5 |' in text      # the launches after the first marker up to the last one, over two steps
+
+
+def test_precision_decision_by_cpu_emulation():
+    """tools/emulate_precision.py: rounding the convolution operands once (fp16 / TF32) sits at the 1e-3 parity bar, the
+    shipped fp16 + e4m3 scheme two orders below it, and block-scaled FP4 corrections in between."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import emulate_precision
+    errs = emulate_precision.run(32, 48, 1)
+    e = {k: v[0] for k, v in errs.items()}
+    assert e['fp16x3'] < 2e-6
+    assert e['fp16x3'] < e['fp16+fp8'] < 1e-4
+    assert e['fp16+fp8'] < e['fp16+fp4'] < 5e-4
+    assert e['fp16+fp4'] < e['fp16+fp8a'] and e['fp16+fp4'] < e['fp16+fp8w']
+    assert 3e-4 < e['fp16x1'] < 5e-3
