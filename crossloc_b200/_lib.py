@@ -22,6 +22,8 @@ SIGNATURES = {
         _c.c_void_p, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_int,
         _c.c_uint64, _c.c_uint32, _c.c_uint32, _c.c_int,
         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'cl_dsac_timing': (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'cl_release_workspaces': (_c.c_int, []),
     'cl_conv_igemm': (_c.c_int, [
         _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _i32p, _c.c_int,
         _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p,
@@ -62,6 +64,19 @@ SIGNATURES = {
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
         _c.c_void_p, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_float, _c.c_float,
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
+    # whole-network runtime (csrc/net.cu); the descriptor structures live in crossloc_b200/net.py
+    'cl_net_create': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    'cl_net_update': (_c.c_int, [_c.c_void_p]),
+    'cl_net_forward': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    'cl_net_forward_frames': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                         _c.c_void_p, _c.c_void_p]),
+    'cl_net_wait_fork': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    'cl_net_output_shape': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'cl_net_buffers': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                  _c.c_void_p]),
+    'cl_net_profile': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                  _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'cl_net_destroy': (None, [_c.c_void_p]),
 }
 
 _lib = None

@@ -23,6 +23,7 @@ UNITS = {
     'cabi.cu': [],
     'dsac.cu': ['--fmad=false'],
     'cabi_cnn.cu': [],
+    'net.cu': [],
     'conv_igemm.cu': [],
     'conv_wgrad_pf.cu': [],
     'cnn_pointwise.cu': [],

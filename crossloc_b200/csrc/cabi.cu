@@ -1,6 +1,9 @@
 // extern "C" entry points declared in include/crossloc_b200.h -- common part and the DSAC* solver.
 #include "../../include/crossloc_b200.h"
 
+#include <memory>
+#include <utility>
+
 #include "cabi_common.h"
 #include "dsac.h"
 
@@ -8,18 +11,42 @@ namespace cl {
 
 thread_local std::string g_last_error;
 
-Workspace& workspace_for_current_device()
+namespace {
+std::mutex g_ws_mutex;
+std::map<std::pair<int, cudaStream_t>, std::unique_ptr<Workspace>> g_workspaces;
+bool g_dsac_timing = false;
+}  // namespace
+
+Workspace& workspace_for(cudaStream_t stream)
 {
-    static Workspace ws[64];
     int dev = 0;
     cudaGetDevice(&dev);
-    return ws[dev & 63];
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    auto& slot = g_workspaces[std::make_pair(dev, stream)];
+    if (!slot) {
+        slot.reset(new Workspace);
+        slot->stream = stream;
+    }
+    return *slot;
 }
 
-std::mutex& api_mutex()
+void release_workspaces()
 {
-    static std::mutex m;
-    return m;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    for (auto it = g_workspaces.begin(); it != g_workspaces.end();) {
+        if (it->first.first == dev) {
+            {
+                std::lock_guard<std::mutex> use(it->second->mu);
+                it->second->release();
+            }
+            it = g_workspaces.erase(it);
+        } else {
+            ++it;
+        }
+    }
 }
 
 }  // namespace cl
@@ -43,9 +70,9 @@ extern "C" int cl_dsac_forward_rgb(const float* coords, int B, int Hc, int Wc, f
     if (max_tries == 0) return fail(-1, "cl_dsac_forward_rgb: max_tries must be >= 1");
     if (B == 0) return 0;
 
-    std::lock_guard<std::mutex> lock(api_mutex());
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-    Workspace& ws = workspace_for_current_device();
+    Workspace& ws = workspace_for(stream);   // intermediates are private to (device, stream): re-entrant across streams
+    std::lock_guard<std::mutex> lock(ws.mu);
     Stager st(ws, stream);
     const size_t n = (size_t)Hc * Wc;
 
@@ -67,7 +94,42 @@ extern "C" int cl_dsac_forward_rgb(const float* coords, int B, int Hc, int Wc, f
     CL_CUDA(ws.get("dsac.errs", (size_t)B * n * sizeof(float), &errs));
     a.errs = static_cast<float*>(errs);
 
-    CL_CUDA(dsac_forward_launch(a, stream));
+    cudaEvent_t* ev = nullptr;
+    if (g_dsac_timing) {
+        std::array<cudaEvent_t, 4> q{};
+        for (auto& e : q) CL_CUDA(cudaEventCreate(&e));
+        ws.timing_log.push_back(q);
+        ev = ws.timing_log.back().data();
+    }
+    CL_CUDA(dsac_forward_launch(a, stream, ev));
     CL_CUDA(st.finish());
+    return 0;
+}
+
+extern "C" int cl_dsac_timing(int enable, void* cuda_stream, float* ms, int* solves)
+{
+    using namespace cl;
+    if (ms) {
+        Workspace& ws = workspace_for(static_cast<cudaStream_t>(cuda_stream));
+        std::lock_guard<std::mutex> lock(ws.mu);
+        ms[0] = ms[1] = ms[2] = 0.f;
+        for (auto& q : ws.timing_log) {
+            CL_CUDA(cudaEventSynchronize(q[3]));
+            for (int i = 0; i < 3; i++) {
+                float t = 0.f;
+                CL_CUDA(cudaEventElapsedTime(&t, q[i], q[i + 1]));
+                ms[i] += t;
+            }
+        }
+        if (solves) *solves = (int)ws.timing_log.size();
+        ws.drop_timing();
+    }
+    g_dsac_timing = enable != 0;
+    return 0;
+}
+
+extern "C" int cl_release_workspaces(void)
+{
+    cl::release_workspaces();
     return 0;
 }

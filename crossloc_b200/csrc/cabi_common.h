@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -42,15 +43,24 @@ inline bool is_device_ptr(const void* p)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-// Named, growable device buffers owned by the library (one set per device).
+// Named, growable device buffers owned by the library: one set per (device, stream), so that calls issued on
+// different streams never share intermediates (two solves in flight on one device used to overwrite each other's
+// scores / hypotheses / error maps).  A buffer only ever grows; before it is replaced the owning stream is
+// synchronised, so no queued kernel can still be reading the old allocation.
 class Workspace {
 public:
+    cudaStream_t stream = nullptr;
+    std::mutex mu;                  // held for the duration of a C-ABI call using this workspace
+    std::vector<std::array<cudaEvent_t, 4>> timing_log;   // cl_dsac_timing: sample / score / refine boundaries per solve
+
     cudaError_t get(const std::string& name, size_t bytes, void** out)
     {
         Slot& s = slots_[name];
         if (s.cap < bytes) {
             if (s.ptr) {
-                cudaError_t e = cudaFree(s.ptr);
+                cudaError_t e = cudaStreamSynchronize(stream);
+                if (e != cudaSuccess) return e;
+                e = cudaFree(s.ptr);
                 if (e != cudaSuccess) return e;
                 s.ptr = nullptr;
                 s.cap = 0;
@@ -63,11 +73,18 @@ public:
         *out = s.ptr;
         return cudaSuccess;
     }
+    void drop_timing()
+    {
+        for (auto& q : timing_log)
+            for (cudaEvent_t e : q) cudaEventDestroy(e);
+        timing_log.clear();
+    }
     void release()
     {
         for (auto& kv : slots_)
             if (kv.second.ptr) cudaFree(kv.second.ptr);
         slots_.clear();
+        drop_timing();
     }
 
 private:
@@ -78,8 +95,10 @@ private:
     std::map<std::string, Slot> slots_;
 };
 
-Workspace& workspace_for_current_device();
-std::mutex& api_mutex();
+// the workspace of (current device, stream); created on first use
+Workspace& workspace_for(cudaStream_t stream);
+// frees every workspace of the current device (synchronises the device first)
+void release_workspaces();
 
 // Stages host inputs into the workspace and copies host outputs back after the launch.
 class Stager {

@@ -5,6 +5,7 @@
 // with t = 0 (hi) / 1 (lo) fp16 split term, ph = parity phase (P = 1, or 4 when the consumer is a
 // stride-2 convolution: ph = (y_in & 1) * 2 + (x_in & 1), (y, x) = (y_in / 2, x_in / 2)), zero borders.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -59,6 +60,18 @@ struct ConvIgemmParams {
 
 // returns nullptr on success, else a static error string
 const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream);
+
+// The same launch split in two: everything that depends only on shapes and pointers (tile schedule, the five TMA
+// tensor maps: ~10 us of driver calls) is prepared once and replayed (csrc/net.cu caches one plan per layer).
+struct alignas(64) ConvIgemmPlan {
+    CUtensorMap tmA, tmW, tmO, tmA8, tmW8;
+    ConvIgemmParams p;
+    size_t smem;
+    int grid, cluster;
+    int variant;            // bit 1: CTA-pair kernel, bit 0: 64-channel k-blocks
+};
+const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan);
+const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream);
 
 // ---------------------------------------------------------------- weight gradient on padded-flat operands
 // dW[tap][co][ci] += out_scale * sum over PF rows r of dY[r][co] * X[tap_phase][r + tap_shift][ci]; both operands

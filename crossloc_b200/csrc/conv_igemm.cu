@@ -692,7 +692,7 @@ bool make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 
 }  // namespace
 
-const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
+const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
 {
     if (d.Cin % 32 != 0) return "conv_igemm: Cin must be a multiple of 32";
     if (d.Cout % 64 != 0) return "conv_igemm: Cout must be a multiple of 64";
@@ -706,7 +706,8 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     const int BN = d.Cout % 256 == 0 ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
     const int nA = d.nterms == 1 ? 1 : 2;
 
-    ConvIgemmParams p{};
+    ConvIgemmParams& p = plan->p;
+    p = ConvIgemmParams{};
     p.num_taps = d.num_taps;
     for (int i = 0; i < d.num_taps; i++) p.tap_a_row[i] = d.tap_a_row[i];
     p.kblocks_per_tap = d.Cin / BK;
@@ -719,9 +720,11 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     p.Mp = d.Mp; p.Cout = d.Cout; p.BN = BN;
     p.tiles_m = (d.Mp + kBlockM - 1) / kBlockM;
     p.tiles_n = d.Cout / BN;
-    int dev = 0, sms = 148;
+    static int sms_cached[64] = {0};
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int& sms = sms_cached[dev & 63];
+    if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
     // d.cluster: 0 / 2 = CTA pairs (cta_group::2, default), 1 = single CTAs, 12 / 14 = single-CTA MMAs with the
     // weight tile TMA-multicast across clusters of 2 / 4 (kept for comparison)
     const bool pair = (d.cluster == 2 || (d.cluster == 0 && p.tiles_m >= 16)) && sms % 2 == 0 && BN % 32 == 0;
@@ -746,65 +749,86 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
     // folds the corrections with scale-input-d and needs one
     if (d.nterms == 2 && d.corr_scale != 1.0f / (float)(1 << kCorrShift)) return "conv_igemm: corr_scale must be 2^-14";
     p.accum_stages = (d.nterms == 2 && !pair ? 4 : 2) * BN <= (int)kTmemCols ? 2 : 1;
-    const size_t smem = (size_t)p.num_stages * p.stage_bytes + kEpilogueStagingBytes + 1024;
+    plan->smem = (size_t)p.num_stages * p.stage_bytes + kEpilogueStagingBytes + 1024;
 
-    CUtensorMap tmA, tmW, tmO;
-    if (!make_tensor_map(&tmA, d.act, (uint64_t)d.a_total_rows, (uint64_t)d.Cin, kBlockM, BK, 2))
+    if (!make_tensor_map(&plan->tmA, d.act, (uint64_t)d.a_total_rows, (uint64_t)d.Cin, kBlockM, BK, 2))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the activation matrix";
-    if (!make_tensor_map(&tmW, d.weights, (uint64_t)(d.nterms == 3 ? 2 : 1) * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, BK, 2))
+    if (!make_tensor_map(&plan->tmW, d.weights, (uint64_t)(d.nterms == 3 ? 2 : 1) * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, BK, 2))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the weight matrix";
-    if (!make_tensor_map(&tmO, d.raw, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 4))
+    if (!make_tensor_map(&plan->tmO, d.raw, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 4))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the output matrix";
-    CUtensorMap tmA8 = tmA, tmW8 = tmW;
+    plan->tmA8 = plan->tmA;
+    plan->tmW8 = plan->tmW;
     if (d.nterms == 2) {
         // the pair kernel streams the e4m3 planes in 128-byte rows (2 * BK channels per box)
         const int bk8 = pair ? 2 * BK : BK;
         if (pair && (d.Cin % 128 != 0)) return "conv_igemm: the fp16 + fp8 mode of the CTA-pair kernel needs Cin % 128 == 0";
-        if (!make_tensor_map(&tmA8, d.act8, (uint64_t)d.a8_total_rows, (uint64_t)d.Cin, kBlockM, bk8, 1))
+        if (!make_tensor_map(&plan->tmA8, d.act8, (uint64_t)d.a8_total_rows, (uint64_t)d.Cin, kBlockM, bk8, 1))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the e4m3 activation matrix";
-        if (!make_tensor_map(&tmW8, d.weights8, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, bk8, 1))
+        if (!make_tensor_map(&plan->tmW8, d.weights8, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, bk8, 1))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the e4m3 weight matrix";
     }
 
     const int num_super = p.super_m * p.tiles_n;
     int clusters = sms / cluster;
     if (clusters > num_super) clusters = num_super;
-    const int grid = clusters * cluster;
+    plan->grid = clusters * cluster;
+    plan->cluster = cluster;
+    plan->variant = (pair ? 2 : 0) + (BK == 64 ? 1 : 0);
+    return nullptr;
+}
 
+const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream)
+{
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(plan.grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = plan.smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.x = plan.cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
 
-    cudaError_t e;
-    if (pair && BK == 64) {
-        e = cudaFuncSetAttribute(conv_igemm_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cudaGetErrorString(e);
-        e = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<64>, tmA, tmW, tmO, tmA8, tmW8, p);
-    } else if (pair) {
-        e = cudaFuncSetAttribute(conv_igemm_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cudaGetErrorString(e);
-        e = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<32>, tmA, tmW, tmO, tmA8, tmW8, p);
-    } else if (BK == 64) {
-        e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cudaGetErrorString(e);
-        e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<64>, tmA, tmW, tmO, tmA8, tmW8, p);
-    } else {
-        e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cudaGetErrorString(e);
-        e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<32>, tmA, tmW, tmO, tmA8, tmW8, p);
+    // the opt-in shared-memory size is a per-function, per-device attribute: raise it once to the maximum any plan uses
+    static bool attr_set[64][4] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& done = attr_set[dev & 63][plan.variant];
+    const int max_smem = 227 * 1024;
+    cudaError_t e = cudaSuccess;
+    switch (plan.variant) {
+        case 3:
+            if (!done) e = cudaFuncSetAttribute(conv_igemm_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<64>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p);
+            break;
+        case 2:
+            if (!done) e = cudaFuncSetAttribute(conv_igemm_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<32>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p);
+            break;
+        case 1:
+            if (!done) e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<64>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p);
+            break;
+        default:
+            if (!done) e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<32>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p);
+            break;
     }
     if (e != cudaSuccess) return cudaGetErrorString(e);
+    done = true;
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
+{
+    ConvIgemmPlan plan;
+    if (const char* err = conv_igemm_prepare(d, &plan)) return err;
+    return conv_igemm_run(plan, stream);
 }
 
 }  // namespace cl

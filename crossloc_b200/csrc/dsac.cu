@@ -11,6 +11,7 @@
 //   pose2trans       :759-770 /
 // The per-hypothesis error maps the reference materialises (dsacstar.cpp:121) are never written:
 // only the winner's map is recomputed for the refinement.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "dsac.h"
@@ -22,7 +23,11 @@ namespace {
 
 constexpr int kSampleWarps = 4;
 constexpr int kScoreThreads = 256;
-constexpr int kRefineThreads = 512;
+constexpr int kRefineThreads = 256;   // per CTA; an image is refined by a cluster of 1..8 CTAs
+// Register cap of the refinement kernel: 256 threads x 136 registers fit on an SM NEXT TO a convolution CTA (256 threads
+// x 112 registers, ~200 KB of shared memory), so a solve running on its own stream shares SMs with the tensor-core-bound
+// convolutions of the following batch instead of waiting for whole SMs (an uncapped build needs 232 registers).
+constexpr int kRefineMaxRegs = 136;
 constexpr int kMaxRefSteps = 100;   // dsacstar.cpp:47
 constexpr double kProbEps = 1e-8;   // dsacstar_util.h:45
 
@@ -140,6 +145,59 @@ __device__ __forceinline__ void block_reduce_sum(double (&v)[NV], double* smem /
     for (int j = 0; j < NV; j++) v[j] = smem[kWarps * NV + j];
 }
 
+// Sum over every thread of the cluster working on one image.  Warp shuffles, one shared-memory slot per warp, then
+// every CTA publishes its NV partial sums and reads those of its peers through distributed shared memory in rank
+// order, so all CTAs (and all threads) end up with bit-identical totals and take the same control flow.  `part` is
+// double-buffered by the caller-held parity: one cluster barrier per reduction suffices (a CTA can only overwrite
+// buffer p after every peer has passed the barrier of the reduction in between, i.e. finished reading p).
+struct ClusterRed {
+    double* warp_part;   // [THREADS / 32][28]
+    double* part;        // [2][28], read by the peers
+    double* total;       // [28]
+    unsigned parity;
+};
+
+template <int NV>
+__device__ __forceinline__ void cluster_reduce_sum(double (&v)[NV], ClusterRed& cr)
+{
+    namespace cg = cooperative_groups;
+    constexpr int kWarps = kRefineThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) cr.warp_part[warp * 28 + j] = v[j];
+    }
+    __syncthreads();
+    double* mine = cr.part + (cr.parity & 1u) * 28;
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < kWarps; w++) s += cr.warp_part[w * 28 + threadIdx.x];
+        mine[threadIdx.x] = s;
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned nranks = cluster.num_blocks();
+    if (nranks > 1) {
+        cluster.sync();
+        if (threadIdx.x < NV) {
+            double s = 0;
+            for (unsigned r = 0; r < nranks; r++) s += cluster.map_shared_rank(mine, r)[threadIdx.x];
+            cr.total[threadIdx.x] = s;
+        }
+    } else {
+        __syncthreads();
+        if (threadIdx.x < NV) cr.total[threadIdx.x] = mine[threadIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; j++) v[j] = cr.total[j];
+    cr.parity++;
+}
+
 // Scoring: block (h, b) streams the image's planar X, Y, Z once (12 B per cell, coalesced), projects
 // in double like cv::projectPoints, and accumulates 1 - sigmoid(beta (err - thr)) in double.
 __global__ void __launch_bounds__(kScoreThreads) dsac_score_kernel(DsacArgs a)
@@ -179,7 +237,7 @@ struct LmSums {
 // inlier set { i : errs[i] < thr }, reduced over the block.  Every thread returns the same sums.
 template <bool WANT_J>
 __device__ void lm_accumulate(const double prm[6], const float* X, const float* errs, int n, int Wc, int S, float thr,
-                              double f, double cx, double cy, double* smem, LmSums& out)
+                              double f, double cx, double cy, ClusterRed& smem, LmSums& out, int first, int stride)
 {
     double R[9], M[9], RM[9];
     rodrigues(prm, R);
@@ -194,7 +252,7 @@ __device__ void lm_accumulate(const double prm[6], const float* X, const float* 
     double acc[NV];
 #pragma unroll
     for (int j = 0; j < NV; j++) acc[j] = 0;
-    for (int i = threadIdx.x; i < n; i += kRefineThreads) {
+    for (int i = first; i < n; i += stride) {
         if (!(errs[i] < thr)) continue;   // strict <, dsacstar_util.h:550
         const int yy = i / Wc, xx = i - yy * Wc;
         int px, py;
@@ -234,7 +292,7 @@ __device__ void lm_accumulate(const double prm[6], const float* X, const float* 
             for (int r2 = 0; r2 < 6; r2++) acc[21 + r2] += Ju[r2] * eu + Jv[r2] * ev;
         }
     }
-    block_reduce_sum<NV, kRefineThreads>(acc, smem);
+    cluster_reduce_sum<NV>(acc, smem);
     out.err = sqrt(acc[NV - 1]);
     if (WANT_J) {
         int k = 0;
@@ -262,20 +320,20 @@ __device__ bool lm_step(const LmSums& s, int lambdaLg10, const double prev[6], d
 // cvFindExtrinsicCameraParams2 -- at most 20 iterations, eps = FLT_EPSILON on the relative parameter
 // change, lambda = 10^k from k = -3, k+1 on a worse step (at most 16), k-1 on an accepted one.
 __device__ bool lm_solve(double prm[6], const float* X, const float* errs, int n, int Wc, int S, float thr, double f,
-                         double cx, double cy, double* smem)
+                         double cx, double cy, ClusterRed& smem, int first, int stride)
 {
     LmSums s;
     double prev[6];
     int lambdaLg10 = -3, iters = 0;
     double prevErr = DBL_MAX, errNorm;
     for (;;) {
-        lm_accumulate<true>(prm, X, errs, n, Wc, S, thr, f, cx, cy, smem, s);
+        lm_accumulate<true>(prm, X, errs, n, Wc, S, thr, f, cx, cy, smem, s, first, stride);
         for (int i = 0; i < 6; i++) prev[i] = prm[i];
         if (!lm_step(s, lambdaLg10, prev, prm)) return false;
         if (iters == 0) prevErr = s.err;
         for (;;) {
             LmSums e;
-            lm_accumulate<false>(prm, X, errs, n, Wc, S, thr, f, cx, cy, smem, e);
+            lm_accumulate<false>(prm, X, errs, n, Wc, S, thr, f, cx, cy, smem, e, first, stride);
             errNorm = e.err;
             if (errNorm > prevErr && ++lambdaLg10 <= 16) {
                 if (!lm_step(s, lambdaLg10, prev, prm)) return false;
@@ -294,12 +352,12 @@ __device__ bool lm_solve(double prm[6], const float* X, const float* errs, int n
 
 // Error map of one pose into errs[] + inlier count (block-uniform return value).
 __device__ int error_map(const double prm[6], const float* X, float* errs, int n, int Wc, int S, float f, float cx,
-                         float cy, float thr, float max_reproj, double* smem)
+                         float cy, float thr, float max_reproj, ClusterRed& smem, int first, int stride)
 {
     double R[9];
     rodrigues(prm, R);
     double cnt[1] = {0};
-    for (int i = threadIdx.x; i < n; i += kRefineThreads) {
+    for (int i = first; i < n; i += stride) {
         const int y = i / Wc, x = i - y * Wc;
         int px, py;
         cell_pixel(x, y, S, px, py);
@@ -307,15 +365,27 @@ __device__ int error_map(const double prm[6], const float* X, float* errs, int n
         errs[i] = e;
         if (e < thr) cnt[0] += 1;
     }
-    block_reduce_sum<1, kRefineThreads>(cnt, smem);
+    cluster_reduce_sum<1>(cnt, smem);
     return (int)cnt[0];
 }
 
-__global__ void __launch_bounds__(kRefineThreads) dsac_refine_kernel(DsacArgs a)
+// One CLUSTER of CTAs per image (cluster size chosen by the launcher from the map size: the fp64 normal equations
+// make a pass over the inliers throughput-bound on one SM's fp64 pipe -- 0.78 ms per image at 60 x 90 cells, 58 of
+// 81 ms per 32 frames at 480 x 720 with one 512-thread block).  Every thread owns the cells first, first + stride,
+// ... for the whole kernel, so the error map it reads back is always the one it wrote itself.
+__global__ void __maxnreg__(kRefineMaxRegs) dsac_refine_kernel(DsacArgs a)
 {
-    __shared__ double red[(kRefineThreads / 32 + 1) * 28];
+    namespace cg = cooperative_groups;
+    __shared__ double s_warp_part[(kRefineThreads / 32) * 28];
+    __shared__ double s_part[2 * 28];
+    __shared__ double s_total[28];
     __shared__ int s_best;
-    const int b = blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nranks = (int)cluster.num_blocks();
+    const int b = (int)blockIdx.x / nranks;
+    const int first = (int)cluster.block_rank() * kRefineThreads + (int)threadIdx.x;
+    const int stride = nranks * kRefineThreads;
+    ClusterRed red{s_warp_part, s_part, s_total, 0u};
     const int n = a.Hc * a.Wc;
     const float* X = a.coords + (size_t)b * 3 * n;
     float* errs = a.errs + (size_t)b * n;
@@ -334,7 +404,7 @@ __global__ void __launch_bounds__(kRefineThreads) dsac_refine_kernel(DsacArgs a)
             if (bestp < 0 || p > bestp) { bestp = p; best = h; }
         }
         s_best = best;
-        if (a.out_best) a.out_best[b] = best;
+        if (a.out_best && first == 0) a.out_best[b] = best;
     }
     __syncthreads();
     const int best = s_best;
@@ -346,23 +416,24 @@ __global__ void __launch_bounds__(kRefineThreads) dsac_refine_kernel(DsacArgs a)
 
     if (a.refine) {
         // refineHyp (dsacstar_util.h:522-597): refit to all inliers while the inlier count grows
-        int inliers = error_map(prm, X, errs, n, a.Wc, a.S, f, a.cx, a.cy, a.thr, a.max_reproj, red);
+        int inliers = error_map(prm, X, errs, n, a.Wc, a.S, f, a.cx, a.cy, a.thr, a.max_reproj, red, first, stride);
         int best_inliers = 4;
         for (int step = 0; step < kMaxRefSteps; step++) {
-            if (a.out_counts && threadIdx.x == 0) a.out_counts[(size_t)b * kMaxRefSteps + step] = inliers;
+            if (a.out_counts && first == 0) a.out_counts[(size_t)b * kMaxRefSteps + step] = inliers;
             if (inliers <= best_inliers) break;
             best_inliers = inliers;
             double upd[6];
 #pragma unroll
             for (int j = 0; j < 6; j++) upd[j] = prm[j];
-            if (!lm_solve(upd, X, errs, n, a.Wc, a.S, a.thr, (double)f, (double)a.cx, (double)a.cy, red)) break;
+            if (!lm_solve(upd, X, errs, n, a.Wc, a.S, a.thr, (double)f, (double)a.cx, (double)a.cy, red, first, stride)) break;
 #pragma unroll
             for (int j = 0; j < 6; j++) prm[j] = upd[j];
-            inliers = error_map(prm, X, errs, n, a.Wc, a.S, f, a.cx, a.cy, a.thr, a.max_reproj, red);
+            inliers = error_map(prm, X, errs, n, a.Wc, a.S, f, a.cx, a.cy, a.thr, a.max_reproj, red, first, stride);
         }
     }
 
-    if (threadIdx.x == 0) {
+    if (nranks > 1) cluster.sync();   // no CTA retires while a peer may still read its partial sums
+    if (first == 0) {
         // pose2trans (dsacstar_util.h:759-770): inverse of [R t; 0 1], row-major float (dsacstar.cpp:174-177)
         double R[9];
         rodrigues(prm, R);
@@ -380,7 +451,7 @@ __global__ void __launch_bounds__(kRefineThreads) dsac_refine_kernel(DsacArgs a)
 
 }  // namespace
 
-cudaError_t dsac_forward_launch(const DsacArgs& a, cudaStream_t stream)
+cudaError_t dsac_forward_launch(const DsacArgs& a, cudaStream_t stream, cudaEvent_t* ev)
 {
     if (a.B <= 0 || a.hyps <= 0) return cudaSuccess;
     if (a.out_counts) {
@@ -388,9 +459,32 @@ cudaError_t dsac_forward_launch(const DsacArgs& a, cudaStream_t stream)
         if (e != cudaSuccess) return e;
     }
     dim3 gs((a.hyps + kSampleWarps - 1) / kSampleWarps, a.B);
+    if (ev) cudaEventRecord(ev[0], stream);
     dsac_sample_kernel<<<gs, kSampleWarps * 32, 0, stream>>>(a);
+    if (ev) cudaEventRecord(ev[1], stream);
     dsac_score_kernel<<<dim3(a.hyps, a.B), kScoreThreads, 0, stream>>>(a);
-    dsac_refine_kernel<<<a.B, kRefineThreads, 0, stream>>>(a);
+    if (ev) cudaEventRecord(ev[2], stream);
+    {
+        // cells per thread stay around four or fewer up to 8 CTAs (the portable cluster limit)
+        const int n = a.Hc * a.Wc;
+        int cs = 1;
+        while (cs < 8 && n > cs * kRefineThreads * 3) cs *= 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(a.B * cs));
+        cfg.blockDim = dim3(kRefineThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, dsac_refine_kernel, a);
+        if (e != cudaSuccess) return e;
+    }
+    if (ev) cudaEventRecord(ev[3], stream);
     return cudaGetLastError();
 }
 

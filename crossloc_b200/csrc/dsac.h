@@ -29,6 +29,7 @@ struct DsacArgs {
     double* out_rt;         // nullable [B, 6] refined rvec, tvec
 };
 
-cudaError_t dsac_forward_launch(const DsacArgs& a, cudaStream_t stream);
+// ev: nullable [4] events recorded before sample, score, refine and after refine (cl_dsac_timing)
+cudaError_t dsac_forward_launch(const DsacArgs& a, cudaStream_t stream, cudaEvent_t* ev = nullptr);
 
 }  // namespace cl

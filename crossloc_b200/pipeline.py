@@ -33,24 +33,65 @@ def frames_to_network_input(frames_u8, mean=None, std=None, out=None):
 
 
 class Localizer:
-    def __init__(self, network, hyps=64, threshold=10.0, alpha=100.0, max_reproj=100.0, seed=1305, device=None):
+    """Network + solver for batches of frames.
+
+    Stream plan.  The CNN runs on the caller's stream; the pose solve (sample / score / refine: fp64 CUDA-core kernels,
+    ~1 ms per 32 frames) runs on `solver_stream`.  With overlap=True the solve of batch k is DEFERRED: it is enqueued
+    right after the CNN of batch k+1 and starts when that CNN enters its tensor-core-bound residual blocks
+    (cl_net_wait_fork), where its blocks co-reside with the convolution CTAs (register / shared-memory budgets are
+    chosen for that, csrc/dsac.cu) instead of delaying the stem of batch k+1.  `flush()` launches a solve that is still
+    deferred (end of a sequence)."""
+
+    def __init__(self, network, hyps=64, threshold=10.0, alpha=100.0, max_reproj=100.0, seed=1305, device=None,
+                 defer_solve=True):
         self.net = network
         self.hyps, self.threshold, self.alpha, self.max_reproj, self.seed = hyps, threshold, alpha, max_reproj, seed
         self.device = torch.device(device if device is not None else 'cuda')
         self.subsample = int(getattr(network, 'OUTPUT_SUBSAMPLE', 8))
         self.num_task = int(getattr(network, 'num_task_channel', 3))
         self._copy_stream = torch.cuda.Stream(self.device)
-        # the pose solver runs on its own stream: its three small kernels (2 ms, one of them a 32-block serial
-        # chain) overlap the convolutions of the next batch instead of idling most of the chip
         self.solver_stream = torch.cuda.Stream(self.device)
-        self.solver_done = None   # event recorded after the last solve; wait on it before reading poses
+        self.solver_done = None   # event recorded after the last LAUNCHED solve; wait on it before reading poses
+        self.defer_solve = defer_solve
+        self.after_solve = None   # optional callable(pose) run on the solver stream right behind every solve (pose gather)
+        self._deferred = None
         self._slots = [None, None]
         self._turn = 0
         self._pending = []
         self.kernel_launches = 0
+        self.solver_launches = 0
+
+    # ------------------------------------------------------------------ solver scheduling
+    def _launch_solve(self, job, wait_fork):
+        coords, out_pose, focal, w, h, image_base, ready, done, extra = job
+        with torch.cuda.stream(self.solver_stream):
+            self.solver_stream.wait_event(ready)
+            if wait_fork:
+                rt = getattr(self.net, '_runtime', None)
+                if rt is not None:
+                    rt.wait_fork(self.solver_stream)
+            for t in (coords, out_pose) + ((focal,) if torch.is_tensor(focal) and focal.is_cuda else ()):
+                t.record_stream(self.solver_stream)
+            dsac.forward_rgb_batch(coords, out_pose, self.hyps, self.threshold, focal, w / 2, h / 2, self.alpha,
+                                   self.max_reproj, self.subsample, seed=self.seed, image_base=image_base)
+            self.solver_launches += 3
+            if self.after_solve is not None:
+                self.after_solve(out_pose)
+            if extra is not None:
+                extra()
+            done.record(self.solver_stream)
+        self.solver_done = done
+
+    def flush(self):
+        """Launch the solve that is still deferred (if any); returns the event that marks the last solve's completion."""
+        if self._deferred is not None:
+            job, self._deferred = self._deferred, None
+            self._launch_solve(job, wait_fork=False)
+        return self.solver_done
 
     # ------------------------------------------------------------------ device-resident entry
-    def localize_device(self, images, focal, coord_offset=None, image_base=0, out_pose=None, debug=False, overlap=False):
+    def localize_device(self, images, focal, coord_offset=None, image_base=0, out_pose=None, debug=False, overlap=False,
+                        _extra=None, _done=None):
         """images [B,C,H,W] fp32 CUDA, focal float or [B]; returns poses [B,4,4] fp32 CUDA (camera-to-world).
 
         `coord_offset` ([B,3,Hc,Wc], optional) is added to the regressed coordinates before the solve: with
@@ -58,13 +99,20 @@ class Localizer:
         it into a consistent scene the same way the decoder's `mean` buffer offsets it.
 
         overlap=False: the poses are ready in the caller's stream on return (stream-ordered).
-        overlap=True: the solve is left running on `self.solver_stream`; wait on `self.solver_done` (or keep
-        working on that stream) before touching the poses.  The caller's stream is free for the next batch.
+        overlap=True: the solve runs on `self.solver_stream`, possibly deferred until the next call; call `flush()`
+        and wait on the returned event (or keep working on that stream) before touching the poses.
         """
         b, _, h, w = images.shape
         main = torch.cuda.current_stream(images.device)
+        dbg = None
         with torch.no_grad():
             pred = self.net(images)
+            self.kernel_launches = sum(e.launches for e in (getattr(self.net, '_engine', None), getattr(self.net, '_runtime', None))
+                                       if e is not None)
+            # the CNN of THIS batch is queued: the previous batch's deferred solve goes behind its fork point
+            if self._deferred is not None:
+                job, self._deferred = self._deferred, None
+                self._launch_solve(job, wait_fork=True)
             coords = pred[:, :self.num_task]
             if coord_offset is not None:
                 coords = coords + coord_offset
@@ -73,20 +121,28 @@ class Localizer:
                 out_pose = torch.empty(b, 4, 4, dtype=torch.float32, device=images.device)
             ready = torch.cuda.Event()
             ready.record(main)
-            with torch.cuda.stream(self.solver_stream):
-                self.solver_stream.wait_event(ready)
-                for t in (coords, out_pose) + ((focal,) if torch.is_tensor(focal) and focal.is_cuda else ()):
-                    t.record_stream(self.solver_stream)
-                dbg = dsac.forward_rgb_batch(coords, out_pose, self.hyps, self.threshold, focal, w / 2, h / 2,
-                                             self.alpha, self.max_reproj, self.subsample, seed=self.seed,
-                                             image_base=image_base, debug=debug)
-                self.solver_done = torch.cuda.Event()
-                self.solver_done.record(self.solver_stream)
-            if not overlap:
-                main.wait_event(self.solver_done)
-        engine = getattr(self.net, '_engine', None)
-        self.kernel_launches = (engine.launches if engine is not None else 0)
-        return (out_pose, dbg) if debug else out_pose
+            done = _done if _done is not None else torch.cuda.Event()
+            if debug:
+                with torch.cuda.stream(self.solver_stream):
+                    self.solver_stream.wait_event(ready)
+                    for t in (coords, out_pose) + ((focal,) if torch.is_tensor(focal) and focal.is_cuda else ()):
+                        t.record_stream(self.solver_stream)
+                    dbg = dsac.forward_rgb_batch(coords, out_pose, self.hyps, self.threshold, focal, w / 2, h / 2,
+                                                 self.alpha, self.max_reproj, self.subsample, seed=self.seed,
+                                                 image_base=image_base, debug=True)
+                    self.solver_launches += 3
+                    done.record(self.solver_stream)
+                self.solver_done = done
+                main.wait_event(done)
+                return out_pose, dbg
+            job = (coords, out_pose, focal, w, h, image_base, ready, done, _extra)
+            if overlap and self.defer_solve:
+                self._deferred = job
+            else:
+                self._launch_solve(job, wait_fork=False)
+                if not overlap:
+                    main.wait_event(self.solver_done)
+        return out_pose
 
     # ------------------------------------------------------------------ host entry, pipelined
     def submit(self, images_host, focal, coord_offset=None, image_base=0):
@@ -117,18 +173,22 @@ class Localizer:
         frames = st['images']
         if frames.dtype == torch.uint8:
             st['frames_f32'] = frames = frames_to_network_input(frames, out=st.get('frames_f32'))
-        self.localize_device(frames, focal, coord_offset, image_base, out_pose=st['pose_dev'], overlap=True)
+
+        def copy_back(st=st):   # poses leave on the solver stream, right behind their solve
+            st['pose_host'].copy_(st['pose_dev'], non_blocking=True)
+
+        self.localize_device(frames, focal, coord_offset, image_base, out_pose=st['pose_dev'], overlap=True,
+                             _extra=copy_back, _done=st['done'])
         st['free'] = torch.cuda.Event()
         st['free'].record(compute)          # the network has consumed the device frames
-        with torch.cuda.stream(self.solver_stream):   # poses leave on the solver stream, behind the solve
-            st['pose_host'].copy_(st['pose_dev'], non_blocking=True)
-            st['done'].record(self.solver_stream)
         self._pending.append(st)
         return st
 
     def result(self):
         """Poses of the oldest submitted batch (host tensor, valid until its slot is reused two submits later)."""
         st = self._pending.pop(0)
+        if self._deferred is not None and self._deferred[7] is st['done']:
+            self.flush()   # nothing was submitted behind it: launch its solve now
         st['done'].synchronize()
         return st['pose_host']
 

@@ -62,6 +62,19 @@ int cl_dsac_forward_rgb(const float* coords, int B, int Hc, int Wc, float* out_p
                         int32_t* out_tries, int32_t* out_counts, double* out_rt, void* cuda_stream);
 
 /*
+ * Re-entrancy.  Intermediates of cl_dsac_forward_rgb (hypotheses, scores, error maps, staged host buffers) live in a
+ * workspace private to (current device, cuda_stream): calls on different streams may be in flight together, calls
+ * on one stream are serialised by the library.  Buffers grow on demand (the stream is synchronised before an old
+ * allocation is replaced) and are kept until cl_release_workspaces(), which frees those of the current device.
+ *
+ * cl_dsac_timing(enable, stream, ms, solves): enable != 0 makes later solves record CUDA events between their kernels;
+ * with ms != NULL it first returns the device milliseconds {sample, score, refine} summed over the `solves` timed
+ * solves issued on `stream` since the last read, and clears that record.
+ */
+int cl_dsac_timing(int enable, void* cuda_stream, float* ms, int* solves);
+int cl_release_workspaces(void);
+
+/*
  * ---- Scene-coordinate CNN operators ---------------------------------------------------------------
  * These replace the cuDNN / ATen kernels stock PyTorch launches for the reference network
  * (/root/reference/networks/networks.py:175-256 encoder, :276-360 decoder, :43-130 vanilla Network).
@@ -234,6 +247,89 @@ int cl_duc_head_forward(const float* raw, int B, int Hc, int Wc, int C, int Co, 
  */
 int cl_frames_to_nchw(const uint8_t* frames, int B, int H, int W, int C, const float* mean, const float* stdv, float* out,
                       void* cuda_stream);
+
+/*
+ * ---- Whole-network runtime -------------------------------------------------------------------------------
+ * `network(image)` of the reference's evaluation loop (/root/reference/test_single_task.py:347; the module is built
+ * by utils/evaluation.py:106-116 as networks.TransPoseNet / Network, /root/reference/networks/networks.py:363-502,
+ * :43-130) as ONE call: cl_net_create() takes the module's layer table (state-dict tensors as plain pointers, host or
+ * device), packs the filters for the tensor cores and owns every workspace; cl_net_forward() runs stem -> strided
+ * ladder -> residual blocks -> head for a batch of frames.  The layer plan of a (B, H, W), its TMA tensor maps and
+ * buffers are built on first use, cached (three sizes) and replayed as a CUDA graph.
+ *
+ * A handle is bound to the device that was current at creation and serves one forward at a time (calls on one handle
+ * are serialised by an internal lock; use one handle per concurrent stream).  Different handles are independent.
+ */
+#define CL_NET_ABI_VERSION 1
+#define CL_NET_MAX_BLOCK_CONVS 4
+#define CL_BLOCK_RESIDUAL 0       /* res = [relu](res + chain(res))                       networks.py:236-240, 251-254 */
+#define CL_BLOCK_RESIDUAL_SKIP 1  /* res = [relu](skip_norm(skip(res)) + chain(res))      networks.py:242-249          */
+#define CL_BLOCK_PLAIN 2          /* res = chain(res) (fc1, fc2)                          networks.py:342-343          */
+
+typedef struct cl_net cl_net;
+
+typedef struct cl_net_layer {     /* one nn.Conv2d [+ nn.GroupNorm] [+ ReLU] */
+    int32_t cin, cout, ksize, stride;   /* 3x3 (padding 1) or 1x1, stride 1 or 2 */
+    const float* weight;          /* OIHW fp32 (the state-dict tensor) */
+    const float* bias;            /* [cout] or NULL */
+    int32_t gn_groups;            /* 0: no GroupNorm after this convolution */
+    const float* gn_weight;       /* [cout] */
+    const float* gn_bias;         /* [cout] */
+    float gn_eps;
+} cl_net_layer;
+
+typedef struct cl_net_block {
+    int32_t kind;                 /* CL_BLOCK_* */
+    int32_t n_convs;
+    int32_t convs[CL_NET_MAX_BLOCK_CONVS];   /* indices into the layer table, in execution order */
+    int32_t skip;                 /* CL_BLOCK_RESIDUAL_SKIP: the 1x1 skip convolution (+ its GroupNorm) */
+} cl_net_block;
+
+typedef struct cl_net_desc {
+    int32_t abi_version;          /* CL_NET_ABI_VERSION */
+    int32_t precision;            /* 1 = one fp16 pass (misses the 1e-3 bar), 2 = fp16 + e4m3 corrections (default), 3 = fp16x3 */
+    int32_t relu_after_add;       /* 1: TransPoseNet (ReLU after every residual add), 0: vanilla Network */
+    int32_t n_layers;
+    const cl_net_layer* layers;
+    int32_t stem[4];              /* conv1 .. conv4 (3x3; strides 1, 2, 2, 2) */
+    int32_t n_blocks;
+    const cl_net_block* blocks;
+    int32_t head_layer;           /* fc3: 1x1, at most 8 output channels */
+    const float* head_mean;       /* [num_task] added to the task channels */
+    int32_t num_task;             /* output channels >= num_task get exp(clamp(x, clamp_lo, clamp_hi)) */
+    float clamp_lo, clamp_hi;
+    int32_t duc_layer;            /* full-size variant: the DUC 3x3 convolution (networks.py:259-273), else -1 */
+    int32_t duc_rate;             /* PixelShuffle factor (8) */
+} cl_net_desc;
+
+int cl_net_create(const cl_net_desc* desc, cl_net** out);
+/* Re-reads every parameter tensor named at creation (they must still be alive at the same addresses) and repacks the
+ * filters: call after load_state_dict() / an optimizer step.  Plans and graphs stay valid. */
+int cl_net_update(cl_net* net);
+/* image: fp32 NCHW [B][Cin][H][W], host or device.  out: fp32 NCHW [B][Co][Ho][Wo] (cl_net_output_shape), host or
+ * device; NULL leaves the result in the plan's output buffer (cl_net_buffers).  Stream-ordered; synchronises only when
+ * `out` is host memory. */
+int cl_net_forward(cl_net* net, const float* image, int B, int H, int W, float* out, void* cuda_stream);
+/* Same for uint8 HWC frames [B][H][W][Cin] (what the decoders deliver; a quarter of the copy): the device applies
+ * torchvision's ToTensor [+ Normalize(mean, std), both [Cin] or both NULL] bit for bit (dataloader.py:189-212). */
+int cl_net_forward_frames(cl_net* net, const uint8_t* frames, int B, int H, int W, const float* mean, const float* stdv,
+                          float* out, void* cuda_stream);
+/* Makes `cuda_stream` wait until the most recently enqueued forward of this handle has finished its stem and strided
+ * ladder and enters the tensor-core-bound residual blocks: work queued on that stream afterwards (the previous batch's
+ * pose solve: fp64 CUDA-core kernels) then shares the SMs with convolutions that leave the CUDA cores idle. */
+int cl_net_wait_fork(cl_net* net, void* cuda_stream);
+int cl_net_output_shape(cl_net* net, int B, int H, int W, int* out_c, int* out_h, int* out_w);
+/* Plan-owned device buffers of a (B, H, W): a caller may fill `in_f32` / `in_u8` itself and pass that pointer to the
+ * forward call (no staging copy), and read the result from `out_buf`.  `launches` = kernels of one forward. */
+int cl_net_buffers(cl_net* net, int B, int H, int W, float** in_f32, uint8_t** in_u8, float** out_buf, int* launches);
+/* Per-op device times.  enable = 1 switches the handle to eager launches with a CUDA event between ops (no graph);
+ * a later call with tables returns, for the plan of (B, H, W), the op list (kinds: 0 memset, 1 stem, 2 convolution,
+ * 3 GroupNorm apply, 4 head, 5 full-size head, 6 statistics; labels [n][4]: convolution cin, cout, ksize, stride /
+ * apply channels, output phases, merge kind), the algorithmic FLOPs per launch and the milliseconds summed over the
+ * `forwards` recorded passes, then clears the record.  Returns the number of ops (negative on error). */
+int cl_net_profile(cl_net* net, int enable, int B, int H, int W, int max_ops, int32_t* kinds, int32_t* labels,
+                   double* flops, float* ms, int* forwards);
+void cl_net_destroy(cl_net* net);
 
 #ifdef __cplusplus
 }

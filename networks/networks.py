@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from crossloc_b200 import net as native_net
 from crossloc_b200 import train as native_train
 from crossloc_b200 import train_plan
 from crossloc_b200.cnn import CoordNetEngine
@@ -57,6 +58,18 @@ def _run_block(block, x, conv):
     return x
 
 
+def _run_native(module, spec, inputs):
+    """Inference on the native kernels: the C++ runtime (cl_net_forward: cached plan, CUDA graph) for every plan it covers,
+    else -- or with CROSSLOC_B200_ENGINE=python -- the Python plan of crossloc_b200.cnn over the same kernels."""
+    if native_net.ENGINE == 'native' and native_net.supported(spec):
+        if module._runtime is None:
+            module._runtime = native_net.NetRuntime()
+        return module._runtime.forward(spec, inputs)
+    if module._engine is None:
+        module._engine = CoordNetEngine()
+    return module._engine.forward(spec, inputs)
+
+
 def _native_ok(module, x):
     if not x.is_cuda:
         raise RuntimeError('crossloc_b200: forward() needs a CUDA tensor -- the native path has no CPU fallback '
@@ -93,6 +106,7 @@ class Network(nn.Module):
         self.register_buffer('mean', mean.clone())
         self.tiny = tiny
         self._engine = None
+        self._runtime = None
 
     def _spec(self):
         names = ['conv1', 'conv2', 'conv3', 'conv4', 'res1_conv1', 'res1_conv2', 'res1_conv3', 'res2_conv1',
@@ -148,9 +162,7 @@ class Network(nn.Module):
     def forward(self, inputs):
         if not _native_ok(self, inputs):
             return self.forward_train(inputs)
-        if self._engine is None:
-            self._engine = CoordNetEngine()
-        return self._engine.forward(self._spec(), inputs)
+        return _run_native(self, self._spec(), inputs)
 
 
 class TransPoseNetEncoder(nn.Module):
@@ -189,6 +201,7 @@ class TransPoseNetEncoder(nn.Module):
         self.enc_add_res_block_ls = [_res_block(tiny, g) for _ in range(enc_add_res_block)]
         for i, block in enumerate(self.enc_add_res_block_ls):
             self.add_module('enc_add_res_block{:d}'.format(i + 1), block)
+        self._engine = None
 
     def plan(self, prefix):
         """(layers, blocks, roles) of this encoder for the native engine; names are state-dict keys under `prefix`."""
@@ -230,8 +243,15 @@ class TransPoseNetEncoder(nn.Module):
         return res
 
     def forward(self, inputs):
-        # the encoder alone (used by the reference's MLR variants) has no native plan yet: plain torch
-        return self.forward_reference(inputs)
+        """The encoder on its own (the reference calls it per MLR branch, networks.py:484-488): the native plan up to the
+        residual stream, returned as an NCHW fp32 activation.  With autograd enabled: native convolutions per layer."""
+        if not _native_ok(self, inputs):
+            return self.forward_reference(inputs, conv=native_train.conv2d)
+        if self._engine is None:
+            self._engine = CoordNetEngine()
+        layers, blocks, roles = self.plan('')
+        return self._engine.forward({'group_norm': True, 'layers': layers, 'blocks': blocks, 'roles': roles,
+                                     'output': 'activation'}, inputs)
 
 
 class DenseUpsamplingConvolution(nn.Module):
@@ -284,6 +304,7 @@ class TransPoseNetDecoder(nn.Module):
             self.fc3 = nn.Conv2d(co, co, 1, 1, 0)
         else:
             self.fc3 = nn.Conv2d(c5, co, 1, 1, 0)
+        self._engine = None
 
     def plan(self, prefix):
         layers, blocks = [], []
@@ -326,7 +347,19 @@ class TransPoseNetDecoder(nn.Module):
         return torch.cat([task, pos], dim=1)
 
     def forward(self, inputs, up_height=None, up_width=None):
-        return self.forward_reference(inputs, up_height, up_width)
+        """The decoder on its own (networks.py:319-360) on an NCHW activation: the native plan from the residual stream
+        to the head.  With autograd enabled: native convolutions per layer."""
+        if not _native_ok(self, inputs):
+            return self.forward_reference(inputs, up_height, up_width, conv=native_train.conv2d)
+        if self._engine is None:
+            self._engine = CoordNetEngine()
+        layers, blocks, head = self.plan('')
+        if 'duc' in head:
+            if up_height is None or up_width is None:
+                raise RuntimeError('crossloc_b200: the full-size decoder needs up_height / up_width (networks.py:344-347)')
+            head['duc']['size'] = (int(up_height), int(up_width))
+        return self._engine.forward({'group_norm': True, 'layers': layers, 'blocks': blocks, 'head': head,
+                                     'input': 'activation'}, inputs)
 
 
 class TransPoseNet(nn.Module):
@@ -378,6 +411,7 @@ class TransPoseNet(nn.Module):
                                            num_gn_channel, full_size_output)
         self.decoder_ls = [self.decoder]
         self._engine = None
+        self._runtime = None
 
         count = sum(p.numel() for p in self.parameters() if p.requires_grad)
         safe_printout('Initialized TransPoseNet (crossloc_b200): tiny {}, grayscale {}, fullsize {}, #MLR {:d}, '
@@ -466,11 +500,22 @@ class TransPoseNet(nn.Module):
     def forward(self, inputs):
         if not _native_ok(self, inputs):
             return self.forward_train(inputs)
-        if self._engine is None:
-            self._engine = CoordNetEngine()
         if self.num_mlr != 0:
+            if self._engine is None:
+                self._engine = CoordNetEngine()
             return self._forward_mlr(inputs)
-        return self._engine.forward(self._spec(inputs), inputs)
+        return _run_native(self, self._spec(inputs), inputs)
+
+    def forward_frames(self, frames_u8, mean=None, std=None):
+        """uint8 HWC frames [B, H, W, C] (host or CUDA) -> network output: the host-to-device copy moves a quarter of the
+        bytes and ToTensor [+ Normalize] run on the device (cl_net_forward_frames), bit-identical to torchvision."""
+        if self.num_mlr != 0:
+            raise RuntimeError('crossloc_b200: forward_frames covers the single-encoder network')
+        if self._runtime is None:
+            self._runtime = native_net.NetRuntime()
+        b, h, w, _ = frames_u8.shape
+        spec = self._spec(torch.empty(0, 3, h, w))
+        return self._runtime.forward_frames(spec, frames_u8, mean, std)
 
 
 class ProjHead(nn.Module):

@@ -37,3 +37,14 @@ def test_reference_arm_under_torchrun_prints_once():
     assert len(lines) == 1, out.stdout
     line = json.loads(lines[0])
     assert line['impl'] == 'reference' and line['n_gpus'] == 2 and line['value'] > 0
+
+
+def test_both_arms_describe_the_same_config():
+    """`config` is built by one function for both arms, so the driver's same-config check holds by construction."""
+    import argparse
+    import bench
+    args = argparse.Namespace(batch=32, hyps=256)
+    cfg = bench.config_of(args, 1)
+    assert cfg['workload'] == 'batch32_480x720_forward+dsac256' and 'l2' in cfg and 'parallelism' in cfg
+    src = open(os.path.join(ROOT, 'bench.py')).read()
+    assert src.count("'config': config_of(args,") == 2   # the native and the reference line

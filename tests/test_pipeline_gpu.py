@@ -108,3 +108,60 @@ def test_localizer_accepts_uint8_host_frames():
     as_f32 = (frames.permute(0, 3, 1, 2).float() / 255).contiguous().pin_memory()
     from_f32 = loc.localize(as_f32, focal_d, offsets, image_base=7).clone()
     assert torch.equal(from_u8, from_f32)
+
+
+def _get_pose_err(gt_pose, est_pose):
+    """utils/evaluation.py:121-132 as written there (cv2.Rodrigues of R_est^T R_gt)."""
+    import cv2
+    transl_err = np.linalg.norm(gt_pose[0:3, 3] - est_pose[0:3, 3])
+    rot_err = est_pose[0:3, 0:3].T.dot(gt_pose[0:3, 0:3])
+    rot_err = cv2.Rodrigues(rot_err)[0]
+    rot_err = np.reshape(rot_err, (1, 3))
+    rot_err = np.reshape(np.linalg.norm(rot_err, axis=1), -1) / np.pi * 180.
+    return transl_err, rot_err[0]
+
+
+@pytest.mark.parametrize('consistent_scene', [True, False])
+def test_reference_evaluation_loop_body_on_a_480x720_frame(consistent_scene):
+    """The reference's own call pattern, call for call (test_single_task.py:347-356 and utils/evaluation.py:156-178):
+    batch 1, `network(image.cuda())`, `torch.split`, `.cpu()`, `dsacstar.forward_rgb` on CPU tensors with a CPU [4, 4]
+    output, `get_pose_err` -- against the shims of this repository, checked against the CPU oracle on the same map.
+    consistent_scene=False is BASELINE config 1 verbatim (raw random-init map: hundreds of tries per hypothesis)."""
+    import dsacstar
+    import networks.networks as nets
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(2021)                                       # test_single_task.py:265
+    network = nets.TransPoseNet(torch.zeros(3), False, False, num_task_channel=3, num_pos_channel=1,
+                                enc_add_res_block=2, dec_add_res_block=2, full_size_output=False, num_mlr=0)
+    network = network.cuda()                                      # utils/evaluation.py:115-116
+    network.eval()
+    image = torch.rand(1, 3, 480, 720, generator=torch.Generator().manual_seed(0))
+    scene = synth.make_scene(77)
+    gt_pose = torch.from_numpy(scene['pose']).float()[None]
+    focal_length = float(torch.tensor([scene['focal']]).view(-1)[0])
+    hypotheses, threshold, inlieralpha, maxpixelerror = 64, 10, 100, 100     # test_single_task.py defaults
+    dsacstar.set_seed(1305, image_index=500)
+    with torch.no_grad():
+        predictions = network(image.cuda())
+        assert predictions.size(2) == 60 and predictions.size(3) == 90 and predictions.is_cuda
+        predictions, uncertainty_map = torch.split(predictions, [network.num_task_channel, network.num_pos_channel], dim=1)
+        if consistent_scene:   # SURVEY 8d: a per-pixel offset plays the role of the decoder's `mean` buffer
+            predictions = predictions + torch.from_numpy(scene['coords'])[None].cuda()
+        # ---- scene_coords_eval
+        out_pose = torch.zeros((4, 4))
+        scene_coords = predictions.cpu()
+        dsacstar.forward_rgb(scene_coords, out_pose, hypotheses, threshold, focal_length,
+                             float(image.size(3) / 2), float(image.size(2) / 2), inlieralpha, maxpixelerror,
+                             network.OUTPUT_SUBSAMPLE)
+        t_err, r_err = _get_pose_err(gt_pose[0].cpu().numpy(), out_pose.numpy())
+    # the oracle on the very same CPU map, same (seed, image index)
+    o = tier2.forward_rgb(np.ascontiguousarray(scene_coords[0].numpy()), hypotheses, float(threshold), focal_length, 360.0, 240.0,
+                          float(inlieralpha), float(maxpixelerror), 8, seed=1305, image=500)
+    assert np.isfinite(out_pose.numpy()).all()
+    assert np.abs(o['pose'] - out_pose.numpy()).max() < 1e-3 * max(1.0, np.abs(o['pose']).max())
+    if consistent_scene:
+        assert t_err < 2.0 and r_err < 1.0, (t_err, r_err)
+        t2, r2 = synth.pose_errors(scene['pose'], out_pose.numpy())
+        assert abs(t2 - t_err) < 1e-4 and abs(r2 - r_err) < 1e-3   # the atan2 restatement of get_pose_err agrees with cv2
+    else:
+        assert int(np.asarray(o['tries']).max()) > 32   # the raw map really needs many tries per hypothesis
