@@ -541,8 +541,8 @@ def run_native(args):
     for kind, label, flops, ms, forwards in prof:
         if kind in ('memset', 'fork'):
             continue
-        key = {'conv': '/'.join(str(x) for x in label), 'gn_apply': 'gn_apply/%d/%d/%d' % label[:3],
-               'stem': 'stem/pass%d' % label[0]}.get(kind, kind)
+        key = {'conv': '/'.join(str(x) for x in label), 'conv_fused': '/'.join(str(x) for x in label) + '+gn',
+               'gn_apply': 'gn_apply/%d/%d/%d' % label[:3], 'stem': 'stem/pass%d' % label[0]}.get(kind, kind)
         ent = by_shape.setdefault(key, [0, 0.0, flops, max(forwards, 1)])
         ent[0] += 1
         ent[1] += ms
@@ -555,12 +555,14 @@ def run_native(args):
                            'tflops_useful': None}
     conv_total_ms = sum(v['ms_per_step'] for k, v in kernel_ms.items() if k.count('/') == 3 and not k.startswith('gn'))
     roofline = None
-    dom = kernel_ms.get('512/512/3/1')
+    fused = '512/512/3/1+gn' in kernel_ms
+    dom = kernel_ms.get('512/512/3/1+gn') or kernel_ms.get('512/512/3/1')
     if dom:
         achieved = dom['tflops_useful']
         nterms = rt.nterms
         traffic, traffic_src = ncu_traffic('conv_igemm_pair_kernel<64> 3x3 512->512')
-        roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel<64> 3x3 512->512 @60x90 x%d images' % B,
+        roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel<64%s> 3x3 512->512 @60x90 x%d images' % (
+                        ', fused GroupNorm epilogue' if fused else '', B),
                     'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                     'traffic': traffic, 'traffic_source': traffic_src,
                     'traffic_unit': 'bytes per launch (dram read + write, ncu --set full)',

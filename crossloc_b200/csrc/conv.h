@@ -38,9 +38,28 @@ struct ConvIgemmDesc {
     int Mp, Hp, Wp;         // output rows (B * Hp * Wp) and padded plane size
     int group_ch;           // GroupNorm channels per group (0: no statistics)
     float out_scale;        // undoes the power-of-two weight pre-scale
-    float* raw;             // fp32 [Mp][Cout] (interior rows only are written)
+    float* raw;             // fp32 [Mp][Cout] (interior rows only are written); unused when `fuse` is set
     const float* bias;      // fp32 [Cout]
     double* stats;          // fp64 [B][groups][2] sum, sum of squares (accumulated, caller zeroes)
+    // ---- optional: dynamic tile scheduling (CTA-pair kernel).  Clusters fetch tiles from a global counter instead of a
+    // fixed stride, so a cluster that starts late (SMs shared with another stream's kernels) simply takes fewer tiles.
+    int* tile_counter;      // nullable device int, zeroed by the caller before every launch
+    // ---- optional: GroupNorm + ReLU (+ residual add + ReLU) fused into the epilogue (CTA-pair kernel, needs tile_counter).
+    // The accumulator of a tile stays in tensor memory until the statistics of its image(s) are complete across the
+    // grid; the epilogue then normalises straight from TMEM and writes the next layer's operand planes -- the fp32 raw
+    // tensor and the separate gn_apply pass (write 4 B + read 4 B per element) disappear.
+    int fuse;
+    const float* gamma;     // [Cout] (group_ch != 0)
+    const float* beta;
+    float eps;
+    int H, W;               // interior size (statistics count = group_ch * H * W)
+    int relu_inner, relu_outer;
+    const __half* res;      // nullable residual stream, fp16 PF [Mp][Cout] hi plane, lo plane res_lo_rows further (0: none)
+    int64_t res_lo_rows;
+    __half* out16;          // fp16 PF [out_terms][Mp][Cout]: hi (and lo) operand planes of the consumer
+    int out_terms;
+    uint8_t* out8;          // nullable e4m3 planes [2][Mp][Cout]
+    int* unit_done;         // [Cout / BN][B] ints, zeroed by the caller: warp slices that have published their statistics
 };
 
 struct ConvIgemmParams {
@@ -56,6 +75,15 @@ struct ConvIgemmParams {
     double* stats;
     int num_stages, accum_stages;
     uint32_t a_bytes, w_bytes, stage_bytes;
+    int* tile_counter;
+    // fused GroupNorm epilogue
+    int fuse, H, W, B, relu_inner, relu_outer, out_terms, has_out8;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    const __half* res;
+    long long res_lo_rows;
+    int* unit_done;
 };
 
 // returns nullptr on success, else a static error string
@@ -63,12 +91,16 @@ const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream);
 
 // The same launch split in two: everything that depends only on shapes and pointers (tile schedule, the five TMA
 // tensor maps: ~10 us of driver calls) is prepared once and replayed (csrc/net.cu caches one plan per layer).
+struct alignas(64) ConvOutMaps {   // TMA store maps of the fused epilogue: fp16 hi / lo planes, e4m3 hi / lo planes
+    CUtensorMap hi, lo, hi8, lo8;
+};
 struct alignas(64) ConvIgemmPlan {
     CUtensorMap tmA, tmW, tmO, tmA8, tmW8;
+    ConvOutMaps out;
     ConvIgemmParams p;
     size_t smem;
     int grid, cluster;
-    int variant;            // bit 1: CTA-pair kernel, bit 0: 64-channel k-blocks
+    int variant;            // bit 2: fused GroupNorm epilogue, bit 1: CTA-pair kernel, bit 0: 64-channel k-blocks
 };
 const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan);
 const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream);

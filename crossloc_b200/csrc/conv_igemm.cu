@@ -30,6 +30,7 @@
 //   warps 4-7 epilogue: tcgen05.ld -> scale + bias -> swizzled smem staging -> TMA store (fp32) + GroupNorm
 //             partial sums (shuffle reduction, fp64 atomics)
 #include <cuda.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include "conv.h"
@@ -407,6 +408,251 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ---- dynamic tile scheduling -------------------------------------------------------------------------------
+// With p.tile_counter set, the leader CTA's warp 2 (idle after the TMEM allocation) fetches tile indices from a global
+// counter and publishes them through a four-slot ring that exists in both CTAs of the pair: it writes the index into
+// its own and (st.shared::cluster) the peer's ring, then arrives on `sched_full[slot]` in both.  Every consumer role
+// (producer warp(s), MMA warp, the four epilogue warps of each CTA) reads the slot and arrives on the LEADER's
+// `sched_empty[slot]`.  -1 terminates.  A cluster whose CTAs start late -- SMs still held by another stream's blocks --
+// takes fewer tiles instead of delaying the whole launch by its statically assigned share.
+constexpr int kRing = 4;
+
+struct TileFeed {
+    // static mode
+    int next_static, stride;
+    // dynamic mode
+    uint32_t full_bar0, empty_bar0, ring0;   // shared-memory addresses of slot 0
+    int slot;
+    uint32_t phase;
+    bool dynamic, leader;
+};
+
+__device__ __forceinline__ int feed_next(TileFeed& f, int num_tiles)
+{
+    if (!f.dynamic) {
+        const int t = f.next_static;
+        f.next_static += f.stride;
+        return t < num_tiles ? t : -1;
+    }
+    ptx::mbar_wait_cluster(f.full_bar0 + 8u * (uint32_t)f.slot, f.phase);
+    int t;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];\n" : "=r"(t) : "r"(f.ring0 + 4u * (uint32_t)f.slot) : "memory");
+    if (f.leader) ptx::mbar_arrive(f.empty_bar0 + 8u * (uint32_t)f.slot);
+    else ptx::mbar_arrive_remote(f.empty_bar0 + 8u * (uint32_t)f.slot, 0u);
+    if (++f.slot == kRing) { f.slot = 0; f.phase ^= 1u; }
+    return t;
+}
+
+// ---- fused GroupNorm epilogue -------------------------------------------------------------------------------
+// 32-row slices [r0, r0 + 32) of the padded-flat matrix that intersect image b
+__device__ __forceinline__ int slices_of_image(int b, int plane) { return ((b + 1) * plane - 1) / 32 - (b * plane) / 32 + 1; }
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Phase 1 of a tile for one epilogue warp: GroupNorm partial sums of the warp's 32 accumulator rows (nothing is stored),
+// then the slice is counted as published for every image it touches.
+__device__ __forceinline__ void fused_phase1(const ConvIgemmParams& p, uint32_t taddr, int n0, int lane, bool valid, int image,
+                                             int r0, int tn)
+{
+    if (p.group_ch) {
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            uint32_t u[32];
+            ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
+            ptx::tmem_ld_wait();
+            float f[32];
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 bb = __ldg(b4 + j);
+                f[4 * j + 0] = __uint_as_float(u[4 * j + 0]) * p.out_scale + bb.x;
+                f[4 * j + 1] = __uint_as_float(u[4 * j + 1]) * p.out_scale + bb.y;
+                f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) * p.out_scale + bb.z;
+                f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) * p.out_scale + bb.w;
+            }
+            const int first_group = (n0 + c0) / p.group_ch;
+            switch (p.group_ch) {
+                case 2: stats_chunk<2>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                case 4: stats_chunk<4>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                case 8: stats_chunk<8>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                case 16: stats_chunk<16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                default: break;
+            }
+        }
+        __threadfence();   // this lane's statistics atomics are visible before the slice is counted
+        __syncwarp();
+        if (lane == 0 && r0 < p.Mp) {
+            const int plane = p.Hp * p.Wp;
+            const int b0 = r0 / plane;
+            const int last = (r0 + 31 < p.Mp ? r0 + 31 : p.Mp - 1) / plane;
+            for (int b = b0; b <= last; b++) atomicAdd(p.unit_done + tn * p.B + b, 1);
+        }
+    }
+}
+
+// true once every slice touching the image(s) of this warp's rows has published its statistics for channel tile tn
+__device__ __forceinline__ bool fused_unit_complete(const ConvIgemmParams& p, int r0, int tn, int lane)
+{
+    if (!p.group_ch || r0 >= p.Mp) return true;
+    int ok = 1;
+    if (lane == 0) {
+        const int plane = p.Hp * p.Wp;
+        const int b0 = r0 / plane;
+        const int last = (r0 + 31 < p.Mp ? r0 + 31 : p.Mp - 1) / plane;
+        for (int b = b0; b <= last; b++)
+            if (ld_acquire(p.unit_done + tn * p.B + b) < slices_of_image(b, plane)) ok = 0;
+    }
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+
+// Phase 2: normalise the warp's 32 rows straight from tensor memory, ReLU, residual merge, split into the consumer's
+// operand planes (fp16 hi / lo, e4m3 hi / lo) and store them with TMA.  Border rows are written as zeros: the planes
+// are the zero-bordered input of the next convolution.
+__device__ __forceinline__ void fused_phase2(const ConvIgemmParams& p, const ConvOutMaps* maps, uint32_t taddr, int n0, int lane,
+                                             bool valid, int image, int r0, int m, uint32_t stage_base, float2* tab)
+{
+    // ---- (mean, 1/sigma) of the tile's groups for the (at most two) images of this slice
+    const int plane = p.Hp * p.Wp;
+    const int img0 = r0 < p.Mp ? r0 / plane : 0;
+    if (p.group_ch) {
+        const int ng = p.BN / p.group_ch;           // groups of this channel tile (<= 32 ... 128)
+        const double count = (double)p.group_ch * p.H * p.W;
+        for (int which = 0; which < 2; which++) {
+            const int b = img0 + which;
+            for (int g = lane; g < ng; g += 32) {   // ng <= 32 (checked by the launcher)
+                float2 mr = make_float2(0.f, 1.f);
+                if (b < p.B) {
+                    const double* st = p.stats + ((size_t)b * p.groups + n0 / p.group_ch + g) * 2;
+                    const double s = __ldcg(st), ss = __ldcg(st + 1);
+                    const double mu = s / count;
+                    double var = ss / count - mu * mu;
+                    var = var > 0 ? var : 0;
+                    mr = make_float2((float)mu, (float)(1.0 / sqrt(var + (double)p.eps)));
+                }
+                tab[which * 32 + g] = mr;
+            }
+        }
+        __syncwarp();
+    }
+    const int which = (valid && image != img0) ? 1 : 0;
+    const int gshift = p.group_ch ? 31 - __clz(p.group_ch) : 0;
+    const uint32_t s_hi = stage_base, s_lo = stage_base + 2048u, s_h8 = stage_base + 4096u, s_l8 = stage_base + 5120u;
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t u[32];
+        ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
+        ptx::tmem_ld_wait();
+        float v[32];
+        const int c = n0 + c0;
+        {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 bb = __ldg(b4 + j);
+                v[4 * j + 0] = __uint_as_float(u[4 * j + 0]) * p.out_scale + bb.x;
+                v[4 * j + 1] = __uint_as_float(u[4 * j + 1]) * p.out_scale + bb.y;
+                v[4 * j + 2] = __uint_as_float(u[4 * j + 2]) * p.out_scale + bb.z;
+                v[4 * j + 3] = __uint_as_float(u[4 * j + 3]) * p.out_scale + bb.w;
+            }
+        }
+        if (p.group_ch) {
+            const float4* g4 = reinterpret_cast<const float4*>(p.gamma + c);
+            const float4* e4 = reinterpret_cast<const float4*>(p.beta + c);
+            const float2* tb = tab + which * 32;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 ga = __ldg(g4 + j), be = __ldg(e4 + j);
+                const float gg[4] = {ga.x, ga.y, ga.z, ga.w}, bb[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float2 mr = tb[(c0 + 4 * j + k) >> gshift];
+                    v[4 * j + k] = (v[4 * j + k] - mr.x) * (mr.y * gg[k]) + bb[k];
+                }
+            }
+        }
+        if (p.relu_inner) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.res && valid) {
+            // res_hi + res_lo first, then the sum is added: the rounding order of gn_apply_kernel
+            const uint4* rh = reinterpret_cast<const uint4*>(p.res + (size_t)m * p.Cout + c);
+            const uint4* rl = reinterpret_cast<const uint4*>(p.res + ((size_t)m + (size_t)p.res_lo_rows) * p.Cout + c);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint4 hq = __ldg(rh + j);
+                const uint4 lq = p.res_lo_rows > 0 ? __ldg(rl + j) : make_uint4(0, 0, 0, 0);
+                const __half2* hh = reinterpret_cast<const __half2*>(&hq);
+                const __half2* ll = reinterpret_cast<const __half2*>(&lq);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float2 a = __half22float2(hh[k]), bq = __half22float2(ll[k]);
+                    v[8 * j + 2 * k] += a.x + bq.x;
+                    v[8 * j + 2 * k + 1] += a.y + bq.y;
+                }
+            }
+        }
+        if (p.relu_outer) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (!valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = 0.f;
+        }
+        // the staging buffers of the previous chunk must have been read by their TMA stores
+        if (lane == 0) ptx::tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {   // 8 channels -> one 16-byte chunk of the hi and of the lo plane (64-byte rows, SWIZZLE_64B)
+            __align__(16) __half h[8];
+            __align__(16) __half l[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                h[k] = __float2half_rn(v[8 * j + k]);
+                l[k] = __float2half_rn(v[8 * j + k] - __half2float(h[k]));
+            }
+            const uint32_t off = (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
+            const uint4 hv = *reinterpret_cast<const uint4*>(h), lv = *reinterpret_cast<const uint4*>(l);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_hi + off), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
+            if (p.out_terms == 2)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_lo + off), "r"(lv.x), "r"(lv.y), "r"(lv.z), "r"(lv.w) : "memory");
+        }
+        if (p.has_out8) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {   // 16 channels -> one 16-byte chunk of each e4m3 plane (32-byte rows, no swizzle)
+                __align__(16) __nv_fp8x2_storage_t h8[8];
+                __align__(16) __nv_fp8x2_storage_t l8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float x0 = v[16 * j + 2 * k], x1 = v[16 * j + 2 * k + 1];
+                    const float a0 = __half2float(__float2half_rn(x0)), a1 = __half2float(__float2half_rn(x1));
+                    h8[k] = __nv_cvt_float2_to_fp8x2(make_float2(a0 * kAct8HiScale, a1 * kAct8HiScale), __NV_SATFINITE, __NV_E4M3);
+                    l8[k] = __nv_cvt_float2_to_fp8x2(make_float2((x0 - a0) * kAct8LoScale, (x1 - a1) * kAct8LoScale), __NV_SATFINITE, __NV_E4M3);
+                }
+                const uint32_t off = (uint32_t)lane * 32u + (uint32_t)(j << 4);
+                const uint4 hv = *reinterpret_cast<const uint4*>(h8), lv = *reinterpret_cast<const uint4*>(l8);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_h8 + off), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_l8 + off), "r"(lv.x), "r"(lv.y), "r"(lv.z), "r"(lv.w) : "memory");
+            }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && r0 < p.Mp) {
+            ptx::tma_store_2d(&maps->hi, s_hi, c, r0);      // rows >= Mp are clipped by the TMA unit
+            if (p.out_terms == 2) ptx::tma_store_2d(&maps->lo, s_lo, c, r0);
+            if (p.has_out8) {
+                ptx::tma_store_2d(&maps->hi8, s_h8, c, r0);
+                ptx::tma_store_2d(&maps->lo8, s_l8, c, r0);
+            }
+            ptx::tma_store_commit();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // CTA-pair variant (tcgen05 cta_group::2).  In the single-CTA kernel every 128 x 256 x 16 MMA reads 12 KB of
 // operands from shared memory in 128 cycles while TMA writes the next stage: more than the 128 B/clk an SM's
@@ -422,11 +668,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Protocol (leader = even CTA of the pair): both CTAs' producers load with the 2-SM TMA form that signals the
 // LEADER's full barrier; the leader's MMA warp issues for the pair and releases stages / publishes accumulators
 // with tcgen05.commit multicast to both CTAs; both epilogues signal the leader's accumulator-empty barrier.
-template <int BK>
+//
+// FUSED (GroupNorm in the epilogue, see ConvIgemmDesc::fuse): the second accumulator doubles as the waiting room of a
+// finished tile.  An epilogue warp first sums the statistics of its 32 rows (phase 1) and counts its slice as published;
+// the accumulator is drained (phase 2) as soon as every slice of the image(s) it touches -- across the whole grid --
+// has been published, which with the dynamic scheduler (consecutive tile indices are handed out within microseconds)
+// is typically long before the next tile's MMAs finish.  Deadlock freedom: a warp only blocks on phase 2 of tile i
+// AFTER it has published phase 1 of tile i + 1, and the launcher admits fused mode only when all tiles of an image
+// fit into the tiles in flight (num_clusters), so the oldest unpublished image always completes.
+template <int BK, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA8,
-                       const __grid_constant__ CUtensorMap tmW8, const ConvIgemmParams p)
+                       const __grid_constant__ CUtensorMap tmW8, const __grid_constant__ ConvOutMaps outMaps,
+                       const ConvIgemmParams p)
 {
     constexpr int kSwizzle = BK * 2;
     extern __shared__ uint8_t smem_raw[];
@@ -434,6 +689,9 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ __align__(8) uint64_t sched_full[kRing];
+    __shared__ __align__(8) uint64_t sched_empty[kRing];
+    __shared__ int tile_ring[kRing];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -447,11 +705,17 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int num_tiles = p.super_m * p.tiles_n;
     const int kblocks = p.num_taps * p.kblocks_per_tap;
     const uint32_t w_half = p.w_bytes / 2;   // this CTA's half of the weight tile (BN / 2 rows)
+    const bool dynamic = p.tile_counter != nullptr;
+    const bool split = p.kblocks_per_tap == 1 && !f8c;   // two producer threads per CTA (see below)
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmW);
-        ptx::prefetch_tensormap(&tmO);
+        if (FUSED) {
+            ptx::prefetch_tensormap(&outMaps.hi);
+        } else {
+            ptx::prefetch_tensormap(&tmO);
+        }
         if (f8c) {
             ptx::prefetch_tensormap(&tmA8);
             ptx::prefetch_tensormap(&tmW8);
@@ -466,6 +730,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);   // MMA commit, multicast to both CTAs
             ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 8);  // leader only: 4 epilogue warps of each CTA
         }
+        const uint32_t consumers = 2u * ((split ? 2u : 1u) + 4u) + 1u;   // producers + epilogue warps of both CTAs, MMA warp
+        for (int s = 0; s < kRing; s++) {
+            ptx::mbar_init(ptx::smem_u32(&sched_full[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&sched_empty[s]), consumers);
+        }
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
@@ -478,7 +747,42 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 0 || warp == 3) {
+    TileFeed feed;
+    feed.next_static = cluster_id;
+    feed.stride = num_clusters;
+    feed.full_bar0 = ptx::smem_u32(&sched_full[0]);
+    feed.empty_bar0 = ptx::smem_u32(&sched_empty[0]);
+    feed.ring0 = ptx::smem_u32(&tile_ring[0]);
+    feed.slot = 0;
+    feed.phase = 0;
+    feed.dynamic = dynamic;
+    feed.leader = leader;
+
+    if (warp == 2) {
+        // ------------------------------------------------------------------ tile scheduler (leader CTA, one thread)
+        if (dynamic && leader && lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int local = 0;; local++) {
+                // A tile is only claimed once the pair has an accumulator for it (the tile two claims ago is drained): a
+                // cluster never sits on tiles it cannot start, so whatever is claimed anywhere in the grid gets accumulated
+                // and published without waiting for anyone else -- the progress argument of the fused epilogue.
+                const int as = local % p.accum_stages;
+                ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), ((uint32_t)(local / p.accum_stages) & 1u) ^ 1u);
+                ptx::mbar_wait(ptx::smem_u32(&sched_empty[slot]), phase ^ 1u);   // every consumer has read this slot's last content
+                int t = atomicAdd(p.tile_counter, 1);
+                if (t >= num_tiles) t = -1;
+                const uint32_t ring = ptx::smem_u32(&tile_ring[slot]);
+                asm volatile("st.volatile.shared.s32 [%0], %1;\n" ::"r"(ring), "r"(t) : "memory");
+                ptx::st_shared_remote_u32(ring, 1u, (uint32_t)t);
+                const uint32_t fb = ptx::smem_u32(&sched_full[slot]);
+                ptx::mbar_arrive_release_cluster(fb);
+                ptx::mbar_arrive_remote(fb, 1u);
+                if (t < 0) break;
+                if (++slot == kRing) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 0 || warp == 3) {
         // ------------------------------------------------------------------ TMA producers (both CTAs)
         // Layers with one k-block per tap (conv2, conv3) use two producer threads per CTA: warp 0 loads the activation
         // boxes (and arms the barrier), warp 3 the weight boxes.  One thread needs ~250 instructions per stage for four
@@ -486,7 +790,6 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // instruction bound, ncu: tensor pipe 18 %; 1.06 -> 0.98 ms stand-alone).
         // Only for layers with a single k-block per tap: with longer K loops the MMAs hide the producer anyway and the
         // second thread costs ~1 % (measured on the 512-channel layers).
-        const bool split = p.kblocks_per_tap == 1 && !f8c;
         const bool load_a = warp == 0, load_w = split ? warp == 3 : warp == 0;
         if (lane == 0 && (load_a || load_w)) {
             int stage = 0;
@@ -496,7 +799,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             // fp16 + fp8: a stage covers 2 * BK input channels -- pass 0 streams the e4m3 planes (128-byte rows, one box
             // per plane), pass 1 the fp16 planes (two boxes per operand); the stage size is the same in both passes
             const int kstep = f8c ? 2 : 1;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int tile = feed_next(feed, num_tiles); tile >= 0; tile = feed_next(feed, num_tiles)) {
                 const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
                 const int n0 = (tile % p.tiles_n) * p.BN;
                 for (int pass = f8c ? 0 : 1; pass < 2; pass++) {
@@ -541,7 +844,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint32_t idesc = ptx::make_idesc_f16(2 * kBlockM, p.BN);
             int stage = 0, local = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
+            for (;; local++) {
+                int tile = 0;
+                if (lane == 0) tile = feed_next(feed, num_tiles);
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+                if (tile < 0) break;
                 const int as = local % p.accum_stages;
                 const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
                 ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aphase ^ 1u);
@@ -618,31 +925,94 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int plane = p.Hp * p.Wp;
         const uint32_t stage_base = smem_base + (uint32_t)p.num_stages * p.stage_bytes + (uint32_t)q * 2u * kStageChunkBytes;
         uint32_t chunk_no = 0;
-        int local = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
-            const int as = local % p.accum_stages;
-            const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
-            const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
-            const int n0 = (tile % p.tiles_n) * p.BN;
-            const int m = m0 + q * 32 + lane;
-            int image = 0;
-            bool valid = false;
+        // a finished tile whose accumulator still waits for the statistics of its image(s) (FUSED only)
+        int pend_tile = -1, pend_as = 0;
+        auto tile_rows = [&](int tile, int& m0, int& n0, int& m, bool& valid, int& image) {
+            m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+            n0 = (tile % p.tiles_n) * p.BN;
+            m = m0 + q * 32 + lane;
+            image = 0;
+            valid = false;
             if (m < p.Mp) {
                 image = m / plane;
                 const int r = m - image * plane;
                 const int y = r / p.Wp, x = r - y * p.Wp;
                 valid = y >= 1 && y <= p.Hp - 2 && x >= 1 && x <= p.Wp - 2;
             }
-            ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
-            epilogue_tile(p, &tmO, taddr, m0, n0, q, lane, stage_base, chunk_no, false, valid, image);   // corrections already folded
+        };
+        auto release = [&](int as) {
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (leader) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
                 else ptx::mbar_arrive_remote(ptx::smem_u32(&tempty_bar[as]), 0u);
             }
+        };
+        auto drain_pending = [&]() {   // phase 2 of the waiting tile; its statistics are complete
+            int m0, n0, m, image;
+            bool valid;
+            tile_rows(pend_tile, m0, n0, m, valid, image);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pend_as * p.BN);
+            ptx::tc_fence_after();
+            // (mean, 1/sigma) table of this warp: the 2 KB of its staging area that phase 2 leaves unused
+            float2* tab = reinterpret_cast<float2*>(smem_raw + (stage_base + 6144u - ptx::smem_u32(smem_raw)));
+            fused_phase2(p, &outMaps, taddr, n0, lane, valid, image, m0 + q * 32, m, stage_base, tab);
+            release(pend_as);
+            pend_tile = -1;
+        };
+        for (int local = 0;; local++) {
+            int tile = 0;
+            if (lane == 0) tile = feed_next(feed, num_tiles);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile < 0) break;
+            const int as = local % p.accum_stages;
+            const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
+            int m0, n0, m, image;
+            bool valid;
+            tile_rows(tile, m0, n0, m, valid, image);
+            const uint32_t tfull = ptx::smem_u32(&tfull_bar[as]);
+            if (FUSED) {
+                // while this tile's MMAs run: drain the waiting tile as soon as its image(s) are complete
+                while (pend_tile >= 0) {
+                    int ready = lane == 0 ? (int)ptx::mbar_test(tfull, aphase) : 0;
+                    ready = __shfl_sync(0xffffffffu, ready, 0);
+                    if (ready) break;
+                    const int pm0 = ((pend_tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+                    if (fused_unit_complete(p, pm0 + q * 32, pend_tile % p.tiles_n, lane)) drain_pending();
+                    else __nanosleep(200);
+                }
+            }
+            ptx::mbar_wait(tfull, aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+            if (FUSED) {
+                fused_phase1(p, taddr, n0, lane, valid, image, m0 + q * 32, tile % p.tiles_n);
+                if (pend_tile >= 0) {
+                    // the previous tile is still waiting: its images only need slices that were handed out before this
+                    // tile, all of which publish without waiting for anyone -- blocking here cannot deadlock
+                    const int pm0 = ((pend_tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+                    const long long t0 = clock64();
+                    while (!fused_unit_complete(p, pm0 + q * 32, pend_tile % p.tiles_n, lane)) {
+                        __nanosleep(200);
+                        if (clock64() - t0 > 4000000000ll) __trap();
+                    }
+                    drain_pending();
+                }
+                pend_tile = tile;
+                pend_as = as;
+            } else {
+                epilogue_tile(p, &tmO, taddr, m0, n0, q, lane, stage_base, chunk_no, false, valid, image);   // corrections already folded
+                release(as);
+            }
+        }
+        if (FUSED && pend_tile >= 0) {
+            const int pm0 = ((pend_tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+            const long long t0 = clock64();
+            while (!fused_unit_complete(p, pm0 + q * 32, pend_tile % p.tiles_n, lane)) {
+                __nanosleep(200);
+                if (clock64() - t0 > 4000000000ll) __trap();
+            }
+            drain_pending();
         }
         if (lane == 0) ptx::tma_store_wait<0>();
     }
@@ -673,7 +1043,7 @@ EncodeTiledFn encode_tiled_fn()
 // row-major [rows][cols] matrix of fp16 (elem_bytes 2) or fp32 (4), box = box_rows x box_cols elements whose
 // byte width is the swizzle span; rows out of range are zero-filled on loads and clipped on stores
 bool make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                     uint32_t box_cols, uint32_t elem_bytes)
+                     uint32_t box_cols, uint32_t elem_bytes, bool no_swizzle = false)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
@@ -682,8 +1052,9 @@ bool make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const uint32_t row_bytes = box_cols * elem_bytes;
-    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                  : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapSwizzle sw = no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                  : (row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                     : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B));
     const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                    : (elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
     return fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
@@ -750,12 +1121,47 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
     if (d.nterms == 2 && d.corr_scale != 1.0f / (float)(1 << kCorrShift)) return "conv_igemm: corr_scale must be 2^-14";
     p.accum_stages = (d.nterms == 2 && !pair ? 4 : 2) * BN <= (int)kTmemCols ? 2 : 1;
     plan->smem = (size_t)p.num_stages * p.stage_bytes + kEpilogueStagingBytes + 1024;
+    p.tile_counter = pair ? d.tile_counter : nullptr;
+    p.fuse = 0;
+    if (d.fuse) {
+        const int plane = d.Hp * d.Wp;
+        if (!pair || !d.tile_counter) return "conv_igemm: the fused GroupNorm epilogue needs the CTA-pair kernel and a tile counter";
+        if (!d.out16 || (d.out_terms != 1 && d.out_terms != 2)) return "conv_igemm: fused epilogue without output planes";
+        if (d.group_ch && (!d.stats || !d.gamma || !d.beta || !d.unit_done)) return "conv_igemm: fused epilogue without GroupNorm parameters";
+        if (d.Mp % plane != 0 || plane < 32) return "conv_igemm: fused epilogue needs whole planes of at least 32 rows";
+        if (p.accum_stages != 2) return "conv_igemm: fused epilogue needs two accumulators";
+        if (BN / (d.group_ch ? d.group_ch : BN) > 32) return "conv_igemm: too many groups per channel tile for the fused epilogue";
+        // deadlock freedom: every tile touching one image must be among the tiles in flight
+        const int tiles_per_image = ((plane + 2 * kBlockM - 1) / (2 * kBlockM) + 1) * p.tiles_n;
+        if (tiles_per_image > sms / 2) return "conv_igemm: image too large for the fused epilogue (tiles of one image exceed the grid)";
+        p.fuse = 1;
+        p.H = d.H; p.W = d.W; p.B = d.Mp / plane;
+        p.relu_inner = d.relu_inner; p.relu_outer = d.relu_outer;
+        p.out_terms = d.out_terms; p.has_out8 = d.out8 ? 1 : 0;
+        p.gamma = d.gamma; p.beta = d.beta; p.eps = d.eps;
+        p.res = d.res; p.res_lo_rows = d.res_lo_rows;
+        p.unit_done = d.unit_done;
+        const size_t plane16 = (size_t)d.Mp * d.Cout;
+        if (!make_tensor_map(&plan->out.hi, d.out16, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 2))
+            return "conv_igemm: cuTensorMapEncodeTiled failed for the fp16 output plane";
+        plan->out.lo = plan->out.hi;
+        plan->out.hi8 = plan->out.hi;
+        plan->out.lo8 = plan->out.hi;
+        if (d.out_terms == 2 && !make_tensor_map(&plan->out.lo, d.out16 + plane16, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 2))
+            return "conv_igemm: cuTensorMapEncodeTiled failed for the fp16 lo output plane";
+        if (d.out8) {
+            if (!make_tensor_map(&plan->out.hi8, d.out8, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 1, true) ||
+                !make_tensor_map(&plan->out.lo8, d.out8 + plane16, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 1, true))
+                return "conv_igemm: cuTensorMapEncodeTiled failed for the e4m3 output planes";
+        }
+    }
 
     if (!make_tensor_map(&plan->tmA, d.act, (uint64_t)d.a_total_rows, (uint64_t)d.Cin, kBlockM, BK, 2))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the activation matrix";
     if (!make_tensor_map(&plan->tmW, d.weights, (uint64_t)(d.nterms == 3 ? 2 : 1) * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, BK, 2))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the weight matrix";
-    if (!make_tensor_map(&plan->tmO, d.raw, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 4))
+    if (d.fuse) plan->tmO = plan->tmA;
+    else if (!make_tensor_map(&plan->tmO, d.raw, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 4))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the output matrix";
     plan->tmA8 = plan->tmA;
     plan->tmW8 = plan->tmW;
@@ -774,7 +1180,7 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
     if (clusters > num_super) clusters = num_super;
     plan->grid = clusters * cluster;
     plan->cluster = cluster;
-    plan->variant = (pair ? 2 : 0) + (BK == 64 ? 1 : 0);
+    plan->variant = (p.fuse ? 4 : 0) + (pair ? 2 : 0) + (BK == 64 ? 1 : 0);
     return nullptr;
 }
 
@@ -794,30 +1200,26 @@ const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream)
     cfg.numAttrs = 1;
 
     // the opt-in shared-memory size is a per-function, per-device attribute: raise it once to the maximum any plan uses
-    static bool attr_set[64][4] = {};
+    static bool attr_set[64][8] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    bool& done = attr_set[dev & 63][plan.variant];
-    const int max_smem = 227 * 1024;
+    bool& done = attr_set[dev & 63][plan.variant & 7];
+    const int max_smem = 227 * 1024 - 1024;   // dynamic part only: the kernels also hold ~300 bytes of static shared memory
     cudaError_t e = cudaSuccess;
+#define CL_LAUNCH(KERNEL, ...)                                                                              \
+    do {                                                                                                    \
+        if (!done) e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); \
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, KERNEL, __VA_ARGS__);                            \
+    } while (0)
     switch (plan.variant) {
-        case 3:
-            if (!done) e = cudaFuncSetAttribute(conv_igemm_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<64>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p);
-            break;
-        case 2:
-            if (!done) e = cudaFuncSetAttribute(conv_igemm_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<32>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p);
-            break;
-        case 1:
-            if (!done) e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<64>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p);
-            break;
-        default:
-            if (!done) e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<32>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p);
-            break;
+        case 7: CL_LAUNCH((conv_igemm_pair_kernel<64, true>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
+        case 6: CL_LAUNCH((conv_igemm_pair_kernel<32, true>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
+        case 3: CL_LAUNCH((conv_igemm_pair_kernel<64, false>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
+        case 2: CL_LAUNCH((conv_igemm_pair_kernel<32, false>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
+        case 1: CL_LAUNCH(conv_igemm_kernel<64>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p); break;
+        default: CL_LAUNCH(conv_igemm_kernel<32>, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p); break;
     }
+#undef CL_LAUNCH
     if (e != cudaSuccess) return cudaGetErrorString(e);
     done = true;
     e = cudaGetLastError();

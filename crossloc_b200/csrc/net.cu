@@ -154,7 +154,7 @@ struct PF {   // one padded-flat activation: fp16 hi / lo planes and (on demand)
 };
 
 struct Op {
-    enum Kind { kMemset, kStem, kConv, kApply, kHead, kDucHead, kRawStats, kFrames, kFork } kind = kMemset;
+    enum Kind { kMemset, kStem, kConv, kApply, kHead, kDucHead, kRawStats, kFrames, kFork, kConvFused } kind = kMemset;
     cudaEvent_t event = nullptr;  // kFork
     int label[4] = {0, 0, 0, 0};  // profiling: conv (cin, cout, ksize, stride), apply (channels, out phases, add kind, 0)
     double flops = 0;             // algorithmic FLOPs of the launch (convolutions and the stem)
@@ -216,12 +216,15 @@ struct Plan {
 // ------------------------------------------------------------------------------------------- engine
 struct Net {
     int device = 0;
+    int sms = 148;
     int precision = 2;         // 1 fp16x1 | 2 fp16 + fp8 | 3 fp16x3
     int terms = 2;             // fp16 planes per activation
     bool relu_after_add = true;
     bool fp8_1x1 = true;
     bool use_graph = true;
     bool profiling = false;    // eager launches with a CUDA event between ops (cl_net_profile)
+    bool fuse_gn = true;       // GroupNorm / ReLU / residual merge in the convolution epilogue where the plan allows it
+    bool dynamic_tiles = true; // tile indices from a global counter instead of a fixed stride (CTA-pair kernel)
     std::vector<std::unique_ptr<Layer>> layers;
     std::vector<Block> blocks;
     int stem[4] = {-1, -1, -1, -1};
@@ -321,7 +324,16 @@ struct Builder {
     std::string err;
     int stat_i = 0;
     int max_groups = 32;
-    int pool_turn = 0;
+    int counter_i = 0;
+    size_t stats_bytes = 0;
+
+    // scheduler / publication counters live behind the statistics in one allocation: a single memset per forward
+    int* next_counters(int count)
+    {
+        int* base = reinterpret_cast<int*>(static_cast<char*>(P.stats.p) + stats_bytes) + counter_i;
+        counter_i += count;
+        return base;
+    }
 
     Builder(Net& net, Plan& plan) : n(net), P(plan) {}
 
@@ -380,10 +392,16 @@ struct Builder {
         return 9;
     }
 
-    bool conv(int li, PF* a, const Geometry& g, float* rawbuf, double* st)
+    struct Fuse {             // GroupNorm + ReLU (+ residual + ReLU) in the epilogue: the consumer's operand planes
+        PF* out = nullptr;
+        PF* res = nullptr;
+        bool relu_inner = true, relu_outer = false, want_lo = true, want8 = false;
+    };
+
+    bool conv(int li, PF* a, const Geometry& g, float* rawbuf, double* st, const Fuse* fuse = nullptr)
     {
         Layer& L = *n.layers[li];
-        if (!a || !rawbuf) return false;
+        if (!a || (!rawbuf && !fuse)) return false;
         ConvIgemmDesc d{};
         d.act = a->h16.p;
         d.a_total_rows = a->rows16();
@@ -410,8 +428,26 @@ struct Builder {
         d.raw = rawbuf;
         d.bias = L.bias.as<float>();
         d.stats = (gc && fused_stats) ? st : nullptr;
+        if (n.dynamic_tiles) d.tile_counter = next_counters(1);
+        if (fuse) {
+            d.fuse = 1;
+            d.gamma = gc ? L.gamma.as<float>() : nullptr;
+            d.beta = gc ? L.beta.as<float>() : nullptr;
+            d.eps = L.gn_eps;
+            d.H = g.H; d.W = g.W;
+            d.relu_inner = fuse->relu_inner; d.relu_outer = fuse->relu_outer;
+            if (fuse->res) {
+                d.res = fuse->res->h16.as<__half>();
+                d.res_lo_rows = n.terms == 2 ? g.Mp : 0;
+            }
+            d.out16 = fuse->out->h16.as<__half>();
+            d.out_terms = (fuse->want_lo && n.terms == 2) ? 2 : 1;
+            d.out8 = fuse->want8 ? f8(fuse->out) : nullptr;
+            if (fuse->want8 && !d.out8) return false;
+            d.unit_done = next_counters(g.B * 8);
+        }
         Op op;
-        op.kind = Op::kConv;
+        op.kind = fuse ? Op::kConvFused : Op::kConv;
         op.conv.reset(new ConvIgemmPlan);
         if (const char* e = conv_igemm_prepare(d, op.conv.get())) return fail(std::string(e));
         op.label[0] = L.cin; op.label[1] = L.cout; op.label[2] = L.ksize; op.label[3] = L.stride;
@@ -426,6 +462,25 @@ struct Builder {
             P.launches++;
         }
         return true;
+    }
+
+    // Can layer li (a convolution at the output resolution followed by GroupNorm / ReLU / an optional fp16 residual merge)
+    // run with the fused epilogue?  Mirrors the checks of conv_igemm_prepare so that the plan never has to back out.
+    bool can_fuse(int li, const Geometry& g) const
+    {
+        if (!n.fuse_gn || !n.dynamic_tiles) return false;
+        const Layer& L = *n.layers[li];
+        const int gc = L.group_ch();
+        if (!igemm_group_ok(gc)) return false;
+        const int BN = L.cout % 256 == 0 ? 256 : (L.cout % 128 == 0 ? 128 : 64);
+        if (gc && BN / gc > 32) return false;
+        if (2 * BN > 512) return false;
+        if (L.nterms == 2 && L.cin % 128 != 0) return false;
+        const int tiles_m = (g.Mp + 127) / 128;
+        if (tiles_m < 16 || n.sms % 2 != 0) return false;                      // CTA-pair kernel only
+        if (g.plane < 32) return false;
+        const int tiles_per_image = ((g.plane + 255) / 256 + 1) * (L.cout / BN);
+        return tiles_per_image <= n.sms / 2;
     }
 
     struct Merge { PF* res = nullptr; float* raw2 = nullptr; int layer2 = -1; double* stats2 = nullptr; };
@@ -515,22 +570,34 @@ struct Builder {
         for (size_t i = 0; i < convs.size(); i++) {
             const int li = convs[i];
             Layer& L = *n.layers[li];
-            float* r = raw(i % 2 ? "r1" : "r0", 3, L.cout);
             double* st = L.gn_groups ? next_stats() : nullptr;
-            if (!conv(li, x, g3, r, st)) return nullptr;
             PF* out = scratch(L.cout, x, res_in);
             if (!out) return nullptr;
             const bool last = i + 1 == convs.size();
             bool want_lo, want8;
-            if (!last) {
-                planes_for({convs[i + 1]}, false, want_lo, want8);
-                if (!apply(r, g3, li, st, out, true, Merge{}, false, want_lo, want8)) return nullptr;
+            if (!last) planes_for({convs[i + 1]}, false, want_lo, want8);
+            else planes_for(next_readers, true, want_lo, want8);
+            const bool merge_raw2 = last && skip && skip->raw2;
+            if (!merge_raw2 && can_fuse(li, g3)) {
+                Fuse f;
+                f.out = out;
+                f.res = last ? (skip ? skip->res : res_in) : nullptr;
+                f.relu_inner = true;
+                f.relu_outer = last && outer_relu;
+                f.want_lo = want_lo;
+                f.want8 = want8;
+                if (!conv(li, x, g3, nullptr, st, &f)) return nullptr;
             } else {
-                planes_for(next_readers, true, want_lo, want8);
-                Merge m;
-                if (skip) m = *skip;
-                else m.res = res_in;
-                if (!apply(r, g3, li, st, out, true, m, outer_relu, want_lo, want8)) return nullptr;
+                float* r = raw(i % 2 ? "r1" : "r0", 3, L.cout);
+                if (!conv(li, x, g3, r, st)) return nullptr;
+                if (!last) {
+                    if (!apply(r, g3, li, st, out, true, Merge{}, false, want_lo, want8)) return nullptr;
+                } else {
+                    Merge m;
+                    if (skip) m = *skip;
+                    else m.res = res_in;
+                    if (!apply(r, g3, li, st, out, true, m, outer_relu, want_lo, want8)) return nullptr;
+                }
             }
             x = out;
         }
@@ -548,7 +615,9 @@ struct Builder {
         for (auto& L : n.layers)
             if (L->gn_groups > max_groups) max_groups = L->gn_groups;
         const size_t n_stat = n.layers.size() + 2;
-        if (cudaError_t e = P.stats.alloc(n_stat * B * max_groups * 2 * sizeof(double), true)) return fail(cudaGetErrorString(e));
+        stats_bytes = n_stat * B * max_groups * 2 * sizeof(double);
+        const size_t counter_bytes = n_stat * ((size_t)B * 8 + 1) * sizeof(int);
+        if (cudaError_t e = P.stats.alloc(stats_bytes + counter_bytes, true)) return fail(cudaGetErrorString(e));
         if (cudaError_t e = P.in_f32.alloc((size_t)B * Cin * H * W * sizeof(float), false)) return fail(cudaGetErrorString(e));
         {
             Op op;
@@ -641,14 +710,22 @@ struct Builder {
                 for (size_t i = 0; i < blk.convs.size(); i++) {
                     const int li = blk.convs[i];
                     Layer& L = *n.layers[li];
-                    float* r = raw("r0", 3, L.cout);
                     double* s2 = L.gn_groups ? next_stats() : nullptr;
-                    if (!conv(li, res, g3, r, s2)) return false;
                     PF* out = scratch(L.cout, res, nullptr);
                     if (!out) return false;
                     bool want_lo, want8;
                     planes_for(i + 1 < blk.convs.size() ? std::vector<int>{blk.convs[i + 1]} : readers, true, want_lo, want8);
-                    if (!apply(r, g3, li, s2, out, true, Merge{}, false, want_lo, want8)) return false;
+                    if (can_fuse(li, g3)) {
+                        Fuse f;
+                        f.out = out;
+                        f.want_lo = want_lo;
+                        f.want8 = want8;
+                        if (!conv(li, res, g3, nullptr, s2, &f)) return false;
+                    } else {
+                        float* r = raw("r0", 3, L.cout);
+                        if (!conv(li, res, g3, r, s2)) return false;
+                        if (!apply(r, g3, li, s2, out, true, Merge{}, false, want_lo, want8)) return false;
+                    }
                     res = out;
                 }
             } else {
@@ -707,7 +784,8 @@ const char* run_op(const Op& op, cudaStream_t s)
             return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
         }
         case Op::kStem: return stem_tc_launch(op.stem, op.stem_stats, s);
-        case Op::kConv: return conv_igemm_run(*op.conv, s);
+        case Op::kConv:
+        case Op::kConvFused: return conv_igemm_run(*op.conv, s);
         case Op::kApply: return gn_apply_launch(op.apply, s);
         case Op::kHead: return head_launch(op.head, s);
         case Op::kDucHead: return duc_head_launch(op.duc, s);
@@ -778,6 +856,31 @@ Plan* plan_for(Net& n, int B, int Cin, int H, int W, std::string& err)
     return out;
 }
 
+// Forwards of ALL handles on one device are chained by an event: a fused-epilogue convolution spins on publications of
+// its own grid, so two such launches from different streams, each holding part of the SMs, could wait for each other
+// forever.  Every forward saturates the chip on its own; nothing is lost by running them one after the other.
+std::mutex g_chain_mutex;
+cudaEvent_t g_chain_event[64] = {};
+
+const char* chain_begin(cudaStream_t stream, int dev)
+{
+    std::lock_guard<std::mutex> lock(g_chain_mutex);
+    cudaEvent_t& ev = g_chain_event[dev & 63];
+    if (!ev) {
+        if (cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) return cudaGetErrorString(e);
+        return nullptr;
+    }
+    cudaError_t e = cudaStreamWaitEvent(stream, ev, 0);
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* chain_end(cudaStream_t stream, int dev)
+{
+    std::lock_guard<std::mutex> lock(g_chain_mutex);
+    cudaError_t e = cudaEventRecord(g_chain_event[dev & 63], stream);
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 int forward_impl(Net& n, const void* image, bool frames_u8, const float* mean, const float* stdv, int B, int H, int W, float* out,
                  cudaStream_t stream)
 {
@@ -818,6 +921,7 @@ int forward_impl(Net& n, const void* image, bool frames_u8, const float* mean, c
         CL_CUDA(cudaMemcpyAsync(P->in_f32.p, image, (size_t)B * Cin * H * W * sizeof(float), cudaMemcpyDefault, stream));
     }
     // ---- run
+    if (const char* e = chain_begin(stream, dev)) return fail(-2, "cl_net_forward: %s", e);
     cudaGraphExec_t& g = frames_u8 ? P->graph_frames : P->graph;
     bool& warm = frames_u8 ? P->warm_frames : P->warm;
     if (n.use_graph && !n.profiling && !P->graph_failed && warm && !g) {
@@ -846,6 +950,7 @@ int forward_impl(Net& n, const void* image, bool frames_u8, const float* mean, c
         if (const char* e = run_ops(*P, frames_u8, stream)) return fail(-2, "cl_net_forward: %s", e);
         warm = true;
     }
+    if (const char* e = chain_end(stream, dev)) return fail(-2, "cl_net_forward: %s", e);
     // ---- hand the result over
     const size_t out_bytes = (size_t)B * P->out_C * P->out_H * P->out_W * sizeof(float);
     if (out && out != P->out.p) {
@@ -869,6 +974,7 @@ extern "C" int cl_net_create(const cl_net_desc* desc, cl_net** out)
     if (desc->precision < 1 || desc->precision > 3) return fail(-1, "cl_net_create: precision must be 1 (fp16x1), 2 (fp16+fp8) or 3 (fp16x3)");
     std::unique_ptr<Net> n(new Net);
     cudaGetDevice(&n->device);
+    if (cudaDeviceGetAttribute(&n->sms, cudaDevAttrMultiProcessorCount, n->device) != cudaSuccess) n->sms = 148;
     n->precision = desc->precision;
     n->terms = desc->precision == 1 ? 1 : 2;
     n->relu_after_add = desc->relu_after_add != 0;
@@ -876,6 +982,10 @@ extern "C" int cl_net_create(const cl_net_desc* desc, cl_net** out)
     n->fp8_1x1 = !(env && env[0] == '0');
     env = getenv("CROSSLOC_B200_NET_GRAPH");
     n->use_graph = !(env && env[0] == '0');
+    env = getenv("CROSSLOC_B200_FUSE_GN");
+    n->fuse_gn = !(env && env[0] == '0');
+    env = getenv("CROSSLOC_B200_DYNAMIC_TILES");
+    n->dynamic_tiles = !(env && env[0] == '0');
     auto idx_ok = [&](int i) { return i >= 0 && i < desc->n_layers; };
     for (int i = 0; i < desc->n_layers; i++) {
         const cl_net_layer& s = desc->layers[i];

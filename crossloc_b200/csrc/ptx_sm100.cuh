@@ -56,6 +56,54 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
+// Non-blocking probe: true when the phase with the given parity has completed.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// Same as mbar_wait with cluster-scope acquire: pairs with data a peer CTA wrote into this CTA's shared memory
+// (st.shared::cluster) before its release.cluster arrive.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (uint32_t spin = 0;; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((spin & 255u) == 255u && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+// arrive (release at cluster scope) on this CTA's own barrier
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+// 32-bit store into the shared memory of CTA `cta` of the cluster (same offset as `addr` in this CTA)
+__device__ __forceinline__ void st_shared_remote_u32(uint32_t addr, uint32_t cta, uint32_t value)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.u32 [ra], %2;\n\t}\n"
+        ::"r"(addr), "r"(cta), "r"(value)
+        : "memory");
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m)
 {

@@ -17,7 +17,7 @@ _c = ctypes
 MAX_BLOCK_CONVS = 4
 BLOCK_KINDS = {'residual': 0, 'residual_skip': 1, 'plain': 2}
 PRECISIONS = {'fp16x1': 1, 'fp16+fp8': 2, 'fp16x3': 3}
-OP_KINDS = {0: 'memset', 1: 'stem', 2: 'conv', 3: 'gn_apply', 4: 'head', 5: 'duc_head', 6: 'raw_stats', 7: 'frames', 8: 'fork'}
+OP_KINDS = {0: 'memset', 1: 'stem', 2: 'conv', 3: 'gn_apply', 4: 'head', 5: 'duc_head', 6: 'raw_stats', 7: 'frames', 8: 'fork', 9: 'conv_fused'}
 
 
 class NetLayer(_c.Structure):

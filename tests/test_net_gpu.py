@@ -163,7 +163,67 @@ def test_profile_mode_lists_every_launch():
         again = net(x)
     assert rel_l2(prof_out, base) < 2e-6 and rel_l2(again, base) < 2e-6
     kinds = [r[0] for r in rows]
-    assert kinds.count('stem') == 2 and kinds.count('head') == 1 and kinds.count('conv') == 18
+    assert kinds.count('stem') == 2 and kinds.count('head') == 1 and kinds.count("conv") == 14
     assert all(r[4] == 3 for r in rows) and sum(r[3] for r in rows) > 0
     convs = [r for r in rows if r[0] == 'conv']
     assert convs[0][1] == (32, 64, 3, 2) and convs[0][2] == 2.0 * 2 * 16 * 24 * 64 * 32 * 9
+
+
+def _fresh_runtime_output(net, x, env):
+    """Forward through a NEW cl_net handle created under the given environment switches (read at cl_net_create)."""
+    import os
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        net._runtime = None
+        with torch.no_grad():
+            outs = [net(x) for _ in range(3)]   # eager, graph, graph
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        net._runtime = None
+    for o in outs[1:]:
+        assert rel_l2(o, outs[0]) < 2e-6
+    return outs[0]
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 256, 384), (1, 3, 480, 720), (3, 3, 200, 312)])
+def test_fused_groupnorm_epilogue_equals_two_pass_path(shape):
+    """Sizes where the CTA-pair kernel runs: GroupNorm / ReLU / residual merge in the convolution epilogue (accumulators
+    wait in tensor memory for the image statistics, dynamic tile scheduler) vs the raw tensor + gn_apply passes, with
+    static and with dynamic tile scheduling, and vs plain fp32 torch."""
+    torch.manual_seed(31)
+    net = nets.TransPoseNet(torch.tensor([1.0, -2.0, 0.5]), False, False, 1, 1, 3, 1).eval().to(DEV)
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(7)).to(DEV)
+    fused = _fresh_runtime_output(net, x, {'CROSSLOC_B200_FUSE_GN': '1', 'CROSSLOC_B200_DYNAMIC_TILES': '1'})
+    two_pass_dyn = _fresh_runtime_output(net, x, {'CROSSLOC_B200_FUSE_GN': '0', 'CROSSLOC_B200_DYNAMIC_TILES': '1'})
+    two_pass_static = _fresh_runtime_output(net, x, {'CROSSLOC_B200_FUSE_GN': '0', 'CROSSLOC_B200_DYNAMIC_TILES': '0'})
+    with torch.no_grad():
+        ref = net.forward_reference(x)
+    assert rel_l2(two_pass_dyn, two_pass_static) < 2e-6
+    assert rel_l2(fused, two_pass_static) < 5e-6
+    assert rel_l2(fused[:, :3], ref[:, :3]) < 1e-4
+
+
+def test_fused_epilogue_vanilla_network_and_many_small_images():
+    """No GroupNorm (vanilla Network: nothing to wait for) and a batch whose images are smaller than a tile (a 128-row
+    tile spans several images: per-image publication counts)."""
+    torch.manual_seed(32)
+    net = nets.Network(torch.tensor([1.0, 2.0, 3.0]), False).eval().to(DEV)
+    x = torch.rand(2, 1, 256, 320, device=DEV)
+    fused = _fresh_runtime_output(net, x, {'CROSSLOC_B200_FUSE_GN': '1'})
+    plain = _fresh_runtime_output(net, x, {'CROSSLOC_B200_FUSE_GN': '0'})
+    with torch.no_grad():
+        ref = net.forward_reference(x)
+    assert rel_l2(fused, plain) < 5e-6 and rel_l2(fused, ref) < 1e-4
+    torch.manual_seed(33)
+    net2 = nets.TransPoseNet(torch.zeros(3), False, False, 0, 1, 3, 1).eval().to(DEV)
+    y = torch.rand(40, 3, 48, 64, device=DEV)      # 6 x 8 cells: padded plane of 80 rows, 40 images -> 25 tiles
+    fused = _fresh_runtime_output(net2, y, {'CROSSLOC_B200_FUSE_GN': '1'})
+    plain = _fresh_runtime_output(net2, y, {'CROSSLOC_B200_FUSE_GN': '0'})
+    with torch.no_grad():
+        ref = net2.forward_reference(y)
+    assert rel_l2(fused, plain) < 5e-6 and rel_l2(fused[:, :3], ref[:, :3]) < 1e-4
