@@ -84,6 +84,8 @@ struct ConvIgemmParams {
     const __half* res;
     long long res_lo_rows;
     int* unit_done;
+    __half* out16;
+    uint8_t* out8;
 };
 
 // returns nullptr on success, else a static error string

@@ -512,8 +512,8 @@ __device__ __forceinline__ bool fused_unit_complete(const ConvIgemmParams& p, in
 // Phase 2: normalise the warp's 32 rows straight from tensor memory, ReLU, residual merge, split into the consumer's
 // operand planes (fp16 hi / lo, e4m3 hi / lo) and store them with TMA.  Border rows are written as zeros: the planes
 // are the zero-bordered input of the next convolution.
-__device__ __forceinline__ void fused_phase2(const ConvIgemmParams& p, const ConvOutMaps* maps, uint32_t taddr, int n0, int lane,
-                                             bool valid, int image, int r0, int m, uint32_t stage_base, float2* tab)
+__device__ __forceinline__ void fused_phase2(const ConvIgemmParams& p, uint32_t taddr, int n0, int lane, bool valid, int image,
+                                             int r0, int m, float2* tab)
 {
     // ---- (mean, 1/sigma) of the tile's groups for the (at most two) images of this slice
     const int plane = p.Hp * p.Wp;
@@ -540,13 +540,24 @@ __device__ __forceinline__ void fused_phase2(const ConvIgemmParams& p, const Con
     }
     const int which = (valid && image != img0) ? 1 : 0;
     const int gshift = p.group_ch ? 31 - __clz(p.group_ch) : 0;
-    const uint32_t s_hi = stage_base, s_lo = stage_base + 2048u, s_h8 = stage_base + 4096u, s_l8 = stage_base + 5120u;
+    const bool add_res = p.res != nullptr && valid;
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        const int c = n0 + c0;
+        // residual stream first: its L2 latency hides behind the TMEM load and the normalisation
+        uint4 rh[4], rl[4];
+        if (add_res) {
+            const uint4* ph = reinterpret_cast<const uint4*>(p.res + (size_t)m * p.Cout + c);
+            const uint4* pl = reinterpret_cast<const uint4*>(p.res + ((size_t)m + (size_t)p.res_lo_rows) * p.Cout + c);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                rh[j] = __ldg(ph + j);
+                rl[j] = p.res_lo_rows > 0 ? __ldg(pl + j) : make_uint4(0, 0, 0, 0);
+            }
+        }
         uint32_t u[32];
         ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
         ptx::tmem_ld_wait();
         float v[32];
-        const int c = n0 + c0;
         {
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
 #pragma unroll
@@ -577,16 +588,12 @@ __device__ __forceinline__ void fused_phase2(const ConvIgemmParams& p, const Con
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.res && valid) {
+        if (add_res) {
             // res_hi + res_lo first, then the sum is added: the rounding order of gn_apply_kernel
-            const uint4* rh = reinterpret_cast<const uint4*>(p.res + (size_t)m * p.Cout + c);
-            const uint4* rl = reinterpret_cast<const uint4*>(p.res + ((size_t)m + (size_t)p.res_lo_rows) * p.Cout + c);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint4 hq = __ldg(rh + j);
-                const uint4 lq = p.res_lo_rows > 0 ? __ldg(rl + j) : make_uint4(0, 0, 0, 0);
-                const __half2* hh = reinterpret_cast<const __half2*>(&hq);
-                const __half2* ll = reinterpret_cast<const __half2*>(&lq);
+                const __half2* hh = reinterpret_cast<const __half2*>(&rh[j]);
+                const __half2* ll = reinterpret_cast<const __half2*>(&rl[j]);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const float2 a = __half22float2(hh[k]), bq = __half22float2(ll[k]);
@@ -599,15 +606,13 @@ __device__ __forceinline__ void fused_phase2(const ConvIgemmParams& p, const Con
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
         }
-        if (!valid) {
+        if (valid) {   // border rows of the planes stay zero (they are never written by anyone)
+        // Straight from registers to the planes: every lane owns 32 consecutive channels of its pixel row (64 contiguous
+        // bytes per fp16 plane, 32 per e4m3 plane).  No shared-memory staging, nothing to wait for between chunks.
+        __half* o_hi = p.out16 + (size_t)m * p.Cout + c;
+        __half* o_lo = o_hi + (size_t)p.Mp * p.Cout;
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = 0.f;
-        }
-        // the staging buffers of the previous chunk must have been read by their TMA stores
-        if (lane == 0) ptx::tma_store_wait_read<0>();
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; j++) {   // 8 channels -> one 16-byte chunk of the hi and of the lo plane (64-byte rows, SWIZZLE_64B)
+        for (int j = 0; j < 4; j++) {
             __align__(16) __half h[8];
             __align__(16) __half l[8];
 #pragma unroll
@@ -615,15 +620,14 @@ __device__ __forceinline__ void fused_phase2(const ConvIgemmParams& p, const Con
                 h[k] = __float2half_rn(v[8 * j + k]);
                 l[k] = __float2half_rn(v[8 * j + k] - __half2float(h[k]));
             }
-            const uint32_t off = (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
-            const uint4 hv = *reinterpret_cast<const uint4*>(h), lv = *reinterpret_cast<const uint4*>(l);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_hi + off), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
-            if (p.out_terms == 2)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_lo + off), "r"(lv.x), "r"(lv.y), "r"(lv.z), "r"(lv.w) : "memory");
+            *reinterpret_cast<uint4*>(o_hi + 8 * j) = *reinterpret_cast<const uint4*>(h);
+            if (p.out_terms == 2) *reinterpret_cast<uint4*>(o_lo + 8 * j) = *reinterpret_cast<const uint4*>(l);
         }
         if (p.has_out8) {
+            uint8_t* o_h8 = p.out8 + (size_t)m * p.Cout + c;
+            uint8_t* o_l8 = o_h8 + (size_t)p.Mp * p.Cout;
 #pragma unroll
-            for (int j = 0; j < 2; j++) {   // 16 channels -> one 16-byte chunk of each e4m3 plane (32-byte rows, no swizzle)
+            for (int j = 0; j < 2; j++) {
                 __align__(16) __nv_fp8x2_storage_t h8[8];
                 __align__(16) __nv_fp8x2_storage_t l8[8];
 #pragma unroll
@@ -633,23 +637,12 @@ __device__ __forceinline__ void fused_phase2(const ConvIgemmParams& p, const Con
                     h8[k] = __nv_cvt_float2_to_fp8x2(make_float2(a0 * kAct8HiScale, a1 * kAct8HiScale), __NV_SATFINITE, __NV_E4M3);
                     l8[k] = __nv_cvt_float2_to_fp8x2(make_float2((x0 - a0) * kAct8LoScale, (x1 - a1) * kAct8LoScale), __NV_SATFINITE, __NV_E4M3);
                 }
-                const uint32_t off = (uint32_t)lane * 32u + (uint32_t)(j << 4);
-                const uint4 hv = *reinterpret_cast<const uint4*>(h8), lv = *reinterpret_cast<const uint4*>(l8);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_h8 + off), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_l8 + off), "r"(lv.x), "r"(lv.y), "r"(lv.z), "r"(lv.w) : "memory");
+                *reinterpret_cast<uint4*>(o_h8 + 16 * j) = *reinterpret_cast<const uint4*>(h8);
+                *reinterpret_cast<uint4*>(o_l8 + 16 * j) = *reinterpret_cast<const uint4*>(l8);
             }
         }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && r0 < p.Mp) {
-            ptx::tma_store_2d(&maps->hi, s_hi, c, r0);      // rows >= Mp are clipped by the TMA unit
-            if (p.out_terms == 2) ptx::tma_store_2d(&maps->lo, s_lo, c, r0);
-            if (p.has_out8) {
-                ptx::tma_store_2d(&maps->hi8, s_h8, c, r0);
-                ptx::tma_store_2d(&maps->lo8, s_l8, c, r0);
-            }
-            ptx::tma_store_commit();
         }
+        __syncwarp();   // reconverge before the next warp-collective tcgen05.ld
     }
 }
 
@@ -767,8 +760,10 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 // A tile is only claimed once the pair has an accumulator for it (the tile two claims ago is drained): a
                 // cluster never sits on tiles it cannot start, so whatever is claimed anywhere in the grid gets accumulated
                 // and published without waiting for anyone else -- the progress argument of the fused epilogue.
-                const int as = local % p.accum_stages;
-                ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), ((uint32_t)(local / p.accum_stages) & 1u) ^ 1u);
+                if (FUSED) {
+                    const int as = local % p.accum_stages;
+                    ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), ((uint32_t)(local / p.accum_stages) & 1u) ^ 1u);
+                }
                 ptx::mbar_wait(ptx::smem_u32(&sched_empty[slot]), phase ^ 1u);   // every consumer has read this slot's last content
                 int t = atomicAdd(p.tile_counter, 1);
                 if (t >= num_tiles) t = -1;
@@ -956,7 +951,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             ptx::tc_fence_after();
             // (mean, 1/sigma) table of this warp: the 2 KB of its staging area that phase 2 leaves unused
             float2* tab = reinterpret_cast<float2*>(smem_raw + (stage_base + 6144u - ptx::smem_u32(smem_raw)));
-            fused_phase2(p, &outMaps, taddr, n0, lane, valid, image, m0 + q * 32, m, stage_base, tab);
+            fused_phase2(p, taddr, n0, lane, valid, image, m0 + q * 32, m, tab);
             release(pend_as);
             pend_tile = -1;
         };
@@ -1141,6 +1136,8 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
         p.gamma = d.gamma; p.beta = d.beta; p.eps = d.eps;
         p.res = d.res; p.res_lo_rows = d.res_lo_rows;
         p.unit_done = d.unit_done;
+        p.out16 = d.out16;
+        p.out8 = d.out8;
         const size_t plane16 = (size_t)d.Mp * d.Cout;
         if (!make_tensor_map(&plan->out.hi, d.out16, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 2))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the fp16 output plane";

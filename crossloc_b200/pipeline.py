@@ -9,6 +9,8 @@ frames, with the coordinate map kept in HBM between the network and the solver (
 `result()` expose the same thing as a two-deep software pipeline so that the host-to-device copy of
 the next batch overlaps the kernels of the current one.
 """
+import os
+
 import torch
 
 from . import _lib, dsac
@@ -52,7 +54,7 @@ class Localizer:
         self._copy_stream = torch.cuda.Stream(self.device)
         self.solver_stream = torch.cuda.Stream(self.device)
         self.solver_done = None   # event recorded after the last LAUNCHED solve; wait on it before reading poses
-        self.defer_solve = defer_solve
+        self.defer_solve = defer_solve and os.environ.get('CROSSLOC_B200_DEFER_SOLVE', '1') != '0'
         self.after_solve = None   # optional callable(pose) run on the solver stream right behind every solve (pose gather)
         self._deferred = None
         self._slots = [None, None]
