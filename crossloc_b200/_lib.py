@@ -28,6 +28,12 @@ SIGNATURES = {
         _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _i32p, _c.c_int,
         _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p,
         _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p]),
+    'cl_conv_igemm_fp4': (_c.c_int, [
+        _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _i32p,
+        _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+        _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'cl_pack_conv_fp4': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p, _c.c_void_p,
+                                    _c.c_void_p]),
     'cl_conv_wgrad_pf': (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                     _c.c_int, _i32p, _i32p, _c.c_int, _c.c_float, _c.c_void_p, _c.c_int, _c.c_void_p,
                                     _c.c_void_p]),
@@ -49,6 +55,11 @@ SIGNATURES = {
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
         _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,
         _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
+    'cl_gn_apply_fp4': (_c.c_int, [
+        _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+        _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+        _c.c_void_p, _c.c_void_p]),
     'cl_pf_groupnorm': (_c.c_int, [
         _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_float,
         _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),

@@ -57,6 +57,43 @@ extern "C" int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo
     return finish(kFn, cl::conv_igemm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 
+extern "C" int cl_conv_igemm_fp4(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int Cin, const void* weights,
+                                 int Cout, int num_taps, const int32_t* tap_a_row, int Mp, int Hp, int Wp, int group_ch,
+                                 float out_scale, float* raw, const float* bias, double* stats, const void* act4,
+                                 int64_t a4_total_rows, int64_t a4_lo_rows, const void* act_sf, const void* weights4,
+                                 const void* w_sf, void* cuda_stream)
+{
+    static const char* kFn = "cl_conv_igemm_fp4";
+    NEED_DEV(act); NEED_DEV(weights); NEED_DEV(raw); NEED_DEV(bias);
+    NEED_DEV(act4); NEED_DEV(act_sf); NEED_DEV(weights4); NEED_DEV(w_sf);
+    if (group_ch) NEED_DEV(stats);
+    if (!tap_a_row) return cl::fail(-1, "%s: tap_a_row must not be NULL", kFn);
+    if (num_taps < 1 || num_taps > 9) return cl::fail(-1, "%s: num_taps=%d out of range", kFn, num_taps);
+    if (Mp <= 0 || Hp < 3 || Wp < 3 || Mp % (Hp * Wp) != 0)
+        return cl::fail(-1, "%s: Mp=%d is not a whole number of %dx%d planes", kFn, Mp, Hp, Wp);
+    cl::ConvIgemmDesc d{};
+    d.act = act; d.a_total_rows = a_total_rows; d.a_lo_rows = a_lo_rows; d.Cin = Cin; d.weights = weights;
+    d.Cout = Cout; d.num_taps = num_taps;
+    for (int i = 0; i < num_taps; i++) d.tap_a_row[i] = tap_a_row[i];
+    d.nterms = 4; d.Mp = Mp; d.Hp = Hp; d.Wp = Wp; d.group_ch = group_ch; d.out_scale = out_scale;
+    d.raw = raw; d.bias = bias; d.stats = stats;
+    d.act4 = act4; d.a4_total_rows = a4_total_rows; d.a4_lo_rows = a4_lo_rows;
+    d.act_sf = static_cast<const uint32_t*>(act_sf);
+    d.weights4 = weights4; d.w_sf = static_cast<const uint32_t*>(w_sf);
+    d.corr_scale = cl::kCorrScale;
+    d.cluster = 2;   // this mode exists in the CTA-pair kernel only
+    return finish(kFn, cl::conv_igemm_launch(d, static_cast<cudaStream_t>(cuda_stream)));
+}
+
+extern "C" int cl_pack_conv_fp4(const float* w, int Cout, int Cin, int num_taps, float scale, void* weights4, void* w_sf,
+                                void* cuda_stream)
+{
+    static const char* kFn = "cl_pack_conv_fp4";
+    NEED_DEV(w); NEED_DEV(weights4); NEED_DEV(w_sf);
+    return finish(kFn, cl::pack_conv_fp4_launch(w, Cout, Cin, num_taps, scale, static_cast<uint8_t*>(weights4),
+                                                static_cast<uint32_t*>(w_sf), static_cast<cudaStream_t>(cuda_stream)));
+}
+
 extern "C" int cl_nchw_to_pf(const float* x, const float* scale, void* out, int B, int C, int H, int W, int phases,
                              void* cuda_stream)
 {
@@ -110,6 +147,18 @@ extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int gro
                            const float* gamma2, const float* beta2, int relu_outer, void* out, int out_phases,
                            int out_terms, void* out8, int out_C, int out_c0, void* cuda_stream)
 {
+    return cl_gn_apply_fp4(raw, B, H, W, C, group_ch, stats, gamma, beta, eps, relu_inner, add_kind, res, res_lo_rows, raw2,
+                           stats2, gamma2, beta2, relu_outer, out, out_phases, out_terms, out8, out_C, out_c0, nullptr,
+                           nullptr, cuda_stream);
+}
+
+extern "C" int cl_gn_apply_fp4(const float* raw, int B, int H, int W, int C, int group_ch, const double* stats,
+                               const float* gamma, const float* beta, float eps, int relu_inner, int add_kind,
+                               const void* res, int64_t res_lo_rows, const float* raw2, const double* stats2,
+                               const float* gamma2, const float* beta2, int relu_outer, void* out, int out_phases,
+                               int out_terms, void* out8, int out_C, int out_c0, void* out4, void* out_sf,
+                               void* cuda_stream)
+{
     static const char* kFn = "cl_gn_apply";
     NEED_DEV(raw); NEED_DEV(out);
     if (group_ch) { NEED_DEV(stats); NEED_DEV(gamma); NEED_DEV(beta); }
@@ -125,6 +174,8 @@ extern "C" int cl_gn_apply(const float* raw, int B, int H, int W, int C, int gro
     d.out_phases = out_phases; d.out_terms = out_terms; d.out8 = static_cast<uint8_t*>(out8);
     d.out_C = out_C; d.out_c0 = out_c0;
     if (out8) NEED_DEV(out8);
+    if (out4) { NEED_DEV(out4); NEED_DEV(out_sf); }
+    d.out4 = static_cast<uint8_t*>(out4); d.out_sf = static_cast<uint32_t*>(out_sf);
     return finish(kFn, cl::gn_apply_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 

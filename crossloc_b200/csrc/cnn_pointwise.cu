@@ -8,6 +8,7 @@
 //   conv1 + norm1 + relu                   :189-190, 231                 -> stem_kernel
 //   fc3, += mean, exp(hardtanh())          :349-358                      -> head_kernel
 #include <cuda_fp16.h>
+#include <cuda_fp4.h>
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
@@ -56,6 +57,48 @@ __device__ __forceinline__ void fp8_store8(uint8_t* hi_ptr, uint8_t* lo_ptr, con
     }
     *reinterpret_cast<uint2*>(hi_ptr) = *reinterpret_cast<const uint2*>(h);
     *reinterpret_cast<uint2*>(lo_ptr) = *reinterpret_cast<const uint2*>(l);
+}
+
+// Block-scaled e2m1 planes of the fp16 + fp4 convolution mode.  The 32 lanes of a warp hold the 256 channels of one
+// pixel (8 each): one power-of-two scale per plane and warp, chosen so that the block maximum lands in (3, 6] -- the
+// top binade of e2m1 -- and stored as a ue8m0 byte.  Returns the scale word (lo, lo, hi, hi) in every lane.
+__device__ __forceinline__ uint32_t ue8m0_for(float amax)
+{
+    // smallest e with amax <= 6 * 2^e:  amax = m * 2^ex, m in [1, 2)  ->  e = ex - 2 (m <= 1.5) or ex - 1
+    const uint32_t bits = __float_as_uint(amax);
+    int sf = (int)(bits >> 23) - 2 + ((bits & 0x7FFFFFu) > 0x400000u ? 1 : 0);
+    return amax > 0.f ? (uint32_t)(sf < 1 ? 1 : sf) : 127u;
+}
+
+__device__ __forceinline__ uint32_t fp4_pack8(const float (&x)[8], float inv)
+{
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        out |= (uint32_t)__nv_cvt_float2_to_fp4x2(make_float2(x[2 * j] * inv, x[2 * j + 1] * inv), __NV_E2M1, cudaRoundNearest) << (8 * j);
+    return out;
+}
+
+__device__ __forceinline__ uint32_t fp4_store8(uint8_t* hi_ptr, uint8_t* lo_ptr, const float (&v)[8])
+{
+    float hi[8], lo[8];
+    float mh = 0.f, ml = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        hi[j] = __half2float(__float2half_rn(v[j]));
+        lo[j] = v[j] - hi[j];
+        mh = fmaxf(mh, fabsf(hi[j]));
+        ml = fmaxf(ml, fabsf(lo[j]));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, off));
+        ml = fmaxf(ml, __shfl_xor_sync(0xffffffffu, ml, off));
+    }
+    const uint32_t sh = ue8m0_for(mh), sl = ue8m0_for(ml);
+    *reinterpret_cast<uint32_t*>(hi_ptr) = fp4_pack8(hi, __uint_as_float((254u - sh) << 23));
+    *reinterpret_cast<uint32_t*>(lo_ptr) = fp4_pack8(lo, __uint_as_float((254u - sl) << 23));
+    return sl | (sl << 8) | (sh << 16) | (sh << 24);
 }
 
 // One work item = 8 consecutive channels of one interior pixel; every thread handles kGnUnroll items per
@@ -170,6 +213,11 @@ __device__ __forceinline__ void gn_finish(const GnApplyDesc& d, const GnLane& t,
     const size_t oc = (size_t)d.out_C, o0 = (size_t)d.out_c0 + c;
     split_store8(d.out + orow * oc + o0, d.out + (orow + olo) * oc + o0, v, d.out_terms == 2);
     if (d.out8) fp8_store8(d.out8 + orow * oc + o0, d.out8 + (orow + olo) * oc + o0, v);
+    if (d.out4) {   // the warp's 32 lanes share the pixel (C % 256 == 0): warp-collective, `live` is warp-uniform
+        const size_t half_c = (size_t)d.C / 2;
+        const uint32_t word = fp4_store8(d.out4 + orow * half_c + c / 2, d.out4 + (orow + olo) * half_c + c / 2, v);
+        if ((c & 255) == 0) d.out_sf[(size_t)(c >> 8) * olo + orow] = word;
+    }
 }
 
 template <int ADD_KIND>
@@ -649,6 +697,32 @@ int sm_count()
     return sms;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Filter planes of the fp16 + fp4 convolution mode: e2m1 [2][tap][Cout][Cin / 2] = fp4(w_hi), fp4(w_lo) with one
+// ue8m0 scale per (tap, output channel, 256 input channels) and plane; the scale words (hi, hi, lo, lo) are stored in
+// the 32-row interleave tcgen05.cp copies into tensor memory.  One warp per (tap, output channel, 256-channel block).
+__global__ void __launch_bounds__(256) pack_conv_fp4_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, float scale,
+                                                            uint8_t* __restrict__ w4, uint32_t* __restrict__ w_sf)
+{
+    const int lane = threadIdx.x & 31;
+    const int kgroups = Cin / 256;
+    const long long units = (long long)taps * Cout * kgroups;
+    const size_t plane_bytes = (size_t)taps * Cout * (Cin / 2);
+    for (long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const int kg = (int)(u % kgroups);
+        const int co = (int)((u / kgroups) % Cout);
+        const int tap = (int)(u / ((long long)kgroups * Cout));
+        const int ci = kg * 256 + lane * 8;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = w[((size_t)co * Cin + ci + j) * taps + tap] * scale;
+        const size_t byte = ((size_t)tap * Cout + co) * (Cin / 2) + ci / 2;
+        const uint32_t word = fp4_store8(w4 + byte, w4 + plane_bytes + byte, v);   // (lo, lo, hi, hi)
+        if (lane == 0)
+            w_sf[((size_t)(tap * kgroups + kg) * (Cout / 128) + co / 128) * 128 + (co & 31) * 4 + ((co & 127) >> 5)] = (word >> 16) | (word << 16);
+    }
+}
+
 const char* last_error()
 {
     cudaError_t e = cudaGetLastError();
@@ -668,6 +742,8 @@ const char* gn_apply_launch(const GnApplyDesc& desc, cudaStream_t stream)
     if (d.out_phases != 1 && d.out_phases != 4) return "gn_apply: out_phases must be 1 or 4";
     if (d.add_kind == 1 && d.out_phases != 1) return "gn_apply: residual add needs a same-resolution output";
     if (d.out8 && d.out_phases != 1) return "gn_apply: e4m3 planes are only produced for same-resolution outputs";
+    if (d.out4 && (d.out_phases != 1 || d.C % 256 != 0 || d.out_C != d.C || !d.out_sf))
+        return "gn_apply: e2m1 planes need a same-resolution, full-width output with C % 256 == 0 and a scale buffer";
     const long long total = (long long)d.B * d.H * d.W * (d.C / 8);
     if (total == 0) return nullptr;
     if (total >= (1ll << 31)) return "gn_apply: tensor too large for 32-bit item indices";
@@ -682,6 +758,16 @@ const char* gn_apply_launch(const GnApplyDesc& desc, cudaStream_t stream)
     if (d.add_kind == 0) gn_apply_kernel<0><<<(unsigned)blocks, kGnThreads, smem, stream>>>(d);
     else if (d.add_kind == 1) gn_apply_kernel<1><<<(unsigned)blocks, kGnThreads, smem, stream>>>(d);
     else gn_apply_kernel<2><<<(unsigned)blocks, kGnThreads, smem, stream>>>(d);
+    return last_error();
+}
+
+const char* pack_conv_fp4_launch(const float* w, int Cout, int Cin, int taps, float scale, uint8_t* w4, uint32_t* w_sf, cudaStream_t stream)
+{
+    if (Cin % 256 != 0 || Cout % 128 != 0 || taps < 1) return "pack_conv_fp4: Cin % 256 == 0 and Cout % 128 == 0 required";
+    const long long units = (long long)taps * Cout * (Cin / 256);
+    long long blocks = (units + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_conv_fp4_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w, Cout, Cin, taps, scale, w4, w_sf);
     return last_error();
 }
 

@@ -29,11 +29,17 @@ struct ConvIgemmDesc {
     int Cout;
     int num_taps;
     int tap_a_row[9];       // activation row shift of every tap (phase offset included)
-    int nterms;             // 1 (single fp16 pass), 2 (fp16 + e4m3 corrections) or 3 (fp16x3 split)
+    int nterms;             // 1 (single fp16 pass), 2 (fp16 + e4m3 corrections), 3 (fp16x3 split) or 4 (fp16 + block-scaled e2m1 corrections)
     const void* act8;       // nterms == 2: e4m3 PF matrix, plane 0 = fp8(a * 2^2), plane 1 = fp8((a - a_hi) * 2^14)
     int64_t a8_total_rows, a8_lo_rows;
     const void* weights8;   // nterms == 2: e4m3 [2][tap][Cout][Cin]: fp8(w_hi), fp8(w_lo * 2^12)
     float corr_scale;       // 2^-14: scale of the correction accumulator
+    // nterms == 4 (CTA-pair kernel, Cin % 256 == 0): the two correction products as kind::mxf4 MMAs (4x the fp16 rate).
+    const void* act4;       // e2m1 PF matrix [2][a4_lo_rows][Cin / 2] (two values per byte, even channel in the low nibble):
+    int64_t a4_total_rows, a4_lo_rows;   // plane 0 = fp4(a_hi / 2^s_hi), plane 1 = fp4((a - a_hi) / 2^s_lo)
+    const uint32_t* act_sf; // [Cin / 256][a4_lo_rows] ue8m0 scales of one pixel row and 256-channel block: bytes (lo, lo, hi, hi)
+    const void* weights4;   // e2m1 [2][tap][Cout][Cin / 2]: fp4(w_hi), fp4(w_lo), scaled per (tap, output channel, 256-channel block)
+    const uint32_t* w_sf;   // [tap][Cin / 256][Cout / 128][128]: bytes (hi, hi, lo, lo); word l * 4 + j belongs to output channel 32 j + l
     int cluster;            // CTAs sharing a weight tile by TMA multicast (0 = default 2; 1, 2 or 4)
     int Mp, Hp, Wp;         // output rows (B * Hp * Wp) and padded plane size
     int group_ch;           // GroupNorm channels per group (0: no statistics)
@@ -76,6 +82,10 @@ struct ConvIgemmParams {
     int num_stages, accum_stages;
     uint32_t a_bytes, w_bytes, stage_bytes;
     int* tile_counter;
+    // fp16 + fp4 mode
+    int a4_lo_rows, kgroups;
+    const uint32_t* act_sf;
+    const uint32_t* w_sf;
     // fused GroupNorm epilogue
     int fuse, H, W, B, relu_inner, relu_outer, out_terms, has_out8;
     const float* gamma;
@@ -102,7 +112,7 @@ struct alignas(64) ConvIgemmPlan {
     ConvIgemmParams p;
     size_t smem;
     int grid, cluster;
-    int variant;            // bit 2: fused GroupNorm epilogue, bit 1: CTA-pair kernel, bit 0: 64-channel k-blocks
+    int variant;            // bit 2: fused GroupNorm epilogue, bit 1: CTA-pair kernel, bit 0: 64-channel k-blocks; 8: CTA pairs with fp4 corrections
 };
 const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan);
 const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream);
@@ -186,8 +196,15 @@ struct GnApplyDesc {
     uint8_t* out8;          // nullable: e4m3 planes [2][B*(H+2)*(W+2)][C] for a consumer in fp16 + fp8 mode
     int out_C;              // channels of the destination matrices (>= C: the output may be a channel slice), 0 = C
     int out_c0;             // first destination channel
+    // nullable: block-scaled e2m1 planes for a consumer in fp16 + fp4 mode (out_phases == 1, C % 256 == 0, no channel slice):
+    uint8_t* out4;          // [2][B*(H+2)*(W+2)][C / 2]: fp4(hi / 2^s_hi), fp4((x - hi) / 2^s_lo), even channel in the low nibble
+    uint32_t* out_sf;       // [C / 256][B*(H+2)*(W+2)]: ue8m0 bytes (s_lo, s_lo, s_hi, s_hi) of the pixel's 256-channel block
 };
 const char* gn_apply_launch(const GnApplyDesc& d, cudaStream_t stream);
+
+// OIHW fp32 filter x scale -> e2m1 planes [2][tap][Cout][Cin / 2] (fp4(w_hi), fp4(w_lo)) and their scale words
+// [tap][Cin / 256][Cout / 128][128] as ConvIgemmDesc::weights4 / w_sf expect them
+const char* pack_conv_fp4_launch(const float* w, int Cout, int Cin, int taps, float scale, uint8_t* w4, uint32_t* w_sf, cudaStream_t stream);
 
 // ---------------------------------------------------------------- GroupNorm / ReLU / residual-merge backward (training)
 struct GnBwdSrc {

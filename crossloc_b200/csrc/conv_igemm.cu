@@ -1018,6 +1018,372 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA-pair kernel with block-scaled FP4 corrections (nterms == 4, "fp16 + fp4").  Same tile, pipeline and protocol as
+// conv_igemm_pair_kernel in fp16 + fp8 mode, except that pass 0 issues the two correction products as kind::mxf4 MMAs
+// (e2m1 operands, K = 64 per instruction, four times the fp16 rate: 1.5 instead of 2 fp16-MMA equivalents per product;
+// tools/emulate_precision.py: 1.5e-4 relative on the coordinate map, against 1.07e-3 of a single fp16 pass).
+//   * A stage of pass 0 holds 256 input channels of the four e2m1 planes (128-byte rows, same 64 KB as an fp16 stage).
+//   * Scales: one ue8m0 exponent per (row, 256 channels) for each plane -- the emulation shows no difference between
+//     32- and 512-channel blocks, the corrections only need ~3 bits -- stored twice so that both 32-element blocks of an
+//     instruction read the same value.  The activation word of a pixel row is (lo, lo, hi, hi), the weight word of an
+//     output channel (hi, hi, lo, lo): product a_lo * w_hi uses scale bytes 0-1, a_hi * w_lo bytes 2-3 of the same words.
+//     Warp 3 of each CTA moves them global -> shared (the tap shift makes the pixel-row order of a tile unknown to any
+//     fixed tiling, so the 32-row interleave tcgen05.cp expects is done here); the MMA thread copies them into tensor
+//     memory (tcgen05.cp, in order with the MMAs) right before the stage's instructions.
+//   * The corrections carry their true scale (no 2^14, no scale-input-d): pass 1 simply keeps accumulating.
+//   * Tensor memory: the scale columns do not fit next to two 256-column accumulators, so the second accumulator starts
+//     at column 224 and the scales live in columns 480..511.  The epilogue drains the 32 shared columns first and then
+//     lets the MMA warp start the next tile; the rest of the drain overlaps that tile's MMAs as before.
+constexpr uint32_t kSfStageBytes = 2048;   // per stage: 512 B activation scales, 2 x 512 B weight scales
+constexpr uint32_t kAcc1Col = 224;
+constexpr uint32_t kSfCol = 480;
+constexpr uint32_t kFp4StagingBytes = 4 * kStageChunkBytes;   // one staging chunk per epilogue warp
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                           const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA4,
+                           const __grid_constant__ CUtensorMap tmW4, const ConvIgemmParams p)
+{
+    constexpr int BK = 64;
+    constexpr int kSwizzle = 128;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t sf_full[kMaxStages];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t ovl_bar;
+    __shared__ __align__(8) uint64_t sched_full[kRing];
+    __shared__ __align__(8) uint64_t sched_empty[kRing];
+    __shared__ int tile_ring[kRing];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sf_base = smem_base + (uint32_t)p.num_stages * p.stage_bytes;
+    const uint32_t crank = ptx::cluster_ctarank();
+    const bool leader = crank == 0;
+    const int cluster_id = (int)ptx::cluster_id_x();
+    const int num_clusters = (int)ptx::cluster_count_x();
+    const int num_tiles = p.super_m * p.tiles_n;
+    const uint32_t w_half = p.w_bytes / 2;
+    const bool dynamic = p.tile_counter != nullptr;
+    const int n4 = p.num_taps * p.kgroups;                    // stages of pass 0 (256 channels of the e2m1 planes each)
+    const int n16 = p.num_taps * p.kblocks_per_tap / 2;       // stages of pass 1 (128 channels of the fp16 planes each)
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmW);
+        ptx::prefetch_tensormap(&tmO);
+        ptx::prefetch_tensormap(&tmA4);
+        ptx::prefetch_tensormap(&tmW4);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.num_stages; s++) {
+            ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&sf_full[s]), 2);     // leader only: the scale loader warp of each CTA
+        }
+        for (int s = 0; s < 2; s++) ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
+        ptx::mbar_init(ptx::smem_u32(&ovl_bar), 8);            // leader only: 4 epilogue warps of each CTA
+        const uint32_t consumers = 2u * (1u + 1u + 4u) + 1u;   // producer, scale loader and epilogue warps of both CTAs, MMA warp
+        for (int s = 0; s < kRing; s++) {
+            ptx::mbar_init(ptx::smem_u32(&sched_full[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&sched_empty[s]), consumers);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc_pair(ptx::smem_u32(&tmem_base_s), kTmemCols);
+        ptx::tmem_relinquish_pair();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    TileFeed feed;
+    feed.next_static = cluster_id;
+    feed.stride = num_clusters;
+    feed.full_bar0 = ptx::smem_u32(&sched_full[0]);
+    feed.empty_bar0 = ptx::smem_u32(&sched_empty[0]);
+    feed.ring0 = ptx::smem_u32(&tile_ring[0]);
+    feed.slot = 0;
+    feed.phase = 0;
+    feed.dynamic = dynamic;
+    feed.leader = leader;
+
+    if (warp == 2) {
+        // ------------------------------------------------------------------ tile scheduler (leader CTA, one thread)
+        if (dynamic && leader && lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (;;) {
+                ptx::mbar_wait(ptx::smem_u32(&sched_empty[slot]), phase ^ 1u);
+                int t = atomicAdd(p.tile_counter, 1);
+                if (t >= num_tiles) t = -1;
+                const uint32_t ring = ptx::smem_u32(&tile_ring[slot]);
+                asm volatile("st.volatile.shared.s32 [%0], %1;\n" ::"r"(ring), "r"(t) : "memory");
+                ptx::st_shared_remote_u32(ring, 1u, (uint32_t)t);
+                const uint32_t fb = ptx::smem_u32(&sched_full[slot]);
+                ptx::mbar_arrive_release_cluster(fb);
+                ptx::mbar_arrive_remote(fb, 1u);
+                if (t < 0) break;
+                if (++slot == kRing) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_pair = 4u * (p.a_bytes + w_half);
+            const int w_rows = p.BN / 2;
+            for (int tile = feed_next(feed, num_tiles); tile >= 0; tile = feed_next(feed, num_tiles)) {
+                const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+                const int n0 = (tile % p.tiles_n) * p.BN;
+                for (int pass = 0; pass < 2; pass++) {
+                    for (int tap = 0; tap < p.num_taps; tap++) {
+                        const int a_row = p.tap_a_row[tap] + m0;
+                        const int w_row = tap * p.w_tap_rows + n0 + (int)crank * w_rows;
+                        const int steps = pass == 0 ? p.kgroups : p.kblocks_per_tap / 2;
+                        for (int ks = 0; ks < steps; ks++) {
+                            ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                            const uint32_t bar = ptx::smem_u32(&full_bar[stage]);
+                            const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                            const uint32_t sw = sa + 2u * p.a_bytes;
+                            if (leader) ptx::mbar_expect_tx(bar, tx_pair);
+                            if (pass == 0) {
+                                ptx::tma_load_2d_pair(sa, &tmA4, bar, ks * 128, p.a4_lo_rows + a_row);        // a_lo4
+                                ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA4, bar, ks * 128, a_row);            // a_hi4
+                                ptx::tma_load_2d_pair(sw, &tmW4, bar, ks * 128, w_row);                        // w_hi4
+                                ptx::tma_load_2d_pair(sw + w_half, &tmW4, bar, ks * 128, p.w_lo_rows + w_row); // w_lo4
+                            } else {
+                                const int kb = 2 * ks;
+                                ptx::tma_load_2d_pair(sa, &tmA, bar, kb * BK, a_row);
+                                ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA, bar, (kb + 1) * BK, a_row);
+                                ptx::tma_load_2d_pair(sw, &tmW, bar, kb * BK, w_row);
+                                ptx::tma_load_2d_pair(sw + w_half, &tmW, bar, (kb + 1) * BK, w_row);
+                            }
+                            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ scale-factor loader (both CTAs, whole warp)
+        int stage = 0;
+        uint32_t phase = 0;
+        const int sf_rows = p.a4_lo_rows;
+        const int nblocks = p.Cout / 128;
+        for (;;) {
+            int tile = 0;
+            if (lane == 0) tile = feed_next(feed, num_tiles);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile < 0) break;
+            const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+            const int n0 = (tile % p.tiles_n) * p.BN;
+            for (int tap = 0; tap < p.num_taps; tap++) {
+                const int a_row = p.tap_a_row[tap] + m0;
+                for (int kg = 0; kg < p.kgroups; kg++) {
+                    // lane l collects the words of rows l, l + 32, l + 64, l + 96 of the tile: one 16-byte row of the
+                    // 32 x 128-bit block tcgen05.cp broadcasts to the four lane quarters
+                    uint4 wa;
+                    {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int r = a_row + 32 * j + lane;
+                            w[j] = (r >= 0 && r < sf_rows) ? __ldg(p.act_sf + (size_t)kg * sf_rows + r) : 0u;
+                        }
+                        wa = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    const uint4* wb = reinterpret_cast<const uint4*>(p.w_sf + ((size_t)(tap * p.kgroups + kg) * nblocks + n0 / 128) * 128);
+                    const uint4 b0 = __ldg(wb + lane), b1 = __ldg(wb + 32 + lane);
+                    ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                    const uint32_t dst = sf_base + (uint32_t)stage * kSfStageBytes + (uint32_t)lane * 16u;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(wa.x), "r"(wa.y), "r"(wa.z), "r"(wa.w) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 512u), "r"(b0.x), "r"(b0.y), "r"(b0.z), "r"(b0.w) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 1024u), "r"(b1.x), "r"(b1.y), "r"(b1.z), "r"(b1.w) : "memory");
+                    ptx::fence_proxy_async_smem();   // tcgen05.cp reads through the async proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (leader) ptx::mbar_arrive_release_cluster(ptx::smem_u32(&sf_full[stage]));
+                        else ptx::mbar_arrive_remote(ptx::smem_u32(&sf_full[stage]), 0u);
+                    }
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+            // pass 1 has no scales; stay in step with the ring (never more than one phase ahead of the MMA warp)
+            for (int i = 0; i < n16; i++) {
+                ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint32_t idesc = ptx::make_idesc_f16(2 * kBlockM, p.BN);
+            const uint32_t idesc4a = ptx::make_idesc_mxf4(2 * kBlockM, p.BN, 0u, 0u);   // a_lo4 * w_hi4: scale bytes 0-1
+            const uint32_t idesc4b = ptx::make_idesc_mxf4(2 * kBlockM, p.BN, 2u, 2u);   // a_hi4 * w_lo4: scale bytes 2-3
+            int stage = 0, local = 0;
+            uint32_t phase = 0, sf_parity = 0;
+            for (;; local++) {
+                int tile = 0;
+                if (lane == 0) tile = feed_next(feed, num_tiles);
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+                if (tile < 0) break;
+                const int as = local & 1;
+                if (local > 0) {
+                    // the previous tile's epilogue has drained the columns both accumulators share (and, before that,
+                    // everything of the tile that used this accumulator last)
+                    ptx::mbar_wait(ptx::smem_u32(&ovl_bar), (uint32_t)(local - 1) & 1u);
+                    ptx::tc_fence_after();
+                }
+                const uint32_t tmem_d = tmem_base + (as ? kAcc1Col : 0u);
+                for (int i = 0; i < n4; i++) {
+                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                    ptx::mbar_wait_cluster(ptx::smem_u32(&sf_full[stage]), (sf_parity >> stage) & 1u);
+                    sf_parity ^= 1u << stage;
+                    ptx::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a4lo = smem_base + (uint32_t)stage * p.stage_bytes, a4hi = a4lo + p.a_bytes;
+                        const uint32_t w4hi = a4lo + 2u * p.a_bytes, w4lo = w4hi + w_half;
+                        const uint32_t sfs = sf_base + (uint32_t)stage * kSfStageBytes;
+                        const uint32_t sfa = tmem_base + kSfCol + (uint32_t)(i & 1) * 16u, sfb = sfa + 4u;
+                        ptx::tmem_cp_sf_pair(sfa, ptx::make_sf_desc(sfs));
+                        ptx::tmem_cp_sf_pair(sfb, ptx::make_sf_desc(sfs + 512u));
+                        ptx::tmem_cp_sf_pair(sfb + 4u, ptx::make_sf_desc(sfs + 1024u));
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(a4lo + k * 32);
+                            const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(w4hi + k * 32);
+                            ptx::mma_mxf4_ss_pair(tmem_d, da, db, idesc4a, (i | k) != 0 ? 1u : 0u, sfa, sfb);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(a4hi + k * 32);
+                            const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(w4lo + k * 32);
+                            ptx::mma_mxf4_ss_pair(tmem_d, da, db, idesc4b, 1u, sfa, sfb);
+                        }
+                        ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 0x3);
+                    }
+                    __syncwarp();
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
+                for (int i = 0; i < n16; i++) {
+                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                    ptx::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        const uint32_t sw = sa + 2u * p.a_bytes;
+#pragma unroll
+                        for (int half = 0; half < 2; half++) {
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++) {
+                                const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(sa + half * p.a_bytes + k * 32);
+                                const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(sw + half * w_half + k * 32);
+                                ptx::mma_f16_ss_pair(tmem_d, da, db, idesc, 1u);
+                            }
+                        }
+                        ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 0x3);
+                        if (i == n16 - 1) ptx::mma_commit_pair(ptx::smem_u32(&tfull_bar[as]), 0x3);
+                    }
+                    __syncwarp();
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        const int q = warp & 3;
+        const int plane = p.Hp * p.Wp;
+        const uint32_t sbuf = sf_base + (uint32_t)p.num_stages * kSfStageBytes + (uint32_t)q * kStageChunkBytes;
+        for (int local = 0;; local++) {
+            int tile = 0;
+            if (lane == 0) tile = feed_next(feed, num_tiles);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile < 0) break;
+            const int as = local & 1;
+            const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
+            const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+            const int n0 = (tile % p.tiles_n) * p.BN;
+            const int m = m0 + q * 32 + lane;
+            int image = 0;
+            bool valid = false;
+            if (m < p.Mp) {
+                image = m / plane;
+                const int r = m - image * plane;
+                const int y = r / p.Wp, x = r - y * p.Wp;
+                valid = y >= 1 && y <= p.Hp - 2 && x >= 1 && x <= p.Wp - 2;
+            }
+            ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as ? kAcc1Col : 0u);
+            const int nchunks = p.BN / 32;
+            for (int idx = 0; idx < nchunks; idx++) {
+                // the chunk in tensor-memory columns 224..255 goes first: it is the only one the other accumulator shares
+                const int c0 = as ? idx * 32 : (idx == 0 ? (nchunks - 1) * 32 : (idx - 1) * 32);
+                uint32_t u[32];
+                ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
+                ptx::tmem_ld_wait();
+                if (idx == 0) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (leader) ptx::mbar_arrive(ptx::smem_u32(&ovl_bar));
+                        else ptx::mbar_arrive_remote(ptx::smem_u32(&ovl_bar), 0u);
+                    }
+                }
+                float f[32];
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 bb = __ldg(b4 + j);
+                    f[4 * j + 0] = __uint_as_float(u[4 * j + 0]) * p.out_scale + bb.x;
+                    f[4 * j + 1] = __uint_as_float(u[4 * j + 1]) * p.out_scale + bb.y;
+                    f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) * p.out_scale + bb.z;
+                    f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) * p.out_scale + bb.w;
+                }
+                if (lane == 0) ptx::tma_store_wait_read<0>();   // single staging chunk per warp: the previous store has read it
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t dst = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                                 "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                                 : "memory");
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(&tmO, sbuf, n0 + c0, m0 + q * 32);
+                    ptx::tma_store_commit();
+                }
+                if (p.group_ch) {
+                    const int first_group = (n0 + c0) / p.group_ch;
+                    switch (p.group_ch) {
+                        case 2: stats_chunk<2>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 4: stats_chunk<4>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 8: stats_chunk<8>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 16: stats_chunk<16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        default: break;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+        }
+        if (lane == 0) ptx::tma_store_wait<0>();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1063,7 +1429,9 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
     if (d.Cin % 32 != 0) return "conv_igemm: Cin must be a multiple of 32";
     if (d.Cout % 64 != 0) return "conv_igemm: Cout must be a multiple of 64";
     if (d.num_taps < 1 || d.num_taps > 9) return "conv_igemm: 1..9 taps";
-    if (d.nterms < 1 || d.nterms > 3) return "conv_igemm: nterms must be 1 (fp16), 2 (fp16 + fp8 corrections) or 3 (fp16x3)";
+    if (d.nterms < 1 || d.nterms > 4) return "conv_igemm: nterms must be 1 (fp16), 2 (fp16 + fp8 corrections), 3 (fp16x3) or 4 (fp16 + fp4 corrections)";
+    if (d.nterms == 4 && (d.Cin % 256 != 0 || d.Cout % 256 != 0 || !d.act4 || !d.act_sf || !d.weights4 || !d.w_sf || d.fuse))
+        return "conv_igemm: the fp16 + fp4 mode needs Cin % 256 == 0, Cout % 256 == 0, the e2m1 operand planes with their scales, and no fused epilogue";
     if (d.nterms == 2 && (d.Cin % 64 != 0 || !d.act8 || !d.weights8))
         return "conv_igemm: the fp16 + fp8 mode needs Cin % 64 == 0 and the e4m3 operand planes";
     if (d.group_ch != 0 && d.group_ch != 2 && d.group_ch != 4 && d.group_ch != 8 && d.group_ch != 16)
@@ -1114,8 +1482,20 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
     // fp16 + fp8 mode keeps two accumulators (main, corrections) per tile in the single-CTA kernel; the pair kernel
     // folds the corrections with scale-input-d and needs one
     if (d.nterms == 2 && d.corr_scale != 1.0f / (float)(1 << kCorrShift)) return "conv_igemm: corr_scale must be 2^-14";
+    if (d.nterms == 4 && !pair) return "conv_igemm: the fp16 + fp4 mode exists in the CTA-pair kernel only";
     p.accum_stages = (d.nterms == 2 && !pair ? 4 : 2) * BN <= (int)kTmemCols ? 2 : 1;
     plan->smem = (size_t)p.num_stages * p.stage_bytes + kEpilogueStagingBytes + 1024;
+    if (d.nterms == 4) {
+        const int budget4 = 227 * 1024 - 2048 - (int)kFp4StagingBytes;
+        p.num_stages = budget4 / (int)(p.stage_bytes + kSfStageBytes);
+        if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+        if (p.num_stages < 2) return "conv_igemm: tile does not fit two pipeline stages";
+        plan->smem = (size_t)p.num_stages * (p.stage_bytes + kSfStageBytes) + kFp4StagingBytes + 1024;
+        p.a4_lo_rows = (int)d.a4_lo_rows;
+        p.kgroups = d.Cin / 256;
+        p.act_sf = d.act_sf;
+        p.w_sf = d.w_sf;
+    }
     p.tile_counter = pair ? d.tile_counter : nullptr;
     p.fuse = 0;
     if (d.fuse) {
@@ -1162,6 +1542,13 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
         return "conv_igemm: cuTensorMapEncodeTiled failed for the output matrix";
     plan->tmA8 = plan->tmA;
     plan->tmW8 = plan->tmW;
+    if (d.nterms == 4) {
+        // e2m1 planes as byte matrices: 128-byte rows = 256 channels per box
+        if (!make_tensor_map(&plan->tmA8, d.act4, (uint64_t)d.a4_total_rows, (uint64_t)d.Cin / 2, kBlockM, 128, 1))
+            return "conv_igemm: cuTensorMapEncodeTiled failed for the e2m1 activation matrix";
+        if (!make_tensor_map(&plan->tmW8, d.weights4, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin / 2, BN / 2, 128, 1))
+            return "conv_igemm: cuTensorMapEncodeTiled failed for the e2m1 weight matrix";
+    }
     if (d.nterms == 2) {
         // the pair kernel streams the e4m3 planes in 128-byte rows (2 * BK channels per box)
         const int bk8 = pair ? 2 * BK : BK;
@@ -1177,7 +1564,7 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
     if (clusters > num_super) clusters = num_super;
     plan->grid = clusters * cluster;
     plan->cluster = cluster;
-    plan->variant = (p.fuse ? 4 : 0) + (pair ? 2 : 0) + (BK == 64 ? 1 : 0);
+    plan->variant = d.nterms == 4 ? 8 : (p.fuse ? 4 : 0) + (pair ? 2 : 0) + (BK == 64 ? 1 : 0);
     return nullptr;
 }
 
@@ -1197,10 +1584,10 @@ const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream)
     cfg.numAttrs = 1;
 
     // the opt-in shared-memory size is a per-function, per-device attribute: raise it once to the maximum any plan uses
-    static bool attr_set[64][8] = {};
+    static bool attr_set[64][16] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    bool& done = attr_set[dev & 63][plan.variant & 7];
+    bool& done = attr_set[dev & 63][plan.variant & 15];
     const int max_smem = 227 * 1024 - 1024;   // dynamic part only: the kernels also hold ~300 bytes of static shared memory
     cudaError_t e = cudaSuccess;
 #define CL_LAUNCH(KERNEL, ...)                                                                              \
@@ -1209,6 +1596,7 @@ const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream)
         if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, KERNEL, __VA_ARGS__);                            \
     } while (0)
     switch (plan.variant) {
+        case 8: CL_LAUNCH(conv_igemm_pair_fp4_kernel, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p); break;
         case 7: CL_LAUNCH((conv_igemm_pair_kernel<64, true>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
         case 6: CL_LAUNCH((conv_igemm_pair_kernel<32, true>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
         case 3: CL_LAUNCH((conv_igemm_pair_kernel<64, false>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;

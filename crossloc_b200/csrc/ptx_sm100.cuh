@@ -285,6 +285,37 @@ __device__ __forceinline__ void mma_f8_ss_pair(uint32_t tmem_d, uint64_t desc_a,
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- block-scaled FP4 (kind::mxf4: e2m1 operands, one ue8m0 scale per 32 elements along K, K = 64 per instruction).
+// Instruction descriptor (block-scaled form): e2m1 x e2m1 -> fp32, both operands K-major, ue8m0 scales; a_sf / b_sf =
+// byte offset (0 or 2) of the instruction's two scale bytes inside the 32-bit scale column of tensor memory.
+__device__ __host__ __forceinline__ uint32_t make_idesc_mxf4(int M, int N, uint32_t a_sf, uint32_t b_sf)
+{
+    return (b_sf << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24) | (a_sf << 29);
+}
+// D[tmem] (+)= (A * 2^sfa)[smem] * (B * 2^sfb)[smem]^T across the CTA pair; sfa / sfb are tensor-memory column addresses
+// of the scale factors (row r of the operand: lane r % 32, column r / 32, replicated in the four lane quarters)
+__device__ __forceinline__ void mma_mxf4_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                                 uint32_t tmem_sfa, uint32_t tmem_sfb)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+// Shared-memory descriptor of one 32-row x 16-byte scale-factor block (512 contiguous bytes, no swizzle).
+__device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+// shared memory -> tensor memory, 32 rows x 128 bits broadcast to the four lane quarters (4 columns); with cta_group::2
+// each CTA of the pair copies from its own shared memory into its own tensor memory.  Ordered with the MMAs of the
+// issuing thread (same pipe).
+__device__ __forceinline__ void tmem_cp_sf_pair(uint32_t tmem_addr, uint64_t sdesc)
+{
+    asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;\n" ::"r"(tmem_addr), "l"(sdesc) : "memory");
+}
 __device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t cta_mask)
 {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"

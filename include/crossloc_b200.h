@@ -111,6 +111,26 @@ int cl_conv_igemm(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int 
                   int64_t a8_total_rows, int64_t a8_lo_rows, const void* weights8, void* cuda_stream);
 
 /*
+ * The same convolution in fp16 + fp4 mode (CTA-pair kernel only): a_hi*w_hi in fp16, the two correction products
+ * (each 2^-11 of the result) as block-scaled e2m1 MMAs (tcgen05 kind::mxf4, four times the fp16 rate) -- 1.5 instead
+ * of 2 fp16-MMA equivalents per product.  Cin % 256 == 0, Cout % 256 == 0.
+ *   act4      e2m1 PF matrix [2][a4_lo_rows][Cin/2], two values per byte (even channel in the low nibble):
+ *             plane 0 = fp4(a_hi / 2^s_hi), plane 1 = fp4((a - a_hi) / 2^s_lo), as cl_gn_apply_fp4 writes them
+ *   act_sf    uint32 [Cin/256][a4_lo_rows]: ue8m0 exponent bytes (s_lo, s_lo, s_hi, s_hi) of a pixel row's 256-channel block
+ *   weights4, w_sf   as cl_pack_conv_fp4 writes them
+ */
+int cl_conv_igemm_fp4(const void* act, int64_t a_total_rows, int64_t a_lo_rows, int Cin, const void* weights, int Cout,
+                      int num_taps, const int32_t* tap_a_row, int Mp, int Hp, int Wp, int group_ch, float out_scale,
+                      float* raw, const float* bias, double* stats, const void* act4, int64_t a4_total_rows,
+                      int64_t a4_lo_rows, const void* act_sf, const void* weights4, const void* w_sf,
+                      void* cuda_stream);
+/* OIHW fp32 filter (x scale, a power of two) -> weights4 e2m1 [2][num_taps][Cout][Cin/2] = fp4(w_hi), fp4(w_lo), one
+ * ue8m0 scale per (tap, output channel, 256 input channels) and plane; w_sf uint32 [num_taps][Cin/256][Cout/128][128],
+ * bytes (s_hi, s_hi, s_lo, s_lo), word l*4 + j of a 128-channel block = output channel 32*j + l (tcgen05.cp order). */
+int cl_pack_conv_fp4(const float* w, int Cout, int Cin, int num_taps, float scale, void* weights4, void* w_sf,
+                     void* cuda_stream);
+
+/*
  * Convolution weight gradient (training step) on padded-flat operands, the layout
  * of cl_conv_igemm / cl_gn_backward:
  *   dw[tap][co][ci] += out_scale * sum over rows r < Mp of grad[r][co] * act[tap_phase[tap]][r + tap_shift[tap]][ci]
@@ -193,6 +213,14 @@ int cl_gn_apply(const float* raw, int B, int H, int W, int C, int group_ch, cons
                 const float* beta, float eps, int relu_inner, int add_kind, const void* res, int64_t res_lo_rows,
                 const float* raw2, const double* stats2, const float* gamma2, const float* beta2, int relu_outer,
                 void* out, int out_phases, int out_terms, void* out8, int out_C, int out_c0, void* cuda_stream);
+
+/* cl_gn_apply that also writes the block-scaled e2m1 planes of a consumer in fp16 + fp4 mode (nullable out4 / out_sf;
+ * out_phases 1, C % 256 == 0, full-width destination): out4 [2][B*(H+2)*(W+2)][C/2], out_sf [C/256][B*(H+2)*(W+2)]. */
+int cl_gn_apply_fp4(const float* raw, int B, int H, int W, int C, int group_ch, const double* stats, const float* gamma,
+                    const float* beta, float eps, int relu_inner, int add_kind, const void* res, int64_t res_lo_rows,
+                    const float* raw2, const double* stats2, const float* gamma2, const float* beta2, int relu_outer,
+                    void* out, int out_phases, int out_terms, void* out8, int out_C, int out_c0, void* out4,
+                    void* out_sf, void* cuda_stream);
 
 /*
  * GroupNorm (no ReLU) of a padded-flat fp16 hi/lo activation [2][B*(H+2)*(W+2)][C]: mlr_norm of the MLR model

@@ -107,6 +107,109 @@ def test_conv_igemm_fp16_plus_fp8_corrections(shape, cluster, monkeypatch):
     assert torch.allclose(stats[:, :, 1], (g * g).sum(-1), rtol=1e-3)
 
 
+# ---- fp16 + fp4 mode: block-scaled e2m1 correction products (tcgen05 kind::mxf4)
+_E2M1 = [0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0]
+
+
+def _decode_fp4(bytes_, sf_bytes):
+    """uint8 [rows][C/2] + ue8m0 exponent byte per (row, 256 channels) -> fp32 [rows][C]."""
+    lut = torch.tensor(_E2M1 + [-v for v in _E2M1], dtype=torch.float32, device=bytes_.device)
+    lo, hi = bytes_ & 0xF, bytes_ >> 4
+    vals = torch.stack([lut[lo.long()], lut[hi.long()]], -1).reshape(bytes_.size(0), -1)   # even channel = low nibble
+    scale = torch.exp2(sf_bytes.to(torch.float32) - 127.0)                                 # [rows][C/256]
+    return vals * scale.repeat_interleave(256, dim=1)
+
+
+def _pf_raw(x):
+    b, c, h, w = x.shape
+    r = torch.zeros(b, h + 2, w + 2, c, device=x.device)
+    r[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    return r.reshape(-1, c).contiguous()
+
+
+def make_fp4_planes(x):
+    """Operand planes of an activation through the production producer (cl_gn_apply_fp4 as an identity pass)."""
+    lib = _lib.load()
+    b, c, h, w = x.shape
+    rows = b * (h + 2) * (w + 2)
+    out = torch.zeros(2 * rows, c, dtype=torch.float16, device=DEV)
+    out4 = torch.zeros(2 * rows, c // 2, dtype=torch.uint8, device=DEV)
+    out_sf = torch.zeros(c // 256, rows, dtype=torch.int32, device=DEV)
+    raw = _pf_raw(x)
+    _lib.check(lib.cl_gn_apply_fp4(raw.data_ptr(), b, h, w, c, 0, 0, 0, 0, 1e-5, 0, 0, 0, 0, 0, 0, 0, 0, 0, out.data_ptr(), 1, 2,
+                                   0, 0, 0, out4.data_ptr(), out_sf.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return out, out4, out_sf
+
+
+def test_gn_apply_fp4_planes():
+    """e2m1 planes + ue8m0 scales written next to the fp16 planes: decode and compare with the fp16 split."""
+    b, c, h, w = 2, 512, 7, 9
+    torch.manual_seed(3)
+    x = (torch.randn(b, c, h, w, device=DEV) * torch.rand(b, 1, h, w, device=DEV) * 4).relu()
+    out, out4, out_sf = make_fp4_planes(x)
+    rows = b * (h + 2) * (w + 2)
+    assert torch.equal(out, layout.to_pf(x))   # the fp16 planes are unchanged
+    hi, lo = out[:rows].float(), _pf_raw(x) - out[:rows].float()
+    sf = out_sf.view(torch.uint8).reshape(c // 256, rows, 4)
+    assert torch.equal(sf[..., 0], sf[..., 1]) and torch.equal(sf[..., 2], sf[..., 3])
+    for plane, want, byte in ((0, hi, 2), (1, lo, 0)):
+        s = sf[..., byte].t().contiguous()                      # [rows][C/256]
+        got = _decode_fp4(out4[plane * rows:(plane + 1) * rows], s)
+        step = torch.exp2(s.to(torch.float32) - 127.0).repeat_interleave(256, dim=1)
+        assert float(((got - want).abs() / step).max()) <= 1.0 + 1e-6     # widest e2m1 gap (4 .. 6) is two steps
+        blk = want.reshape(rows, c // 256, 256).abs().amax(-1)
+        live = blk > 0
+        ratio = (blk / torch.exp2(s.to(torch.float32) - 127.0))[live]
+        assert float(ratio.max()) <= 6.0 + 1e-5 and float(ratio.min()) > 3.0 - 1e-5   # block maximum in e2m1's top binade
+        assert float((got - want).norm() / want.norm()) < 0.2
+
+
+def run_conv_fp4(x, conv, groups):
+    lib = _lib.load()
+    b, cin, h, w = x.shape
+    pack = PackedConv(conv.weight, conv.bias, 1, 1)
+    geo = _Geometry(b, h, w)
+    act, act4, act_sf = make_fp4_planes(x)
+    taps_n = pack.ksize * pack.ksize
+    w4 = torch.zeros(2 * taps_n * pack.cout, cin // 2, dtype=torch.uint8, device=DEV)
+    w_sf = torch.zeros(taps_n * (cin // 256) * pack.cout, dtype=torch.int32, device=DEV)
+    wsrc = conv.weight.detach().float().contiguous()
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.cl_pack_conv_fp4(wsrc.data_ptr(), pack.cout, cin, taps_n, 1.0 / pack.out_scale, w4.data_ptr(), w_sf.data_ptr(), stream))
+    raw = torch.zeros(geo.Mp, pack.cout, dtype=torch.float32, device=DEV)
+    group_ch = pack.cout // groups if groups else 0
+    stats = torch.zeros(b, max(groups, 1), 2, dtype=torch.float64, device=DEV)
+    taps = _taps(pack, geo)
+    arr = (ctypes.c_int32 * len(taps))(*taps)
+    _lib.check(lib.cl_conv_igemm_fp4(act.data_ptr(), act.size(0), geo.Mp, cin, pack.weights.data_ptr(), pack.cout, len(taps), arr,
+                                     geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale, raw.data_ptr(), pack.bias.data_ptr(),
+                                     stats.data_ptr(), act4.data_ptr(), act4.size(0), geo.Mp, act_sf.data_ptr(), w4.data_ptr(),
+                                     w_sf.data_ptr(), stream))
+    torch.cuda.synchronize()
+    return layout.raw_to_nchw(raw, b, h, w), stats
+
+
+@pytest.mark.parametrize('shape', [(256, 256, 3, 1, 2, 9, 14), (512, 512, 3, 1, 1, 60, 90), (256, 512, 3, 1, 3, 7, 5),
+                                   (512, 512, 1, 1, 2, 9, 14), (512, 512, 3, 1, 4, 60, 90)])
+def test_conv_igemm_fp16_plus_fp4_corrections(shape):
+    """nterms == 4: a_hi*w_hi in fp16, both correction products as block-scaled e2m1 MMAs into the same accumulator."""
+    cin, cout, k, stride, b, h, w = shape
+    torch.manual_seed(cin + cout + k)
+    conv = torch.nn.Conv2d(cin, cout, k, stride, k // 2).to(DEV)
+    x = (torch.randn(b, cin, h, w, device=DEV) * 1.5).relu()
+    with torch.no_grad():
+        ref = conv(x)
+    out, stats = run_conv_fp4(x, conv, 32)
+    err = rel_l2(out, ref)
+    one, _ = run_conv(x, conv, 1, 32)
+    err1 = rel_l2(one, ref)
+    assert err < 0.35 * err1, (err, err1)   # corrections carried with ~2 bits: fp16x1 error x ~0.15
+    assert err < 1.5e-4, err
+    g = ref.double().reshape(b, 32, -1)
+    assert torch.allclose(stats[:, :, 1], (g * g).sum(-1), rtol=2e-3)
+
+
 def test_gn_apply_variants():
     lib = _lib.load()
     b, c, h, w = 2, 256, 9, 13
