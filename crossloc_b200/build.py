@@ -15,7 +15,7 @@ LIB = os.path.join(OUT_DIR, 'libcrossloc_b200.so')
 
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
-COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-ccbin', '/usr/bin/g++']
+COMMON = (["-DCL_DEBUG_TRAP"] if os.environ.get("CL_DEBUG_TRAP") else []) + ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-ccbin', '/usr/bin/g++']
 
 # translation unit -> extra flags.  The pose solver is built without FMA contraction so that its double
 # arithmetic rounds like the reference's x86 build of the same expressions.

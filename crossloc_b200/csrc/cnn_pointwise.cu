@@ -79,7 +79,7 @@ __device__ __forceinline__ uint32_t fp4_pack8(const float (&x)[8], float inv)
     return out;
 }
 
-__device__ __forceinline__ uint32_t fp4_store8(uint8_t* hi_ptr, uint8_t* lo_ptr, const float (&v)[8])
+__device__ __forceinline__ uint32_t fp4_store8(uint8_t* hi_ptr, uint8_t* lo_ptr, const float (&v)[8], bool exact_lo = false)
 {
     float hi[8], lo[8];
     float mh = 0.f, ml = 0.f;
@@ -90,12 +90,18 @@ __device__ __forceinline__ uint32_t fp4_store8(uint8_t* hi_ptr, uint8_t* lo_ptr,
         mh = fmaxf(mh, fabsf(hi[j]));
         ml = fmaxf(ml, fabsf(lo[j]));
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, off));
-        ml = fmaxf(ml, __shfl_xor_sync(0xffffffffu, ml, off));
+    // block maximum over the warp: non-negative floats order like their bit patterns (one redux.sync instead of a butterfly)
+    const uint32_t mh_bits = __reduce_max_sync(0xffffffffu, __float_as_uint(mh));
+    const uint32_t sh = ue8m0_for(__uint_as_float(mh_bits));
+    uint32_t sl;
+    if (exact_lo) {
+        sl = ue8m0_for(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ml))));
+    } else {
+        // |x - fp16(x)| <= half an fp16 ulp of the block maximum = 2^(ex - 11) (2^-25 below the fp16 normal range):
+        // the scale 2^(ex - 13) puts that bound at 4.0, inside e2m1's range, without a second reduction
+        const uint32_t e = mh_bits >> 23;
+        sl = (e < 113u ? 113u : e) - 13u;
     }
-    const uint32_t sh = ue8m0_for(mh), sl = ue8m0_for(ml);
     *reinterpret_cast<uint32_t*>(hi_ptr) = fp4_pack8(hi, __uint_as_float((254u - sh) << 23));
     *reinterpret_cast<uint32_t*>(lo_ptr) = fp4_pack8(lo, __uint_as_float((254u - sl) << 23));
     return sl | (sl << 8) | (sh << 16) | (sh << 24);
@@ -717,7 +723,7 @@ __global__ void __launch_bounds__(256) pack_conv_fp4_kernel(const float* __restr
 #pragma unroll
         for (int j = 0; j < 8; j++) v[j] = w[((size_t)co * Cin + ci + j) * taps + tap] * scale;
         const size_t byte = ((size_t)tap * Cout + co) * (Cin / 2) + ci / 2;
-        const uint32_t word = fp4_store8(w4 + byte, w4 + plane_bytes + byte, v);   // (lo, lo, hi, hi)
+        const uint32_t word = fp4_store8(w4 + byte, w4 + plane_bytes + byte, v, true);   // (lo, lo, hi, hi)
         if (lane == 0)
             w_sf[((size_t)(tap * kgroups + kg) * (Cout / 128) + co / 128) * 128 + (co & 31) * 4 + ((co & 127) >> 5)] = (word >> 16) | (word << 16);
     }

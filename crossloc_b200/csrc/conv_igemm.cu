@@ -410,12 +410,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // ---- dynamic tile scheduling -------------------------------------------------------------------------------
 // With p.tile_counter set, the leader CTA's warp 2 (idle after the TMEM allocation) fetches tile indices from a global
-// counter and publishes them through a four-slot ring that exists in both CTAs of the pair: it writes the index into
+// counter and publishes them through an eight-slot ring that exists in both CTAs of the pair: it writes the index into
 // its own and (st.shared::cluster) the peer's ring, then arrives on `sched_full[slot]` in both.  Every consumer role
 // (producer warp(s), MMA warp, the four epilogue warps of each CTA) reads the slot and arrives on the LEADER's
 // `sched_empty[slot]`.  -1 terminates.  A cluster whose CTAs start late -- SMs still held by another stream's blocks --
 // takes fewer tiles instead of delaying the whole launch by its statically assigned share.
-constexpr int kRing = 4;
+// Ring depth: the consumers of one cluster spread over at most ~6 tiles (the scale loader of the fp4 kernel prefetches up to
+// two short tiles ahead of the MMA warp, the epilogue trails it by one); a consumer that blocks on a slot the scheduler
+// cannot publish yet would stall the pipeline it is part of.
+constexpr int kRing = 8;
 
 struct TileFeed {
     // static mode
@@ -434,7 +437,7 @@ __device__ __forceinline__ int feed_next(TileFeed& f, int num_tiles)
         f.next_static += f.stride;
         return t < num_tiles ? t : -1;
     }
-    ptx::mbar_wait_cluster(f.full_bar0 + 8u * (uint32_t)f.slot, f.phase);
+    ptx::mbar_wait_cluster(f.full_bar0 + 8u * (uint32_t)f.slot, f.phase, 10);
     int t;
     asm volatile("ld.volatile.shared.s32 %0, [%1];\n" : "=r"(t) : "r"(f.ring0 + 4u * (uint32_t)f.slot) : "memory");
     if (f.leader) ptx::mbar_arrive(f.empty_bar0 + 8u * (uint32_t)f.slot);
@@ -1035,7 +1038,9 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 //   * Tensor memory: the scale columns do not fit next to two 256-column accumulators, so the second accumulator starts
 //     at column 224 and the scales live in columns 480..511.  The epilogue drains the 32 shared columns first and then
 //     lets the MMA warp start the next tile; the rest of the drain overlaps that tile's MMAs as before.
-constexpr uint32_t kSfStageBytes = 2048;   // per stage: 512 B activation scales, 2 x 512 B weight scales
+constexpr uint32_t kSfStageBytes = 2048;   // shared memory reserved per pipeline stage for the scale ring below
+constexpr int kSfSlots = 4;                // the scales have their own ring (only pass 0 uses them): a slot = 512 B activation
+constexpr uint32_t kSfSlotBytes = 1536;    // scales + 2 x 512 B weight scales; kSfSlots * kSfSlotBytes <= 3 * kSfStageBytes
 constexpr uint32_t kAcc1Col = 224;
 constexpr uint32_t kSfCol = 480;
 constexpr uint32_t kFp4StagingBytes = 4 * kStageChunkBytes;   // one staging chunk per epilogue warp
@@ -1050,7 +1055,8 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t sf_full[kMaxStages];
+    __shared__ __align__(8) uint64_t sf_full[kSfSlots];
+    __shared__ __align__(8) uint64_t sf_empty[kSfSlots];
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t ovl_bar;
     __shared__ __align__(8) uint64_t sched_full[kRing];
@@ -1070,6 +1076,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const bool dynamic = p.tile_counter != nullptr;
     const int n4 = p.num_taps * p.kgroups;                    // stages of pass 0 (256 channels of the e2m1 planes each)
     const int n16 = p.num_taps * p.kblocks_per_tap / 2;       // stages of pass 1 (128 channels of the fp16 planes each)
+    static_assert(kSfSlots * kSfSlotBytes <= 3 * kSfStageBytes, "scale ring exceeds the shared memory reserved for it");
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -1082,7 +1089,10 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         for (int s = 0; s < p.num_stages; s++) {
             ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
             ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < kSfSlots; s++) {
             ptx::mbar_init(ptx::smem_u32(&sf_full[s]), 2);     // leader only: the scale loader warp of each CTA
+            ptx::mbar_init(ptx::smem_u32(&sf_empty[s]), 1);    // the leader's MMA commit, multicast to both CTAs
         }
         for (int s = 0; s < 2; s++) ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
         ptx::mbar_init(ptx::smem_u32(&ovl_bar), 8);            // leader only: 4 epilogue warps of each CTA
@@ -1120,7 +1130,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             int slot = 0;
             uint32_t phase = 0;
             for (;;) {
-                ptx::mbar_wait(ptx::smem_u32(&sched_empty[slot]), phase ^ 1u);
+                ptx::mbar_wait(ptx::smem_u32(&sched_empty[slot]), phase ^ 1u, 1);
                 int t = atomicAdd(p.tile_counter, 1);
                 if (t >= num_tiles) t = -1;
                 const uint32_t ring = ptx::smem_u32(&tile_ring[slot]);
@@ -1149,7 +1159,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                         const int w_row = tap * p.w_tap_rows + n0 + (int)crank * w_rows;
                         const int steps = pass == 0 ? p.kgroups : p.kblocks_per_tap / 2;
                         for (int ks = 0; ks < steps; ks++) {
-                            ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                            ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u, 2);
                             const uint32_t bar = ptx::smem_u32(&full_bar[stage]);
                             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                             const uint32_t sw = sa + 2u * p.a_bytes;
@@ -1174,52 +1184,66 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
     } else if (warp == 3) {
         // ------------------------------------------------------------------ scale-factor loader (both CTAs, whole warp)
-        int stage = 0;
-        uint32_t phase = 0;
+        // The global loads of a stage's scales run kSfAhead stages ahead of the store into shared memory (a rotating set
+        // of registers): their L2 latency (~1 us) is several times the MMA time of a stage.
+        constexpr int kSfAhead = 4;
+        uint4 qa[kSfAhead], qb0[kSfAhead], qb1[kSfAhead];
+        bool qv[kSfAhead];
         const int sf_rows = p.a4_lo_rows;
         const int nblocks = p.Cout / 128;
-        for (;;) {
-            int tile = 0;
-            if (lane == 0) tile = feed_next(feed, num_tiles);
-            tile = __shfl_sync(0xffffffffu, tile, 0);
-            if (tile < 0) break;
-            const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
-            const int n0 = (tile % p.tiles_n) * p.BN;
-            for (int tap = 0; tap < p.num_taps; tap++) {
-                const int a_row = p.tap_a_row[tap] + m0;
-                for (int kg = 0; kg < p.kgroups; kg++) {
-                    // lane l collects the words of rows l, l + 32, l + 64, l + 96 of the tile: one 16-byte row of the
-                    // 32 x 128-bit block tcgen05.cp broadcasts to the four lane quarters
-                    uint4 wa;
-                    {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const int r = a_row + 32 * j + lane;
-                            w[j] = (r >= 0 && r < sf_rows) ? __ldg(p.act_sf + (size_t)kg * sf_rows + r) : 0u;
-                        }
-                        wa = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                    const uint4* wb = reinterpret_cast<const uint4*>(p.w_sf + ((size_t)(tap * p.kgroups + kg) * nblocks + n0 / 128) * 128);
-                    const uint4 b0 = __ldg(wb + lane), b1 = __ldg(wb + 32 + lane);
-                    ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
-                    const uint32_t dst = sf_base + (uint32_t)stage * kSfStageBytes + (uint32_t)lane * 16u;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(wa.x), "r"(wa.y), "r"(wa.z), "r"(wa.w) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 512u), "r"(b0.x), "r"(b0.y), "r"(b0.z), "r"(b0.w) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 1024u), "r"(b1.x), "r"(b1.y), "r"(b1.z), "r"(b1.w) : "memory");
-                    ptx::fence_proxy_async_smem();   // tcgen05.cp reads through the async proxy
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (leader) ptx::mbar_arrive_release_cluster(ptx::smem_u32(&sf_full[stage]));
-                        else ptx::mbar_arrive_remote(ptx::smem_u32(&sf_full[stage]), 0u);
-                    }
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
-                }
+        int ltap = p.num_taps, lkg = 0, lm0 = 0, ln0 = 0;
+        bool ldone = false;
+        auto load_item = [&](uint4& wa, uint4& b0, uint4& b1) -> bool {
+            if (ldone) return false;
+            if (ltap == p.num_taps) {
+                int tile = 0;
+                if (lane == 0) tile = feed_next(feed, num_tiles);
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+                if (tile < 0) { ldone = true; return false; }
+                lm0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
+                ln0 = (tile % p.tiles_n) * p.BN;
+                ltap = 0;
+                lkg = 0;
             }
-            // pass 1 has no scales; stay in step with the ring (never more than one phase ahead of the MMA warp)
-            for (int i = 0; i < n16; i++) {
-                ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
-                if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+            // lane l collects the words of rows l, l + 32, l + 64, l + 96 of the tile: one 16-byte row of the
+            // 32 x 128-bit block tcgen05.cp broadcasts to the four lane quarters
+            const int a_row = p.tap_a_row[ltap] + lm0;
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int r = a_row + 32 * j + lane;
+                w[j] = (r >= 0 && r < sf_rows) ? __ldg(p.act_sf + (size_t)lkg * sf_rows + r) : 0u;
+            }
+            wa = make_uint4(w[0], w[1], w[2], w[3]);
+            const uint4* wb = reinterpret_cast<const uint4*>(p.w_sf + ((size_t)(ltap * p.kgroups + lkg) * nblocks + ln0 / 128) * 128);
+            b0 = __ldg(wb + lane);
+            b1 = __ldg(wb + 32 + lane);
+            if (++lkg == p.kgroups) { lkg = 0; ++ltap; }
+            return true;
+        };
+#pragma unroll
+        for (int u = 0; u < kSfAhead; u++) qv[u] = load_item(qa[u], qb0[u], qb1[u]);
+        // The scale ring is independent of the operand stages: a slot is handed over per pass-0 stage and released by the
+        // MMA warp's commit, so the loader neither has to follow the stages of pass 1 nor can it be lapped by them.
+        int slot = 0;
+        uint32_t sphase = 0;
+        for (bool more = true; more;) {
+#pragma unroll
+            for (int u = 0; u < kSfAhead; u++) {
+                if (!qv[u]) { more = false; break; }
+                ptx::mbar_wait(ptx::smem_u32(&sf_empty[slot]), sphase ^ 1u, 3);
+                const uint32_t dst = sf_base + (uint32_t)slot * kSfSlotBytes + (uint32_t)lane * 16u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(qa[u].x), "r"(qa[u].y), "r"(qa[u].z), "r"(qa[u].w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 512u), "r"(qb0[u].x), "r"(qb0[u].y), "r"(qb0[u].z), "r"(qb0[u].w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 1024u), "r"(qb1[u].x), "r"(qb1[u].y), "r"(qb1[u].z), "r"(qb1[u].w) : "memory");
+                ptx::fence_proxy_async_smem();   // tcgen05.cp reads through the async proxy
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) ptx::mbar_arrive_release_cluster(ptx::smem_u32(&sf_full[slot]));
+                    else ptx::mbar_arrive_remote(ptx::smem_u32(&sf_full[slot]), 0u);
+                }
+                if (++slot == kSfSlots) { slot = 0; sphase ^= 1u; }
+                qv[u] = load_item(qa[u], qb0[u], qb1[u]);   // the stage kSfAhead further on
             }
         }
     } else if (warp == 1) {
@@ -1229,7 +1253,8 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             const uint32_t idesc4a = ptx::make_idesc_mxf4(2 * kBlockM, p.BN, 0u, 0u);   // a_lo4 * w_hi4: scale bytes 0-1
             const uint32_t idesc4b = ptx::make_idesc_mxf4(2 * kBlockM, p.BN, 2u, 2u);   // a_hi4 * w_lo4: scale bytes 2-3
             int stage = 0, local = 0;
-            uint32_t phase = 0, sf_parity = 0;
+            uint32_t phase = 0, sphase = 0;
+            int slot = 0;
             for (;; local++) {
                 int tile = 0;
                 if (lane == 0) tile = feed_next(feed, num_tiles);
@@ -1239,19 +1264,18 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 if (local > 0) {
                     // the previous tile's epilogue has drained the columns both accumulators share (and, before that,
                     // everything of the tile that used this accumulator last)
-                    ptx::mbar_wait(ptx::smem_u32(&ovl_bar), (uint32_t)(local - 1) & 1u);
+                    ptx::mbar_wait(ptx::smem_u32(&ovl_bar), (uint32_t)(local - 1) & 1u, 5);
                     ptx::tc_fence_after();
                 }
                 const uint32_t tmem_d = tmem_base + (as ? kAcc1Col : 0u);
                 for (int i = 0; i < n4; i++) {
-                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
-                    ptx::mbar_wait_cluster(ptx::smem_u32(&sf_full[stage]), (sf_parity >> stage) & 1u);
-                    sf_parity ^= 1u << stage;
+                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, 6);
+                    ptx::mbar_wait_cluster(ptx::smem_u32(&sf_full[slot]), sphase, 7);
                     ptx::tc_fence_after();
                     if (lane == 0) {
                         const uint32_t a4lo = smem_base + (uint32_t)stage * p.stage_bytes, a4hi = a4lo + p.a_bytes;
                         const uint32_t w4hi = a4lo + 2u * p.a_bytes, w4lo = w4hi + w_half;
-                        const uint32_t sfs = sf_base + (uint32_t)stage * kSfStageBytes;
+                        const uint32_t sfs = sf_base + (uint32_t)slot * kSfSlotBytes;
                         const uint32_t sfa = tmem_base + kSfCol + (uint32_t)(i & 1) * 16u, sfb = sfa + 4u;
                         ptx::tmem_cp_sf_pair(sfa, ptx::make_sf_desc(sfs));
                         ptx::tmem_cp_sf_pair(sfb, ptx::make_sf_desc(sfs + 512u));
@@ -1269,12 +1293,14 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                             ptx::mma_mxf4_ss_pair(tmem_d, da, db, idesc4b, 1u, sfa, sfb);
                         }
                         ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 0x3);
+                        ptx::mma_commit_pair(ptx::smem_u32(&sf_empty[slot]), 0x3);   // the scale slot has been copied and used
                     }
                     __syncwarp();
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                    if (++slot == kSfSlots) { slot = 0; sphase ^= 1u; }
                 }
                 for (int i = 0; i < n16; i++) {
-                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, 8);
                     ptx::tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
@@ -1319,7 +1345,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 const int y = r / p.Wp, x = r - y * p.Wp;
                 valid = y >= 1 && y <= p.Hp - 2 && x >= 1 && x <= p.Wp - 2;
             }
-            ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase);
+            ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase, 9);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as ? kAcc1Col : 0u);
             const int nchunks = p.BN / 32;
@@ -1489,7 +1515,7 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
         const int budget4 = 227 * 1024 - 2048 - (int)kFp4StagingBytes;
         p.num_stages = budget4 / (int)(p.stage_bytes + kSfStageBytes);
         if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
-        if (p.num_stages < 2) return "conv_igemm: tile does not fit two pipeline stages";
+        if (p.num_stages < 3) return "conv_igemm: the fp16 + fp4 tile does not fit three pipeline stages";
         plan->smem = (size_t)p.num_stages * (p.stage_bytes + kSfStageBytes) + kFp4StagingBytes + 1024;
         p.a4_lo_rows = (int)d.a4_lo_rows;
         p.kgroups = d.Cin / 256;

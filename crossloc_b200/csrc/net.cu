@@ -126,7 +126,7 @@ struct Layer {
     // caller-owned sources (re-read by cl_net_update)
     const float *src_w = nullptr, *src_b = nullptr, *src_g = nullptr, *src_be = nullptr;
     // engine-owned device copies
-    DevBuf w32, bias, gamma, beta, w16, w8;
+    DevBuf w32, bias, gamma, beta, w16, w8, w4, wsf;
     int nterms = 3;
     float out_scale = 1.f;
     bool tensor_core = false;   // runs through conv_igemm (everything except the stem and the small heads)
@@ -148,7 +148,7 @@ struct Geometry {
 struct PF {   // one padded-flat activation: fp16 hi / lo planes and (on demand) the e4m3 planes
     const Geometry* geo = nullptr;
     int channels = 0, phases = 1, terms = 2;
-    DevBuf h16, f8;
+    DevBuf h16, f8, f4, sf;   // f4 / sf: block-scaled e2m1 planes and their scale words (fp16 + fp4 consumers)
     int64_t rows16() const { return (int64_t)terms * phases * geo->Mp; }
     int64_t rows8() const { return (int64_t)2 * phases * geo->Mp; }
 };
@@ -217,7 +217,7 @@ struct Plan {
 struct Net {
     int device = 0;
     int sms = 148;
-    int precision = 2;         // 1 fp16x1 | 2 fp16 + fp8 | 3 fp16x3
+    int precision = 2;         // 1 fp16x1 | 2 fp16 + fp8 | 3 fp16x3 | 4 fp16 + fp4 (fp16 + fp8 where a layer cannot)
     int terms = 2;             // fp16 planes per activation
     bool relu_after_add = true;
     bool fp8_1x1 = true;
@@ -252,7 +252,9 @@ namespace {
 int nterms_for(const Net& n, const Layer& L)
 {
     if (n.precision == 1) return 1;
-    if (n.precision == 2 && L.stride == 1 && L.cin % 128 == 0 && L.cin >= 256 && (L.ksize == 3 || (n.fp8_1x1 && L.cin >= 512))) return 2;
+    if ((n.precision == 2 || n.precision == 4) && L.stride == 1 && L.cin % 128 == 0 && L.cin >= 256 &&
+        (L.ksize == 3 || (n.fp8_1x1 && L.cin >= 512)))
+        return n.precision == 4 && L.cin % 256 == 0 && L.cout % 256 == 0 ? 4 : 2;
     return 3;
 }
 
@@ -298,6 +300,13 @@ const char* load_params(Net& n)
         if (cudaError_t e = L.w16.ensure((size_t)planes16 * wcount * sizeof(__half), false)) return cudaGetErrorString(e);
         if (L.nterms == 2)
             if (cudaError_t e = L.w8.ensure((size_t)2 * wcount, false)) return cudaGetErrorString(e);
+        if (L.nterms == 4) {
+            if (cudaError_t e = L.w4.ensure(wcount, false)) return cudaGetErrorString(e);
+            if (cudaError_t e = L.wsf.ensure((size_t)L.taps * (L.cin / 256) * L.cout * sizeof(uint32_t), false)) return cudaGetErrorString(e);
+            if (const char* e = pack_conv_fp4_launch(L.w32.as<float>(), L.cout, L.cin, L.taps, ldexpf(1.0f, ex), L.w4.as<uint8_t>(),
+                                                     L.wsf.as<uint32_t>(), nullptr))
+                return e;
+        }
         size_t blocks = (wcount + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         pack_conv_kernel<<<(unsigned)blocks, 256>>>(L.w32.as<float>(), L.cout, L.cin, L.taps, ldexpf(1.0f, ex), L.w16.as<__half>(),
@@ -372,6 +381,14 @@ struct Builder {
         P.raws[key] = std::move(b);
         return out;
     }
+    bool f4(PF* a)
+    {
+        if (a->f4.p) return true;
+        if (a->phases != 1 || a->channels % 256 != 0) return fail("e2m1 planes need a same-resolution activation with C % 256 == 0");
+        if (cudaError_t e = a->f4.alloc((size_t)a->geo->Mp * a->channels, true)) return fail(cudaGetErrorString(e));
+        if (cudaError_t e = a->sf.alloc((size_t)(a->channels / 256) * a->geo->Mp * sizeof(uint32_t), true)) return fail(cudaGetErrorString(e));
+        return true;
+    }
     double* next_stats() { return P.stats.as<double>() + (size_t)(stat_i++) * P.B * max_groups * 2; }
 
     // activation row shift of every filter tap in the padded-flat layout of the OUTPUT resolution
@@ -420,6 +437,16 @@ struct Builder {
         }
         d.corr_scale = kCorrScale;
         d.cluster = 0;
+        if (L.nterms == 4) {
+            if (!f4(a)) return false;
+            d.act4 = a->f4.p;
+            d.a4_total_rows = (int64_t)2 * g.Mp;
+            d.a4_lo_rows = g.Mp;
+            d.act_sf = a->sf.as<uint32_t>();
+            d.weights4 = L.w4.p;
+            d.w_sf = L.wsf.as<uint32_t>();
+            d.cluster = 2;
+        }
         d.Mp = g.Mp; d.Hp = g.Hp; d.Wp = g.Wp;
         const int gc = L.group_ch();
         const bool fused_stats = igemm_group_ok(gc);
@@ -468,7 +495,7 @@ struct Builder {
     // run with the fused epilogue?  Mirrors the checks of conv_igemm_prepare so that the plan never has to back out.
     bool can_fuse(int li, const Geometry& g) const
     {
-        if (!n.fuse_gn || !n.dynamic_tiles) return false;
+        if (!n.fuse_gn || !n.dynamic_tiles || n.precision == 4) return false;
         const Layer& L = *n.layers[li];
         const int gc = L.group_ch();
         if (!igemm_group_ok(gc)) return false;
@@ -486,7 +513,7 @@ struct Builder {
     struct Merge { PF* res = nullptr; float* raw2 = nullptr; int layer2 = -1; double* stats2 = nullptr; };
 
     bool apply(float* rawbuf, const Geometry& g, int li, double* st, PF* out, bool relu_inner, const Merge& m, bool relu_outer,
-               bool want_lo, bool want8)
+               bool want_lo, int want8)   // want8: bit 0 = e4m3 planes, bit 1 = block-scaled e2m1 planes
     {
         Layer& L = *n.layers[li];
         if (!out || !rawbuf) return false;
@@ -515,8 +542,13 @@ struct Builder {
         d.out = out->h16.as<__half>();
         d.out_phases = out->phases;
         d.out_terms = (want_lo && n.terms == 2) ? 2 : 1;
-        d.out8 = want8 ? f8(out) : nullptr;
-        if (want8 && !d.out8) return false;
+        d.out8 = (want8 & 1) ? f8(out) : nullptr;
+        if ((want8 & 1) && !d.out8) return false;
+        if (want8 & 2) {
+            if (!f4(out)) return false;
+            d.out4 = out->f4.as<uint8_t>();
+            d.out_sf = out->sf.as<uint32_t>();
+        }
         d.out_C = 0; d.out_c0 = 0;
         Op op;
         op.kind = Op::kApply;
@@ -527,14 +559,15 @@ struct Builder {
         return true;
     }
 
-    void planes_for(const std::vector<int>& consumers, bool also_lo, bool& want_lo, bool& want8) const
+    void planes_for(const std::vector<int>& consumers, bool also_lo, bool& want_lo, int& want8) const
     {
-        want8 = false;
+        want8 = 0;
         want_lo = also_lo;
         for (int c : consumers) {
             if (c < 0) continue;
             const Layer& L = *n.layers[c];
-            if (L.nterms == 2) want8 = true;
+            if (L.nterms == 2) want8 |= 1;
+            if (L.nterms == 4) want8 |= 2;
             if (L.nterms == 3) want_lo = true;
         }
     }
@@ -574,7 +607,8 @@ struct Builder {
             PF* out = scratch(L.cout, x, res_in);
             if (!out) return nullptr;
             const bool last = i + 1 == convs.size();
-            bool want_lo, want8;
+            bool want_lo;
+            int want8;
             if (!last) planes_for({convs[i + 1]}, false, want_lo, want8);
             else planes_for(next_readers, true, want_lo, want8);
             const bool merge_raw2 = last && skip && skip->raw2;
@@ -585,7 +619,7 @@ struct Builder {
                 f.relu_inner = true;
                 f.relu_outer = last && outer_relu;
                 f.want_lo = want_lo;
-                f.want8 = want8;
+                f.want8 = want8 != 0;
                 if (!conv(li, x, g3, nullptr, st, &f)) return nullptr;
             } else {
                 float* r = raw(i % 2 ? "r1" : "r0", 3, L.cout);
@@ -664,7 +698,8 @@ struct Builder {
             double* s2 = L.gn_groups ? next_stats() : nullptr;
             if (!conv(li, a, P.geo[level], r, s2)) return false;
             PF* out;
-            bool want_lo = true, want8 = false;
+            bool want_lo = true;
+            int want8 = 0;
             if (level < 3) {
                 out = act("ladder", level + 1, L.cout, 4);
             } else {
@@ -713,13 +748,14 @@ struct Builder {
                     double* s2 = L.gn_groups ? next_stats() : nullptr;
                     PF* out = scratch(L.cout, res, nullptr);
                     if (!out) return false;
-                    bool want_lo, want8;
+                    bool want_lo;
+            int want8;
                     planes_for(i + 1 < blk.convs.size() ? std::vector<int>{blk.convs[i + 1]} : readers, true, want_lo, want8);
                     if (can_fuse(li, g3)) {
                         Fuse f;
                         f.out = out;
                         f.want_lo = want_lo;
-                        f.want8 = want8;
+                        f.want8 = want8 != 0;
                         if (!conv(li, res, g3, nullptr, s2, &f)) return false;
                     } else {
                         float* r = raw("r0", 3, L.cout);
@@ -971,7 +1007,7 @@ extern "C" int cl_net_create(const cl_net_desc* desc, cl_net** out)
     *out = nullptr;
     if (desc->abi_version != CL_NET_ABI_VERSION) return fail(-1, "cl_net_create: abi_version %d, library has %d", desc->abi_version, CL_NET_ABI_VERSION);
     if (desc->n_layers <= 0 || !desc->layers) return fail(-1, "cl_net_create: empty layer table");
-    if (desc->precision < 1 || desc->precision > 3) return fail(-1, "cl_net_create: precision must be 1 (fp16x1), 2 (fp16+fp8) or 3 (fp16x3)");
+    if (desc->precision < 1 || desc->precision > 4) return fail(-1, "cl_net_create: precision must be 1 (fp16x1), 2 (fp16+fp8), 3 (fp16x3) or 4 (fp16+fp4)");
     std::unique_ptr<Net> n(new Net);
     cudaGetDevice(&n->device);
     if (cudaDeviceGetAttribute(&n->sms, cudaDevAttrMultiProcessorCount, n->device) != cudaSuccess) n->sms = 148;

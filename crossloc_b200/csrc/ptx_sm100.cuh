@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
 
 namespace cl {
 namespace ptx {
@@ -38,7 +39,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 }
 // Waits until the phase with the given parity has completed.  The wait is bounded (~2 s of SM clocks):
 // a protocol bug becomes a trap (launch error) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0)
 {
     uint32_t done = 0;
     const long long t0 = clock64();
@@ -52,7 +53,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
-        if ((spin & 255u) == 255u && clock64() - t0 > 4000000000ll) __trap();
+        if ((spin & 255u) == 255u && clock64() - t0 > 4000000000ll) {
+#ifdef CL_DEBUG_TRAP
+            printf("mbar_wait timeout: block %d thread %d site %d bar 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, site, bar, parity);
+            while (clock64() - t0 < 6000000000ll) {}   // let every other stuck waiter report too
+#endif
+            __trap();
+        }
     }
 }
 
@@ -71,7 +78,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
 }
 // Same as mbar_wait with cluster-scope acquire: pairs with data a peer CTA wrote into this CTA's shared memory
 // (st.shared::cluster) before its release.cluster arrive.
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int site = 0)
 {
     uint32_t done = 0;
     const long long t0 = clock64();
@@ -85,7 +92,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
-        if ((spin & 255u) == 255u && clock64() - t0 > 4000000000ll) __trap();
+        if ((spin & 255u) == 255u && clock64() - t0 > 4000000000ll) {
+#ifdef CL_DEBUG_TRAP
+            printf("mbar_wait_cluster timeout: block %d thread %d site %d bar 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, site, bar, parity);
+            while (clock64() - t0 < 6000000000ll) {}
+#endif
+            __trap();
+        }
     }
 }
 // arrive (release at cluster scope) on this CTA's own barrier

@@ -16,7 +16,9 @@ from . import _lib
 _c = ctypes
 MAX_BLOCK_CONVS = 4
 BLOCK_KINDS = {'residual': 0, 'residual_skip': 1, 'plain': 2}
-PRECISIONS = {'fp16x1': 1, 'fp16+fp8': 2, 'fp16x3': 3}
+PRECISIONS = {'fp16x1': 1, 'fp16+fp8': 2, 'fp16x3': 3, 'fp16+fp4': 4}
+# fp16-MMA equivalents issued per product on the large layers
+MMA_EQUIVALENTS = {'fp16x1': 1.0, 'fp16+fp8': 2.0, 'fp16x3': 3.0, 'fp16+fp4': 1.5}
 OP_KINDS = {0: 'memset', 1: 'stem', 2: 'conv', 3: 'gn_apply', 4: 'head', 5: 'duc_head', 6: 'raw_stats', 7: 'frames', 8: 'fork', 9: 'conv_fused'}
 
 
@@ -55,7 +57,7 @@ class NetRuntime:
         self.precision = precision or cnn.PRECISION
         if self.precision not in PRECISIONS:
             raise ValueError('unknown conv precision %r (%s)' % (self.precision, ' | '.join(PRECISIONS)))
-        self.nterms = {'fp16x1': 1, 'fp16x3': 3, 'fp16+fp8': 2}[self.precision]
+        self.nterms = MMA_EQUIVALENTS[self.precision]
         self._handle = None
         self._addresses = None
         self._versions = None

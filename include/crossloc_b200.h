@@ -315,7 +315,7 @@ typedef struct cl_net_block {
 
 typedef struct cl_net_desc {
     int32_t abi_version;          /* CL_NET_ABI_VERSION */
-    int32_t precision;            /* 1 = one fp16 pass (misses the 1e-3 bar), 2 = fp16 + e4m3 corrections (default), 3 = fp16x3 */
+    int32_t precision;            /* 1 = one fp16 pass (misses the 1e-3 bar), 2 = fp16 + e4m3 corrections, 3 = fp16x3, 4 = fp16 + block-scaled e2m1 corrections */
     int32_t relu_after_add;       /* 1: TransPoseNet (ReLU after every residual add), 0: vanilla Network */
     int32_t n_layers;
     const cl_net_layer* layers;

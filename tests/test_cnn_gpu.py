@@ -161,7 +161,10 @@ def test_gn_apply_fp4_planes():
         blk = want.reshape(rows, c // 256, 256).abs().amax(-1)
         live = blk > 0
         ratio = (blk / torch.exp2(s.to(torch.float32) - 127.0))[live]
-        assert float(ratio.max()) <= 6.0 + 1e-5 and float(ratio.min()) > 3.0 - 1e-5   # block maximum in e2m1's top binade
+        if plane == 0:
+            assert float(ratio.max()) <= 6.0 + 1e-5 and float(ratio.min()) > 3.0 - 1e-5   # block maximum in e2m1's top binade
+        else:   # scale derived from the block maximum of the hi plane: half an fp16 ulp of it lands on 4.0
+            assert float(ratio.max()) <= 4.0 + 1e-5 and float(ratio.min()) > 0.9
         assert float((got - want).norm() / want.norm()) < 0.2
 
 
@@ -330,7 +333,7 @@ def test_network_matches_reference_fixture_and_torch(name):
     assert rel_l2(out[:, :k], ref[:, :k]) < 1e-3          # north-star tolerance: 1e-3 relative fp32
     assert rel_l2(out[:, :k], gold[:, :k]) < 1e-3
     assert rel_l2(out, gold) < 1e-3
-    assert rel_l2(out[:, :k], gold[:, :k]) < 1e-4          # what the default fp16 + fp8 scheme actually delivers
+    assert rel_l2(out[:, :k], gold[:, :k]) < 3.3e-4        # the default fp16 + fp4 scheme: a 3x margin on the bar (fp16 + fp8: 3e-5)
     assert float((out[:, :k] - gold[:, :k]).abs().max() / gold[:, :k].abs().max()) < 1e-3
 
 
@@ -352,7 +355,7 @@ def test_network_full_resolution_parity_and_determinism():
     # batch entries are independent: image 1 alone gives the same map
     with torch.no_grad():
         single = net(x[1:2])
-    assert rel_l2(single, out[1:2]) < 2e-5   # e4m3 rounding of the correction operands amplifies last-bit statistics noise
+    assert rel_l2(single, out[1:2]) < 1e-4   # e2m1 rounding of the correction operands amplifies last-bit statistics noise
 
 
 def test_precision_modes():
