@@ -271,6 +271,143 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_apply_kernel(GnApplyDesc d)
     }
 }
 
+// ---- row-wise variant for the wide same-resolution layers (C % 256 == 0, groups of >= 8 channels, full-width output).
+// The generic kernel above spends ~500 instructions per 8-channel item (pixel index divisions, per-item table look-ups,
+// 64-bit address arithmetic for every variant) and is issue bound at 45-60 % of the HBM rate.  Here a block owns one
+// image row: no divisions, the lane's affine parameters AND its group's (mean, 1/sigma) live in registers, a warp walks
+// along x with constant pointer strides (one pixel x 256 channels per step: 1 KB coalesced loads), four pixels in flight.
+// PLANES: bit 0 = e4m3 planes, bit 1 = block-scaled e2m1 planes.  Same arithmetic, bit for bit, as gn_apply_kernel.
+template <int ADD_KIND, int PLANES>
+__global__ void __launch_bounds__(256, 2) gn_apply_rows_kernel(GnApplyDesc d)
+{
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kgroups = d.C >> 8;
+    const int kg = warp % kgroups;
+    const int xstep = 8 / kgroups;   // pixels the block's 8 warps cover per step
+    const int b = blockIdx.x / d.H, y = blockIdx.x - b * d.H;
+    const int c = kg * 256 + lane * 8;
+    const int Wp = d.W + 2;
+    const size_t rows = (size_t)d.B * (d.H + 2) * Wp;
+    float ga[8], be[8], mean = 0.f;
+    float ga2[8], be2[8], mean2 = 0.f;
+    {
+        float rstd = 1.f;
+        if (d.group_ch) {
+            const int groups = d.C / d.group_ch;
+            mean_rstd(d.stats, b, groups, c / d.group_ch, (double)d.group_ch * d.H * d.W, d.eps, mean, rstd);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            ga[j] = d.group_ch ? rstd * __ldg(d.gamma + c + j) : 1.f;
+            be[j] = d.group_ch ? __ldg(d.beta + c + j) : 0.f;
+        }
+        if (ADD_KIND == 2) {
+            float rstd2 = 1.f;
+            const int groups = d.C / d.group_ch;
+            mean_rstd(d.stats2, b, groups, c / d.group_ch, (double)d.group_ch * d.H * d.W, d.eps, mean2, rstd2);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                ga2[j] = rstd2 * __ldg(d.gamma2 + c + j);
+                be2[j] = __ldg(d.beta2 + c + j);
+            }
+        }
+    }
+    // running pointers of the warp's current pixel; one pixel step = xstep rows of the padded-flat matrices
+    const int xw = warp / kgroups;
+    const size_t row_first = ((size_t)b * (d.H + 2) + (y + 1)) * Wp + 1 + xw;
+    const size_t e_first = row_first * d.C + c;
+    const size_t estep = (size_t)xstep * d.C;        // elements per pixel step
+    const size_t lo_off = rows * d.C;                // element distance of the lo planes
+    const float* praw = d.raw + e_first;
+    const __half* pres = ADD_KIND == 1 ? d.res + e_first : nullptr;
+    const size_t res_lo = (size_t)d.res_lo_rows * d.C;
+    const float* praw2 = ADD_KIND == 2 ? d.raw2 + e_first : nullptr;
+    __half* pout = d.out + e_first;
+    uint8_t* pout8 = (PLANES & 1) ? d.out8 + e_first : nullptr;
+    uint8_t* pout4 = (PLANES & 2) ? d.out4 + e_first / 2 : nullptr;
+    uint32_t* psf = (PLANES & 2) ? d.out_sf + (size_t)kg * rows + row_first : nullptr;
+    const bool write_lo = d.out_terms == 2;
+    for (int x0 = xw; x0 < d.W; x0 += xstep * U) {
+        float4 r0[U], r1[U];
+        uint4 a0[U], a1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (x0 + u * xstep < d.W) {
+                const float4* r4 = reinterpret_cast<const float4*>(praw + u * estep);
+                r0[u] = __ldg(r4);
+                r1[u] = __ldg(r4 + 1);
+                if (ADD_KIND == 1) {
+                    a0[u] = __ldg(reinterpret_cast<const uint4*>(pres + u * estep));
+                    a1[u] = d.res_lo_rows > 0 ? __ldg(reinterpret_cast<const uint4*>(pres + u * estep + res_lo)) : make_uint4(0, 0, 0, 0);
+                } else if (ADD_KIND == 2) {
+                    const uint4* q4 = reinterpret_cast<const uint4*>(praw2 + u * estep);
+                    a0[u] = __ldg(q4);
+                    a1[u] = __ldg(q4 + 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (x0 + u * xstep >= d.W) break;   // warp-uniform
+            float v[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+            if (d.group_ch) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = (v[j] - mean) * ga[j] + be[j];
+            }
+            if (d.relu_inner) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (ADD_KIND == 1) {
+                const __half2* hh = reinterpret_cast<const __half2*>(&a0[u]);
+                const __half2* ll = reinterpret_cast<const __half2*>(&a1[u]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 a = __half22float2(hh[j]), bq = __half22float2(ll[j]);
+                    v[2 * j] += a.x + bq.x;
+                    v[2 * j + 1] += a.y + bq.y;
+                }
+            } else if (ADD_KIND == 2) {
+                const float w[8] = {__uint_as_float(a0[u].x), __uint_as_float(a0[u].y), __uint_as_float(a0[u].z), __uint_as_float(a0[u].w),
+                                    __uint_as_float(a1[u].x), __uint_as_float(a1[u].y), __uint_as_float(a1[u].z), __uint_as_float(a1[u].w)};
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] += (w[j] - mean2) * ga2[j] + be2[j];
+            }
+            if (d.relu_outer) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
+            }
+            __half* o = pout + u * estep;
+            split_store8(o, o + lo_off, v, write_lo);
+            if (PLANES & 1) fp8_store8(pout8 + u * estep, pout8 + u * estep + lo_off, v);
+            if (PLANES & 2) {
+                uint8_t* o4 = pout4 + u * (estep / 2);
+                const uint32_t word = fp4_store8(o4, o4 + lo_off / 2, v);
+                if (lane == 0) psf[u * xstep] = word;
+            }
+        }
+        praw += U * estep;
+        if (ADD_KIND == 1) pres += U * estep;
+        if (ADD_KIND == 2) praw2 += U * estep;
+        pout += U * estep;
+        if (PLANES & 1) pout8 += U * estep;
+        if (PLANES & 2) { pout4 += U * (estep / 2); psf += U * xstep; }
+    }
+}
+
+template <int ADD_KIND>
+void gn_apply_rows_dispatch(const GnApplyDesc& d, int planes, cudaStream_t stream)
+{
+    const unsigned grid = (unsigned)(d.B * d.H);
+    switch (planes) {
+        case 0: gn_apply_rows_kernel<ADD_KIND, 0><<<grid, 256, 0, stream>>>(d); break;
+        case 1: gn_apply_rows_kernel<ADD_KIND, 1><<<grid, 256, 0, stream>>>(d); break;
+        case 2: gn_apply_rows_kernel<ADD_KIND, 2><<<grid, 256, 0, stream>>>(d); break;
+        default: gn_apply_rows_kernel<ADD_KIND, 3><<<grid, 256, 0, stream>>>(d); break;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Stem: direct 3x3 convolution on the CUDA cores (K = 27 is too thin for the tensor pipe), weights broadcast
 // from shared memory.  One thread = two vertically adjacent output pixels x 32 channels, so every weight
@@ -758,6 +895,15 @@ const char* gn_apply_launch(const GnApplyDesc& desc, cudaStream_t stream)
     const int groups = d.group_ch ? d.C / d.group_ch : 0;
     const size_t smem = (size_t)d.B * groups * sizeof(float2) * (d.add_kind == 2 ? 2 : 1);
     if (smem > 48 * 1024) return "gn_apply: batch * groups exceeds the 48 KB statistics table";
+    const int kgroups = d.C / 256;
+    if (d.out_phases == 1 && d.C % 256 == 0 && (kgroups == 1 || kgroups == 2 || kgroups == 4 || kgroups == 8) && d.out_C == d.C &&
+        d.group_ch % 8 == 0 && !(d.add_kind == 2 && !d.group_ch)) {
+        const int planes = (d.out8 ? 1 : 0) | (d.out4 ? 2 : 0);
+        if (d.add_kind == 0) gn_apply_rows_dispatch<0>(d, planes, stream);
+        else if (d.add_kind == 1) gn_apply_rows_dispatch<1>(d, planes, stream);
+        else gn_apply_rows_dispatch<2>(d, planes, stream);
+        return last_error();
+    }
     long long blocks = (total + kGnThreads * kGnUnroll - 1) / (kGnThreads * kGnUnroll);
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;

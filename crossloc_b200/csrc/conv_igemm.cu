@@ -30,6 +30,8 @@
 //   warps 4-7 epilogue: tcgen05.ld -> scale + bias -> swizzled smem staging -> TMA store (fp32) + GroupNorm
 //             partial sums (shuffle reduction, fp64 atomics)
 #include <cuda.h>
+
+#include <cstdlib>
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
@@ -1148,7 +1150,8 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_pair = 4u * (p.a_bytes + w_half);
+            const bool skip_w = p.corr_scale < 0.f;   // EXPERIMENT: no weight loads (timing only, results are garbage)
+            const uint32_t tx_pair = skip_w ? 4u * p.a_bytes : 4u * (p.a_bytes + w_half);
             const int w_rows = p.BN / 2;
             for (int tile = feed_next(feed, num_tiles); tile >= 0; tile = feed_next(feed, num_tiles)) {
                 const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
@@ -1167,14 +1170,18 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                             if (pass == 0) {
                                 ptx::tma_load_2d_pair(sa, &tmA4, bar, ks * 128, p.a4_lo_rows + a_row);        // a_lo4
                                 ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA4, bar, ks * 128, a_row);            // a_hi4
+                                if (!skip_w) {
                                 ptx::tma_load_2d_pair(sw, &tmW4, bar, ks * 128, w_row);                        // w_hi4
                                 ptx::tma_load_2d_pair(sw + w_half, &tmW4, bar, ks * 128, p.w_lo_rows + w_row); // w_lo4
+                                }
                             } else {
                                 const int kb = 2 * ks;
                                 ptx::tma_load_2d_pair(sa, &tmA, bar, kb * BK, a_row);
                                 ptx::tma_load_2d_pair(sa + p.a_bytes, &tmA, bar, (kb + 1) * BK, a_row);
+                                if (!skip_w) {
                                 ptx::tma_load_2d_pair(sw, &tmW, bar, kb * BK, w_row);
                                 ptx::tma_load_2d_pair(sw + w_half, &tmW, bar, (kb + 1) * BK, w_row);
+                                }
                             }
                             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                         }
@@ -1474,7 +1481,7 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
     p.nterms = d.nterms;
     p.a_lo_rows = (int)d.a_lo_rows;
     p.a8_lo_rows = (int)d.a8_lo_rows;
-    p.corr_scale = d.corr_scale;
+    p.corr_scale = (d.nterms == 4 && getenv("CL_EXPERIMENT_SKIP_W")) ? -1.f : d.corr_scale;
     p.w_tap_rows = d.Cout;
     p.w_lo_rows = d.num_taps * d.Cout;
     p.Mp = d.Mp; p.Cout = d.Cout; p.BN = BN;
