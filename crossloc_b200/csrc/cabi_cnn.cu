@@ -319,3 +319,13 @@ extern "C" int cl_head_backward(const void* act, int64_t act_lo_rows, int B, int
     d.weight = weight; d.g_sc = g_sc; d.g_x = g_x; d.g_w = g_w;
     return finish(kFn, cl::head_bwd_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
+
+#ifdef CL_DEBUG_TRAP
+namespace cl { void conv_debug_counters(unsigned long long* out16, bool reset); }
+// debug builds only (-DCL_DEBUG_TRAP): wait-cycle counters of the fp4 convolution kernel
+extern "C" int cl_debug_counters(unsigned long long* out16, int reset)
+{
+    cl::conv_debug_counters(out16, reset != 0);
+    return 0;
+}
+#endif

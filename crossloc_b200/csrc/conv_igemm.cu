@@ -106,11 +106,11 @@ __device__ __forceinline__ bool scatter_owner(int lane)
 
 // GroupNorm partial sums of one 32-column chunk held by the warp (one row per lane).
 // GC = channels per group; the chunk covers 32 / GC whole groups.
-template <int GC>
-__device__ __forceinline__ void stats_chunk(const float (&f)[32], bool valid, int image, int lane, double* stats,
+template <int GC, int NC = 32>
+__device__ __forceinline__ void stats_chunk(const float (&f)[NC], bool valid, int image, int lane, double* stats,
                                             int groups, int first_group)
 {
-    constexpr int NG = 32 / GC, NV = 2 * NG;
+    constexpr int NG = NC / GC, NV = 2 * NG;
     float v[NV];
 #pragma unroll
     for (int g = 0; g < NG; g++) {
@@ -1040,14 +1040,24 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 //   * Tensor memory: the scale columns do not fit next to two 256-column accumulators, so the second accumulator starts
 //     at column 224 and the scales live in columns 480..511.  The epilogue drains the 32 shared columns first and then
 //     lets the MMA warp start the next tile; the rest of the drain overlaps that tile's MMAs as before.
-constexpr uint32_t kSfStageBytes = 2048;   // shared memory reserved per pipeline stage for the scale ring below
-constexpr int kSfSlots = 4;                // the scales have their own ring (only pass 0 uses them): a slot = 512 B activation
+#ifdef CL_DEBUG_TRAP
+__device__ unsigned long long g_conv_dbg[16];   // wait cycles by site (debug builds only): see cl_debug_counters
+#define CL_DBG_T0() const long long _t0 = clock64()
+#define CL_DBG_ADD(i) do { if (lane == 0) atomicAdd(&g_conv_dbg[i], (unsigned long long)(clock64() - _t0)); } while (0)
+#else
+#define CL_DBG_T0() do {} while (0)
+#define CL_DBG_ADD(i) do {} while (0)
+#endif
+constexpr uint32_t kSfStageBytes = 4096;   // shared memory reserved per pipeline stage for the scale ring below
+constexpr int kSfSlots = 8;                // the scales have their own ring (only pass 0 uses them): a slot = 512 B activation
 constexpr uint32_t kSfSlotBytes = 1536;    // scales + 2 x 512 B weight scales; kSfSlots * kSfSlotBytes <= 3 * kSfStageBytes
 constexpr uint32_t kAcc1Col = 224;
 constexpr uint32_t kSfCol = 480;
-constexpr uint32_t kFp4StagingBytes = 4 * kStageChunkBytes;   // one staging chunk per epilogue warp
+constexpr int kFp4Threads = 384;           // eight epilogue warps: two per tensor-memory lane quarter, alternating 16-column chunks
+constexpr uint32_t kFp4ChunkBytes = 32 * 16 * 4;               // one staging chunk: 32 rows x 16 fp32 (64-byte rows, SWIZZLE_64B)
+constexpr uint32_t kFp4StagingBytes = 8 * kFp4ChunkBytes;      // one staging chunk per epilogue warp
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFp4Threads, 1)
 conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA4,
                            const __grid_constant__ CUtensorMap tmW4, const ConvIgemmParams p)
@@ -1097,8 +1107,8 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             ptx::mbar_init(ptx::smem_u32(&sf_empty[s]), 1);    // the leader's MMA commit, multicast to both CTAs
         }
         for (int s = 0; s < 2; s++) ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
-        ptx::mbar_init(ptx::smem_u32(&ovl_bar), 8);            // leader only: 4 epilogue warps of each CTA
-        const uint32_t consumers = 2u * (1u + 1u + 4u) + 1u;   // producer, scale loader and epilogue warps of both CTAs, MMA warp
+        ptx::mbar_init(ptx::smem_u32(&ovl_bar), 16);           // leader only: 8 epilogue warps of each CTA
+        const uint32_t consumers = 2u * (1u + 1u + 8u) + 1u;   // producer, scale loader and epilogue warps of both CTAs, MMA warp
         for (int s = 0; s < kRing; s++) {
             ptx::mbar_init(ptx::smem_u32(&sched_full[s]), 1);
             ptx::mbar_init(ptx::smem_u32(&sched_empty[s]), consumers);
@@ -1262,6 +1272,9 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             int stage = 0, local = 0;
             uint32_t phase = 0, sphase = 0;
             int slot = 0;
+#ifdef CL_DEBUG_TRAP
+            const long long _tk = clock64();
+#endif
             for (;; local++) {
                 int tile = 0;
                 if (lane == 0) tile = feed_next(feed, num_tiles);
@@ -1271,13 +1284,15 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 if (local > 0) {
                     // the previous tile's epilogue has drained the columns both accumulators share (and, before that,
                     // everything of the tile that used this accumulator last)
-                    ptx::mbar_wait(ptx::smem_u32(&ovl_bar), (uint32_t)(local - 1) & 1u, 5);
+                    { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&ovl_bar), (uint32_t)(local - 1) & 1u, 5); CL_DBG_ADD(0); }
                     ptx::tc_fence_after();
                 }
                 const uint32_t tmem_d = tmem_base + (as ? kAcc1Col : 0u);
                 for (int i = 0; i < n4; i++) {
-                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, 6);
-                    ptx::mbar_wait_cluster(ptx::smem_u32(&sf_full[slot]), sphase, 7);
+                    { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, 6); CL_DBG_ADD(1); }
+                    // (CTA-scope wait, as for the operand barrier: the peer's scales stay in the peer's shared memory and are
+                    // read there by its own tensor core; a cluster-scope acquire here costs ~350 cycles per stage)
+                    { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&sf_full[slot]), sphase, 7); CL_DBG_ADD(2); }
                     ptx::tc_fence_after();
                     if (lane == 0) {
                         const uint32_t a4lo = smem_base + (uint32_t)stage * p.stage_bytes, a4hi = a4lo + p.a_bytes;
@@ -1307,7 +1322,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     if (++slot == kSfSlots) { slot = 0; sphase ^= 1u; }
                 }
                 for (int i = 0; i < n16; i++) {
-                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, 8);
+                    { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, 8); CL_DBG_ADD(3); }
                     ptx::tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
@@ -1328,12 +1343,19 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
+#ifdef CL_DEBUG_TRAP
+            if (lane == 0) { atomicAdd(&g_conv_dbg[6], (unsigned long long)(clock64() - _tk)); atomicAdd(&g_conv_dbg[7], (unsigned long long)local); }
+#endif
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        // Two warps per lane quarter drain alternating 16-column chunks: with short K loops (1x1 layers: six stages per
+        // tile) the drain of a tile, not its MMAs, is the critical path -- TMEM load, scale + bias, staging, TMA store and
+        // the GroupNorm sums of 128 x 256 values take longer than 48 MMAs.
         const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
         const int plane = p.Hp * p.Wp;
-        const uint32_t sbuf = sf_base + (uint32_t)p.num_stages * kSfStageBytes + (uint32_t)q * kStageChunkBytes;
+        const uint32_t sbuf = sf_base + (uint32_t)p.num_stages * kSfStageBytes + (uint32_t)(warp - 4) * kFp4ChunkBytes;
         for (int local = 0;; local++) {
             int tile = 0;
             if (lane == 0) tile = feed_next(feed, num_tiles);
@@ -1352,17 +1374,19 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 const int y = r / p.Wp, x = r - y * p.Wp;
                 valid = y >= 1 && y <= p.Hp - 2 && x >= 1 && x <= p.Wp - 2;
             }
-            ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase, 9);
+            { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aphase, 9); if (warp == 4) CL_DBG_ADD(4); }
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as ? kAcc1Col : 0u);
-            const int nchunks = p.BN / 32;
-            for (int idx = 0; idx < nchunks; idx++) {
-                // the chunk in tensor-memory columns 224..255 goes first: it is the only one the other accumulator shares
-                const int c0 = as ? idx * 32 : (idx == 0 ? (nchunks - 1) * 32 : (idx - 1) * 32);
-                uint32_t u[32];
-                ptx::tmem_ld_32x32(taddr + (uint32_t)c0, u);
+            const int nchunks = p.BN / 16;
+            for (int idx = grp; idx < nchunks; idx += 2) {
+                // drain order: the two chunks in tensor-memory columns 224..255 (the only ones the other accumulator
+                // shares) go first, one per warp group
+                const int c0 = as ? idx * 16 : (idx < 2 ? (nchunks - 2 + idx) * 16 : (idx - 2) * 16);
+                uint32_t u[16];
+                ptx::tmem_ld_32x16(taddr + (uint32_t)c0, u);
                 ptx::tmem_ld_wait();
-                if (idx == 0) {
+                if (idx < 2) {
+                    // this warp is done with the previous tile and with the shared columns of this one
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -1370,21 +1394,21 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                         else ptx::mbar_arrive_remote(ptx::smem_u32(&ovl_bar), 0u);
                     }
                 }
-                float f[32];
+                float f[16];
                 const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < 4; j++) {
                     const float4 bb = __ldg(b4 + j);
                     f[4 * j + 0] = __uint_as_float(u[4 * j + 0]) * p.out_scale + bb.x;
                     f[4 * j + 1] = __uint_as_float(u[4 * j + 1]) * p.out_scale + bb.y;
                     f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) * p.out_scale + bb.z;
                     f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) * p.out_scale + bb.w;
                 }
-                if (lane == 0) ptx::tma_store_wait_read<0>();   // single staging chunk per warp: the previous store has read it
+                { CL_DBG_T0(); if (lane == 0) ptx::tma_store_wait_read<0>(); if (warp == 4) CL_DBG_ADD(5); }   // single staging chunk per warp: the previous store has read it
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t dst = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t dst = sbuf + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "f"(f[4 * j]), "f"(f[4 * j + 1]),
                                  "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
                                  : "memory");
@@ -1398,10 +1422,10 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 if (p.group_ch) {
                     const int first_group = (n0 + c0) / p.group_ch;
                     switch (p.group_ch) {
-                        case 2: stats_chunk<2>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        case 4: stats_chunk<4>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        case 8: stats_chunk<8>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        case 16: stats_chunk<16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 2: stats_chunk<2, 16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 4: stats_chunk<4, 16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 8: stats_chunk<8, 16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 16: stats_chunk<16, 16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
                         default: break;
                     }
                 }
@@ -1571,7 +1595,7 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
     if (!make_tensor_map(&plan->tmW, d.weights, (uint64_t)(d.nterms == 3 ? 2 : 1) * d.num_taps * d.Cout, (uint64_t)d.Cin, BN / cluster, BK, 2))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the weight matrix";
     if (d.fuse) plan->tmO = plan->tmA;
-    else if (!make_tensor_map(&plan->tmO, d.raw, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, 32, 4))
+    else if (!make_tensor_map(&plan->tmO, d.raw, (uint64_t)d.Mp, (uint64_t)d.Cout, 32, d.nterms == 4 ? 16 : 32, 4))
         return "conv_igemm: cuTensorMapEncodeTiled failed for the output matrix";
     plan->tmA8 = plan->tmA;
     plan->tmW8 = plan->tmW;
@@ -1605,7 +1629,7 @@ const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(plan.grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(plan.variant == 8 ? kFp4Threads : kThreads);
     cfg.dynamicSmemBytes = plan.smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1643,6 +1667,18 @@ const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream)
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
+
+#ifdef CL_DEBUG_TRAP
+void conv_debug_counters(unsigned long long* out16, bool reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_conv_dbg, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long zero[16] = {};
+        cudaMemcpyToSymbol(g_conv_dbg, zero, sizeof(zero));
+    }
+}
+#endif
 
 const char* conv_igemm_launch(const ConvIgemmDesc& d, cudaStream_t stream)
 {
