@@ -100,6 +100,15 @@ def peaks():
     return tf, bw
 
 
+# arithmetic of the path per convolution scheme (crossloc_b200.cnn.PRECISION)
+DTYPES = {
+    'fp16+fp4': 'f16 products + block-scaled e2m1 (fp4) correction products -> f32 accumulate (conv) + f64 (pose solve)',
+    'fp16+fp8': 'f16 products + e4m3 (fp8) correction products -> f32 accumulate (conv) + f64 (pose solve)',
+    'fp16x3': 'f16 split products (three per product) -> f32 accumulate (conv) + f64 (pose solve)',
+    'fp16x1': 'f16 products -> f32 accumulate (conv) + f64 (pose solve)',
+}
+
+
 def ncu_traffic(kernel):
     """DRAM bytes per launch from the committed `ncu --set full` capture of this kernel, with its provenance."""
     path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
@@ -470,8 +479,8 @@ def run_native(args):
         if rank == 0:
             emit({'metric': METRIC, 'unit': UNIT, 'value': res['images_per_s'], 'n_gpus': world, 'steps': 1, 'warmup': 1,
                   'ms_per_step': 1e3 * res['wall_s'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                  'dtype': 'f16+f8 split products -> f32 accumulate (conv) + f64 (pose solve)', 'data': 'synthetic',
-                  'config': {'workload': 'eval5_%d_frames_sharded' % res['images']}, 'detail': res})
+                  'dtype': DTYPES.get(net._runtime.precision if getattr(net, '_runtime', None) else '', 'f16 split products'),
+                  'data': 'synthetic', 'config': {'workload': 'eval5_%d_frames_sharded' % res['images']}, 'detail': res})
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -560,17 +569,19 @@ def run_native(args):
     if dom:
         achieved = dom['tflops_useful']
         nterms = rt.nterms
-        traffic, traffic_src = ncu_traffic('conv_igemm_pair_kernel<64> 3x3 512->512')
-        roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel<64%s> 3x3 512->512 @60x90 x%d images' % (
-                        ', fused GroupNorm epilogue' if fused else '', B),
+        kname = 'conv_igemm_pair_fp4_kernel' if rt.precision == 'fp16+fp4' else 'conv_igemm_pair_kernel<64%s>' % (
+            ', fused GroupNorm epilogue' if fused else '')
+        traffic, traffic_src = ncu_traffic('%s 3x3 512->512' % kname)
+        roofline = {'bound': 'tensor', 'kernel': '%s 3x3 512->512 @60x90 x%d images' % (kname, B),
                     'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                     'traffic': traffic, 'traffic_source': traffic_src,
                     'traffic_unit': 'bytes per launch (dram read + write, ncu --set full)',
                     'peak_source': peak_tf_src, 'avg_launch_ms': dom['avg_ms'],
                     'launches_timed': dom['launches_per_step'] * args.steps,
                     'issued_tflops': achieved * nterms, 'issued_frac': achieved * nterms / peak_tf,
-                    'note': 'achieved counts algorithmic FLOPs (2*pixels*Cout*Cin*9); %s issues %d fp16-MMA equivalents per '
-                            'product (fp16+fp8: one fp16 MMA + two e4m3 MMAs at twice the rate)' % (rt.precision, nterms),
+                    'note': 'achieved counts algorithmic FLOPs (2*pixels*Cout*Cin*9); %s issues %.1f fp16-MMA equivalents per '
+                            'product (one fp16 MMA + the two 2^-11 correction products as block-scaled e2m1 MMAs at four times '
+                            'the fp16 rate [fp16+fp4] or as e4m3 MMAs at twice the rate [fp16+fp8])' % (rt.precision, nterms),
                     'all_conv_ms_per_step': conv_total_ms}
     score_ms = kernel_ms['dsac_score']['avg_ms']
     cells = 60 * 90
@@ -645,7 +656,7 @@ def run_native(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f16+f8 split products -> f32 accumulate (conv) + f64 (pose solve)', 'data': 'synthetic',
+            'dtype': DTYPES.get(rt.precision, rt.precision), 'data': 'synthetic',
             'config': config_of(args, world),
             'impl_detail': {'conv_precision': rt.precision, 'timed_mode': 'cl_net_forward, per-op event mode (eager launches)',
                             'graph_mode_ms_per_step': graph_ms,

@@ -75,6 +75,15 @@ SIGNATURES = {
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
         _c.c_void_p, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_float, _c.c_float,
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
+    # input frames (csrc/frames.cu)
+    'cl_png_info': (_c.c_int, [_c.c_void_p, _c.c_size_t, _i32p, _i32p, _i32p]),
+    'cl_decode_png': (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_int, _c.c_int]),
+    'cl_decode_png_batch': (_c.c_int, [_c.POINTER(_c.c_void_p), _c.POINTER(_c.c_size_t), _c.c_int, _c.c_void_p, _c.c_int,
+                                       _c.c_int, _c.c_int]),
+    'cl_resize_frames': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+                                    _c.c_size_t, _c.c_void_p]),
+    'cl_resize_workspace_bytes': (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    'cl_resize_coeffs': (_c.c_int, [_c.c_int, _c.c_int, _i32p, _i32p, _i32p]),
     # whole-network runtime (csrc/net.cu); the descriptor structures live in crossloc_b200/net.py
     'cl_net_create': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     'cl_net_update': (_c.c_int, [_c.c_void_p]),

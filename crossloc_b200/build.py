@@ -30,6 +30,7 @@ UNITS = {
     'stem_tc.cu': [],
     'gn_backward.cu': [],
     'train_layout.cu': [],
+    'frames.cu': [],
 }
 
 
@@ -74,7 +75,7 @@ def build(force=False, verbose=False):
             print('nvcc failed for %s' % src, file=sys.stderr)
     if failed:
         raise RuntimeError('crossloc_b200: nvcc build failed')
-    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs + ['-lcudart', '-ccbin', '/usr/bin/g++']
+    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs + ['-lcudart', '-lz', '-ccbin', '/usr/bin/g++']
     subprocess.check_call(cmd)
     with open(stamp, 'w') as fh:
         fh.write(digest)

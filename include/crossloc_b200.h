@@ -16,6 +16,7 @@
 #ifndef CROSSLOC_B200_H
 #define CROSSLOC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -275,6 +276,29 @@ int cl_duc_head_forward(const float* raw, int B, int Hc, int Wc, int C, int Co, 
  */
 int cl_frames_to_nchw(const uint8_t* frames, int B, int H, int W, int C, const float* mean, const float* stdv, float* out,
                       void* cuda_stream);
+
+/*
+ * ---- Input frames ---------------------------------------------------------------
+ * The image path of the reference's data loader, /root/reference/dataloader/dataloader.py:306-316 (io.imread, gray2rgb,
+ * RGBA -> RGB) and :189-212 (ToPILImage -> Resize(image_height) -> ToTensor [-> Normalize]), without the DataLoader
+ * workers: PNG files are decoded on host threads straight into a (pinned) uint8 batch, Resize runs on the device and
+ * cl_frames_to_nchw / cl_net_forward_frames do ToTensor / Normalize.
+ *   cl_png_info          size of a PNG file image (and the channel count stored in the file)
+ *   cl_decode_png        8-bit gray / gray+alpha / RGB / RGBA / palette, non-interlaced -> uint8 [H][W][3]
+ *   cl_decode_png_batch  `count` files of one size -> uint8 [count][H][W][3] on `threads` host threads
+ *   cl_resize_frames     Pillow's antialiased bilinear resample (what torchvision Resize does to a PIL image), uint8
+ *                        [B][Hin][Win][3] -> [B][Hout][Wout][3] on the device, bit-identical to Image.resize(BILINEAR);
+ *                        workspace: device memory of cl_resize_workspace_bytes() bytes
+ *   cl_resize_coeffs     the fixed-point coefficient table of one axis (host only; bounds / kk may be NULL to query ksize)
+ */
+int cl_png_info(const void* file, size_t file_bytes, int* height, int* width, int* file_channels);
+int cl_decode_png(const void* file, size_t file_bytes, uint8_t* out_rgb, int height, int width);
+int cl_decode_png_batch(const void* const* files, const size_t* file_bytes, int count, uint8_t* out_rgb, int height, int width,
+                        int threads);
+int cl_resize_frames(const uint8_t* src, int B, int Hin, int Win, uint8_t* dst, int Hout, int Wout, void* workspace,
+                     size_t workspace_bytes, void* cuda_stream);
+size_t cl_resize_workspace_bytes(int B, int Hin, int Win, int Hout, int Wout);
+int cl_resize_coeffs(int in_size, int out_size, int* ksize, int* bounds, int* kk);
 
 /*
  * ---- Whole-network runtime -------------------------------------------------------------------------------
