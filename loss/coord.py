@@ -7,6 +7,8 @@ Same public functions, argument order and return values as /root/reference/loss/
 autograd flows into the coordinate map; tensors are created on the inputs' device instead of the reference's
 hard-wired `.cuda()`.
 """
+import os
+
 import torch
 
 try:
@@ -16,6 +18,12 @@ except Exception:   # pragma: no cover - reference utils not on the path
         print(words)
 
 _TINY = 1.e-7
+# CROSSLOC_B200_LOSS_SYNC_FREE=1 (or loss.coord.SYNC_FREE = True): no device -> host synchronisation inside the loss.  The
+# reference reads three scalars back per step (loss/coord.py:132 `.cpu().numpy()`, :168-175 `.item()` for its progress
+# line), which stalls the launch queue of a GPU that trains at 300 frames/s.  In this mode the progress line is skipped,
+# the "any valid prediction" branch becomes a device-side select and valid_pred_rate is returned as a 0-dim tensor
+# (`float(rate)` gives the reference's number when the caller wants it).  Same loss value, bit for bit.
+SYNC_FREE = os.environ.get('CROSSLOC_B200_LOSS_SYNC_FREE', '0') == '1'
 
 
 def get_cam_mat(width, height, focal_length):
@@ -74,18 +82,21 @@ def scene_coords_regression_loss(min_depth, soft_clamp, hard_clamp, init_toleran
 
     has_label = _valid_labels(label[:, :3, :], nodata_value)
     valid = check_constraints(cam_pred, reproj, dist3d, ~has_label, min_depth, hard_clamp, init_tolerance)
-    num_valid = valid.sum(dim=1).cpu().numpy()
+    sync_free = SYNC_FREE
+    num_valid = valid.sum() if sync_free else valid.sum(dim=1).cpu().numpy()
     pixels_batch = valid.numel()
     pixels_instance = valid[0].numel()
 
     # soft-clamped L1 of the reprojection error over valid predictions: linear up to soft_clamp, sqrt beyond
     loss_reproj = 0
-    if num_valid.sum() > 0:
+    if sync_free or num_valid.sum() > 0:
         reproj = reproj * valid
         linear = (reproj * (reproj <= soft_clamp)).clamp(min=_TINY)
         root = (reproj * (reproj > soft_clamp)).clamp(min=_TINY)
         root = torch.sqrt(soft_clamp * root + _TINY).clamp(min=_TINY)
         loss_reproj = linear + root
+        if sync_free:   # the reference adds nothing when no prediction is valid
+            loss_reproj = torch.where(num_valid > 0, loss_reproj, torch.zeros_like(loss_reproj))
 
     if uncertainty is None:
         loss = torch.sum(dist3d * has_label + loss_reproj, dim=1)
@@ -94,13 +105,14 @@ def scene_coords_regression_loss(min_depth, soft_clamp, hard_clamp, init_toleran
         sq = dist3d.square().clamp(min=_TINY)
         nll = 3.0 * torch.log(sigma) + sq / (2.0 * sigma.square().clamp(min=_TINY))
         loss = torch.sum(nll * has_label + loss_reproj, dim=1)
-        safe_printout('Regression error: coord:  %.2f, reprojection:  %.2f' % (
-            torch.sum(dist3d * has_label).item() / max(1, has_label.sum().item()),
-            torch.sum(reproj * valid).item() / max(1, valid.sum().item())))
+        if not sync_free:
+            safe_printout('Regression error: coord:  %.2f, reprojection:  %.2f' % (
+                torch.sum(dist3d * has_label).item() / max(1, has_label.sum().item()),
+                torch.sum(reproj * valid).item() / max(1, valid.sum().item())))
     else:
         raise NotImplementedError
 
-    valid_pred_rate = num_valid.sum() / pixels_batch
+    valid_pred_rate = num_valid / pixels_batch if sync_free else num_valid.sum() / pixels_batch
     if reduction is None:
         loss = loss / pixels_instance
     elif reduction == 'mean':

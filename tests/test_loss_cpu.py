@@ -62,3 +62,33 @@ def test_get_cam_mat():
     from loss.coord import get_cam_mat
     k = get_cam_mat(720, 480, 480.0).cpu()
     assert k[0, 0] == 480.0 and k[1, 1] == 480.0 and k[0, 2] == 360.0 and k[1, 2] == 240.0 and k[2, 2] == 1.0
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_sync_free_mode_matches_reference_fixture(name, monkeypatch):
+    """CROSSLOC_B200_LOSS_SYNC_FREE: no .cpu() / .item() inside the loss -- same loss, rate and
+    gradient as the reference fixture; the rate comes back as a 0-dim tensor."""
+    import loss.coord as lc
+    monkeypatch.setattr(lc, 'SYNC_FREE', True)
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'loss_golden.npz'))
+    args, kwargs, coords = make_inputs(CASES[name])
+    loss, rate = lc.scene_coords_regression_loss(*args, **kwargs)
+    loss.sum().backward()
+    assert torch.is_tensor(rate) and rate.dim() == 0
+    assert np.allclose(loss.detach().numpy(), gold[name + '_loss'], rtol=1e-5, atol=1e-6)
+    assert abs(float(rate) - float(gold[name + '_rate'])) < 1e-7
+    assert np.allclose(coords.grad.reshape(-1)[::97].numpy(), gold[name + '_grad_sample'], rtol=1e-4, atol=1e-6)
+
+
+def test_sync_free_mode_without_any_valid_prediction(monkeypatch):
+    """The reference adds no reprojection term when no prediction passes the constraints (loss/coord.py:141): the
+    device-side select of the sync-free mode must reproduce that branch."""
+    import loss.coord as lc
+    args, kwargs, _ = make_inputs((2, 'MLE', 'mean', 5000.0, 7))
+    args = list(args)
+    args[2] = 1e-9                           # hard clamp: no reprojection error can pass
+    want, rate_w = lc.scene_coords_regression_loss(*args, **kwargs)
+    assert float(rate_w) == 0.0
+    monkeypatch.setattr(lc, 'SYNC_FREE', True)
+    got, rate_g = lc.scene_coords_regression_loss(*args, **kwargs)
+    assert float(rate_g) == 0.0 and torch.equal(got, want)
