@@ -22,6 +22,11 @@ SIGNATURES = {
         _c.c_void_p, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_int,
         _c.c_uint64, _c.c_uint32, _c.c_uint32, _c.c_int,
         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'cl_dsac_backward_rgb': (_c.c_int, [
+        _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_float,
+        _c.c_void_p, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_int,
+        _c.c_uint64, _c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     'cl_dsac_timing': (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     'cl_release_workspaces': (_c.c_int, []),
     'cl_conv_igemm': (_c.c_int, [

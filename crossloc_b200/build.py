@@ -22,6 +22,7 @@ COMMON = (["-DCL_DEBUG_TRAP"] if os.environ.get("CL_DEBUG_TRAP") else []) + ['-O
 UNITS = {
     'cabi.cu': [],
     'dsac.cu': ['--fmad=false'],
+    'dsac_backward.cu': ['--fmad=false'],
     'cabi_cnn.cu': [],
     'net.cu': [],
     'conv_igemm.cu': [],

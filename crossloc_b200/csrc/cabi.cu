@@ -106,6 +106,65 @@ extern "C" int cl_dsac_forward_rgb(const float* coords, int B, int Hc, int Wc, f
     return 0;
 }
 
+extern "C" int cl_dsac_backward_rgb(const float* coords, int B, int Hc, int Wc, float* grad, const float* gt_pose,
+                                    int hyps, float thr, const float* focal, float cx, float cy, float w_rot,
+                                    float w_trans, float soft_clamp, float alpha, float max_reproj, int subsample,
+                                    uint64_t seed, uint32_t image_base, uint32_t max_tries,
+                                    const int32_t* forced_samples, double* out_loss, double* out_probs,
+                                    double* out_losses, double* out_hyps, double* out_ref_rt, int32_t* out_tries,
+                                    int32_t* out_cells, void* cuda_stream)
+{
+    using namespace cl;
+    if (!coords || !grad || !gt_pose || !focal || !out_loss)
+        return fail(-1, "cl_dsac_backward_rgb: coords, grad, gt_pose, focal and out_loss must not be NULL");
+    if (B < 0 || Hc <= 0 || Wc <= 0 || hyps <= 0 || subsample <= 0)
+        return fail(-1, "cl_dsac_backward_rgb: invalid sizes B=%d Hc=%d Wc=%d hyps=%d subsample=%d", B, Hc, Wc, hyps, subsample);
+    if (B > 65535) return fail(-1, "cl_dsac_backward_rgb: B=%d exceeds the 65535 images one launch takes", B);
+    if (max_tries == 0) return fail(-1, "cl_dsac_backward_rgb: max_tries must be >= 1");
+    if (B == 0) return 0;
+
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    Workspace& ws = workspace_for(stream);
+    std::lock_guard<std::mutex> lock(ws.mu);
+    Stager st(ws, stream);
+    const size_t n = (size_t)Hc * Wc, bh = (size_t)B * hyps;
+
+    DsacBwdArgs a{};
+    DsacArgs& f = a.fwd;
+    f.B = B; f.Hc = Hc; f.Wc = Wc; f.hyps = hyps; f.thr = thr; f.cx = cx; f.cy = cy; f.alpha = alpha;
+    f.max_reproj = max_reproj; f.S = subsample; f.seed = seed; f.image_base = image_base; f.max_tries = max_tries;
+    f.refine = 1;
+    a.w_rot = w_rot; a.w_trans = w_trans; a.soft_clamp = soft_clamp;
+    CL_CUDA(st.in("dsac.coords", coords, (size_t)B * 3 * n, &f.coords));
+    CL_CUDA(st.in("dsac.focal", focal, (size_t)B, &f.focal));
+    CL_CUDA(st.in("dsac.forced", forced_samples, bh * 8, &f.forced));
+    CL_CUDA(st.in("dsacb.gt", gt_pose, (size_t)B * 16, &a.gt_pose));
+    CL_CUDA(st.inout("dsacb.grad", grad, (size_t)B * 3 * n, &a.grad));
+    CL_CUDA(st.out("dsacb.loss", out_loss, (size_t)B, &a.out_loss));
+    CL_CUDA(st.out("dsac.scores", (double*)nullptr, bh, &f.scores, /*always=*/true));
+    CL_CUDA(st.out("dsac.hyps", out_hyps, bh * 6, &f.hyp_rt, /*always=*/true));
+    CL_CUDA(st.out("dsac.tries", out_tries, bh, &f.tries));
+    CL_CUDA(st.out("dsacb.cells", out_cells, bh * 8, &f.out_cells, /*always=*/true));
+    CL_CUDA(st.out("dsacb.probs", out_probs, bh, &a.probs, /*always=*/true));
+    CL_CUDA(st.out("dsacb.losses", out_losses, bh, &a.losses, /*always=*/true));
+    CL_CUDA(st.out("dsacb.ref", out_ref_rt, bh * 6, &a.ref_rt, /*always=*/true));
+    void* p;
+    CL_CUDA(ws.get("dsacb.dloss", bh * 6 * sizeof(double), &p));
+    a.dloss = static_cast<double*>(p);
+    CL_CUDA(ws.get("dsacb.accepted", bh * sizeof(int32_t), &p));
+    a.accepted = static_cast<int32_t*>(p);
+    CL_CUDA(ws.get("dsacb.errs", bh * n * sizeof(float), &p));
+    a.errs = static_cast<float*>(p);
+    CL_CUDA(ws.get("dsacb.inlier", bh * n, &p));
+    a.inlier = static_cast<uint8_t*>(p);
+    CL_CUDA(ws.get("dsacb.hyp_grad", bh * n * 3 * sizeof(double), &p));
+    a.hyp_grad = static_cast<double*>(p);
+
+    CL_CUDA(dsac_backward_launch(a, stream));
+    CL_CUDA(st.finish());
+    return 0;
+}
+
 extern "C" int cl_dsac_timing(int enable, void* cuda_stream, float* ms, int* solves)
 {
     using namespace cl;

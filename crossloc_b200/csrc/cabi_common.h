@@ -134,6 +134,21 @@ public:
         return cudaSuccess;
     }
 
+    // Device view of a buffer the kernels accumulate into: host contents are staged in and copied back by finish().
+    template <typename T>
+    cudaError_t inout(const char* name, T* p, size_t count, T** dev)
+    {
+        if (!p || count == 0) { *dev = nullptr; return cudaSuccess; }
+        if (is_device_ptr(p)) { *dev = p; return cudaSuccess; }
+        void* d;
+        cudaError_t e = ws_.get(name, count * sizeof(T), &d);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, stream_);
+        *dev = static_cast<T*>(d);
+        pending_.push_back({p, d, count * sizeof(T)});
+        return e;
+    }
+
     // Copies pending host outputs back and synchronises the stream if there were any.
     cudaError_t finish()
     {

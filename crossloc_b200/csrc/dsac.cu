@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32) dsac_sample_kernel(DsacArgs
 #pragma unroll
         for (int j = 0; j < 3; j++) { cand.r[j] = 0; cand.t[j] = 0; }
         bool accept = false;
+        int cells[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (t < max_tries) {
-            int cells[8];
             if (forced) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) cells[j] = a.forced[((size_t)b * a.hyps + h) * 8 + j];
@@ -100,6 +100,13 @@ __global__ void __launch_bounds__(kSampleWarps * 32) dsac_sample_kernel(DsacArgs
                 win.t[j] = __shfl_sync(0xffffffffu, cand.t[j], src);
             }
             tries_used = base + (uint32_t)src + 1;
+            if (a.out_cells) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int c = __shfl_sync(0xffffffffu, cells[j], src);
+                    if (lane == 0) a.out_cells[((size_t)b * a.hyps + h) * 8 + j] = c;
+                }
+            }
             break;
         }
     }
@@ -222,6 +229,15 @@ __global__ void __maxnreg__(kRefineMaxRegs) dsac_refine_kernel(DsacArgs a)
 }
 
 }  // namespace
+
+cudaError_t dsac_sample_score_launch(const DsacArgs& a, cudaStream_t stream)
+{
+    if (a.B <= 0 || a.hyps <= 0) return cudaSuccess;
+    dim3 gs((a.hyps + kSampleWarps - 1) / kSampleWarps, a.B);
+    dsac_sample_kernel<<<gs, kSampleWarps * 32, 0, stream>>>(a);
+    dsac_score_kernel<<<dim3(a.hyps, a.B), kScoreThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t dsac_forward_launch(const DsacArgs& a, cudaStream_t stream, cudaEvent_t* ev)
 {

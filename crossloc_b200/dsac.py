@@ -1,4 +1,4 @@
-"""Host side of the DSAC* solver: tensor plumbing around cl_dsac_forward_rgb.
+"""Host side of the DSAC* solver: tensor plumbing around cl_dsac_forward_rgb / cl_dsac_backward_rgb.
 
 Mirrors the operator interface of the reference extension
 (/root/reference/dsacstar/dsacstar.cpp:63-73, :888 -- `dsacstar.forward_rgb`) and adds the batched
@@ -120,3 +120,75 @@ def forward_rgb(scene_coordinates, out_pose, ransac_hypotheses, inlier_threshold
     forward_rgb_batch(scene_coordinates, out_pose, ransac_hypotheses, inlier_threshold, focal_length, ppoint_x,
                       ppoint_y, inlier_alpha, max_reproj, sub_sampling)
     return None
+
+
+def backward_rgb_batch(coords, grad, gt_pose, hyps, thr, focal, cx, cy, w_rot, w_trans, soft_clamp, alpha, max_reproj,
+                       subsample, seed=None, image_base=None, max_tries=MAX_HYPOTHESES_TRIES, forced_samples=None,
+                       debug=False):
+    """Expected pose loss and its gradient for a batch.  coords / grad [B,3,Hc,Wc] float32 on one device (CPU or
+    CUDA), grad is accumulated into; gt_pose [B,4,4] float32.  Returns the [B] float64 expected losses (host tensor),
+    and with debug=True also a dict of host tensors (probs, losses, hyps_rt, ref_rt, tries, cells)."""
+    lib = _lib.load()
+    if coords.dim() != 4 or coords.size(1) != 3:
+        raise RuntimeError('scene coordinates must be [B, 3, H, W], got %s' % (tuple(coords.shape),))
+    if coords.dtype != torch.float32 or grad.dtype != torch.float32:
+        raise RuntimeError('scene coordinates and their gradient must be float32')
+    if grad.shape != coords.shape or not grad.is_contiguous() or grad.device != coords.device:
+        raise RuntimeError('the gradient tensor must be contiguous, of the shape and on the device of the scene coordinates')
+    B, _, Hc, Wc = coords.shape
+    coords_c = coords.contiguous()
+    gt = torch.as_tensor(gt_pose).to(torch.float32).reshape(B, 16).contiguous().cpu()
+    if torch.is_tensor(focal):
+        focal_t = focal.to(torch.float32).reshape(-1).contiguous().cpu()
+        if focal_t.numel() == 1 and B > 1:
+            focal_t = focal_t.expand(B).contiguous()
+    else:
+        focal_t = torch.full((B,), float(focal), dtype=torch.float32)
+    if focal_t.numel() != B:
+        raise RuntimeError('focal must be a scalar or hold one value per image')
+    if seed is None:
+        seed = _state['seed']
+    if image_base is None:
+        image_base = _state['image_index']
+        _state['image_index'] += B
+    forced_t = None
+    if forced_samples is not None:
+        forced_t = torch.as_tensor(forced_samples, dtype=torch.int32).reshape(B, hyps, 4, 2).contiguous()
+    loss = torch.zeros(B, dtype=torch.float64)
+    dbg = None
+    if debug:
+        dbg = {
+            'probs': torch.zeros(B, hyps, dtype=torch.float64),
+            'losses': torch.zeros(B, hyps, dtype=torch.float64),
+            'hyps_rt': torch.zeros(B, hyps, 6, dtype=torch.float64),
+            'ref_rt': torch.zeros(B, hyps, 6, dtype=torch.float64),
+            'tries': torch.zeros(B, hyps, dtype=torch.int32),
+            'cells': torch.zeros(B, hyps, 4, 2, dtype=torch.int32),
+        }
+    if coords_c.is_cuda:
+        torch.cuda.set_device(coords_c.device)
+    code = lib.cl_dsac_backward_rgb(
+        _ptr(coords_c), B, Hc, Wc, _ptr(grad), _ptr(gt), int(hyps), float(thr), _ptr(focal_t), float(cx), float(cy),
+        float(w_rot), float(w_trans), float(soft_clamp), float(alpha), float(max_reproj), int(subsample),
+        int(seed) & 0xFFFFFFFFFFFFFFFF, int(image_base) & 0xFFFFFFFF, int(max_tries), _ptr(forced_t), _ptr(loss),
+        _ptr(dbg['probs']) if dbg else None, _ptr(dbg['losses']) if dbg else None,
+        _ptr(dbg['hyps_rt']) if dbg else None, _ptr(dbg['ref_rt']) if dbg else None,
+        _ptr(dbg['tries']) if dbg else None, _ptr(dbg['cells']) if dbg else None, _stream_for(coords_c))
+    _lib.check(code)
+    return (loss, dbg) if debug else loss
+
+
+def backward_rgb(scene_coordinates, out_scene_coordinates_grad, gt_pose, ransac_hypotheses, inlier_threshold,
+                 focal_length, ppoint_x, ppoint_y, w_loss_rot, w_loss_trans, soft_clamp, inlier_alpha, max_reproj,
+                 sub_sampling, random_seed):
+    """`dsacstar.backward_rgb` (/root/reference/dsacstar/dsacstar.cpp:200-215, :889): [1,3,Hc,Wc] map, gradient tensor
+    of the same shape (accumulated into) and [4,4] ground-truth pose -> expected pose loss (Python float).
+
+    `random_seed` re-keys the sampler for this call as the reference's ThreadRand::init(randomSeed) does (:217).
+    Also accepts CUDA tensors and batches (then returns a [B] float64 tensor).  Never prints."""
+    gt = torch.as_tensor(gt_pose)
+    B = scene_coordinates.size(0)
+    loss = backward_rgb_batch(scene_coordinates, out_scene_coordinates_grad, gt.reshape(B, 4, 4), ransac_hypotheses,
+                              inlier_threshold, focal_length, ppoint_x, ppoint_y, w_loss_rot, w_loss_trans, soft_clamp,
+                              inlier_alpha, max_reproj, sub_sampling, seed=int(random_seed), image_base=0)
+    return float(loss[0]) if B == 1 else loss

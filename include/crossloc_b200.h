@@ -63,6 +63,34 @@ int cl_dsac_forward_rgb(const float* coords, int B, int Hc, int Wc, float* out_p
                         int32_t* out_tries, int32_t* out_counts, double* out_rt, void* cuda_stream);
 
 /*
+ * cl_dsac_backward_rgb -- replaces dsacstar_rgb_backward (/root/reference/dsacstar/dsacstar.cpp:200-215, bound as
+ * `dsacstar.backward_rgb` at :889): expected pose loss over all hypotheses and its gradient w.r.t. the scene
+ * coordinates (path I through the refined hypotheses, path II through the soft inlier scores; dsacstar_derivative.h,
+ * dsacstar_loss.h).  The reference handles one image per call; here B images, each as the reference would.
+ *
+ *   coords, B, Hc, Wc, hyps, thr, focal, cx, cy, alpha, max_reproj, subsample, seed, image_base, max_tries,
+ *   forced_samples       as for cl_dsac_forward_rgb
+ *   grad                 [B, 3, Hc, Wc] float32, ACCUMULATED into (+=) like outSceneCoordinatesGradSrc (:469-477)
+ *   gt_pose              [B, 16] float32 row-major ground-truth camera-to-world transforms (gtPoseSrc)
+ *   w_rot, w_trans       loss weights of the rotation (degrees) and translation error (wLossRot, wLossTrans)
+ *   soft_clamp           loss value above which sqrt(soft_clamp * loss) is used (softClamp)
+ *   out_loss             [B] double expected loss (the reference's return value)
+ *   out_probs            nullable [B, hyps] double selection probabilities
+ *   out_losses           nullable [B, hyps] double loss of every (refined) hypothesis
+ *   out_hyps             nullable [B, hyps, 6] double initial rvec, tvec
+ *   out_ref_rt           nullable [B, hyps, 6] double refined rvec, tvec (initial where the probability is < 0.001)
+ *   out_tries            nullable [B, hyps] int32 tries used
+ *   out_cells            nullable [B, hyps, 4, 2] int32 minimal sets (x, y)
+ * Workspace: B * hyps * Hc * Wc * 29 bytes (per-hypothesis gradient, error and inlier maps).
+ */
+int cl_dsac_backward_rgb(const float* coords, int B, int Hc, int Wc, float* grad, const float* gt_pose, int hyps,
+                         float thr, const float* focal, float cx, float cy, float w_rot, float w_trans,
+                         float soft_clamp, float alpha, float max_reproj, int subsample, uint64_t seed,
+                         uint32_t image_base, uint32_t max_tries, const int32_t* forced_samples, double* out_loss,
+                         double* out_probs, double* out_losses, double* out_hyps, double* out_ref_rt,
+                         int32_t* out_tries, int32_t* out_cells, void* cuda_stream);
+
+/*
  * Re-entrancy.  Intermediates of cl_dsac_forward_rgb (hypotheses, scores, error maps, staged host buffers) live in a
  * workspace private to (current device, cuda_stream): calls on different streams may be in flight together, calls
  * on one stream are serialised by the library.  Buffers grow on demand (the stream is synchronised before an old

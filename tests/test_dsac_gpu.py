@@ -116,7 +116,7 @@ def test_dsacstar_dropin_signature():
     t_err, r_err = synth.pose_errors(s['pose'], out_pose.numpy())
     assert t_err < 1.0 and r_err < 1.0
     with pytest.raises(NotImplementedError):
-        dsacstar.backward_rgb()
+        dsacstar.forward_rgbd()
 
 
 def test_full_size_batch_accuracy():

@@ -38,3 +38,31 @@ def has_duplicate_cells(cells):
 def score_mismatch(a, b, rel=1e-5):
     a, b = np.asarray(a), np.asarray(b)
     return np.abs(a - b) > rel * max(1.0, float(np.max(np.abs(a))))
+
+
+BACKWARD_GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'dsac_backward_golden.npz')
+
+
+def backward_module():
+    """tests/golden/make_backward_golden.py as a module (case table, parameters, ground-truth pose rule)."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location('make_backward_golden', os.path.join(ROOT, 'tests', 'golden', 'make_backward_golden.py'))
+    mod = importlib.util.module_from_spec(spec)
+    saved = list(sys.path)
+    spec.loader.exec_module(mod)
+    sys.path[:] = saved
+    return mod
+
+
+def backward_case(ci):
+    """Inputs (regenerated) and stored tier-1 outputs of backward fixture `ci` (tests/golden/make_backward_golden.py)."""
+    mod = backward_module()
+    idx, hyps, kw, skw = mod.CASES[ci]
+    scene = synth.make_scene(idx, **kw)
+    h, w = kw.get('height', 480), kw.get('width', 720)
+    p = dict(mod.PARAMS)
+    p.update(skw)
+    g = np.load(BACKWARD_GOLDEN)
+    ref = {k[len('case%d_' % ci):]: g[k] for k in g.files if k.startswith('case%d_' % ci)}
+    return idx, hyps, scene, mod.gt_pose_for(scene, idx), (w / 2, h / 2), p, ref
