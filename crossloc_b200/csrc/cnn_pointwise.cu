@@ -277,10 +277,42 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_apply_kernel(GnApplyDesc d)
 // image row: no divisions, the lane's affine parameters AND its group's (mean, 1/sigma) live in registers, a warp walks
 // along x with constant pointer strides (one pixel x 256 channels per step: 1 KB coalesced loads), four pixels in flight.
 // PLANES: bit 0 = e4m3 planes, bit 1 = block-scaled e2m1 planes.  Same arithmetic, bit for bit, as gn_apply_kernel.
+constexpr int kRowsU = 4;   // pixels a warp keeps in flight per batch
+
+template <int ADD_KIND>
+struct RowsBatch {
+    float4 r0[kRowsU], r1[kRowsU];
+    uint4 a0[kRowsU], a1[kRowsU];
+};
+
+template <int ADD_KIND>
+__device__ __forceinline__ void rows_load(RowsBatch<ADD_KIND>& q, const GnApplyDesc& d, const float* praw, const __half* pres,
+                                          const float* praw2, size_t estep, size_t res_lo, int x0, int xstep)
+{
+#pragma unroll
+    for (int u = 0; u < kRowsU; u++) {
+        if (x0 + u * xstep < d.W) {
+            const float4* r4 = reinterpret_cast<const float4*>(praw + u * estep);
+            q.r0[u] = __ldg(r4);
+            q.r1[u] = __ldg(r4 + 1);
+            if (ADD_KIND == 1) {
+                q.a0[u] = __ldg(reinterpret_cast<const uint4*>(pres + u * estep));
+                q.a1[u] = d.res_lo_rows > 0 ? __ldg(reinterpret_cast<const uint4*>(pres + u * estep + res_lo)) : make_uint4(0, 0, 0, 0);
+            } else if (ADD_KIND == 2) {
+                const uint4* q4 = reinterpret_cast<const uint4*>(praw2 + u * estep);
+                q.a0[u] = __ldg(q4);
+                q.a1[u] = __ldg(q4 + 1);
+            }
+        }
+    }
+}
+
 template <int ADD_KIND, int PLANES>
 __global__ void __launch_bounds__(256, 2) gn_apply_rows_kernel(GnApplyDesc d)
 {
-    constexpr int U = 4;
+    constexpr int U = kRowsU;
+    // register double buffering of the loads; the merging variants hold twice the operands and would spill
+    constexpr bool kPrefetch = ADD_KIND == 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kgroups = d.C >> 8;
     const int kg = warp % kgroups;
@@ -289,6 +321,19 @@ __global__ void __launch_bounds__(256, 2) gn_apply_rows_kernel(GnApplyDesc d)
     const int c = kg * 256 + lane * 8;
     const int Wp = d.W + 2;
     const size_t rows = (size_t)d.B * (d.H + 2) * Wp;
+    // running pointers of the warp's current pixel; one pixel step = xstep rows of the padded-flat matrices
+    const int xw = warp / kgroups;
+    const size_t row_first = ((size_t)b * (d.H + 2) + (y + 1)) * Wp + 1 + xw;
+    const size_t e_first = row_first * d.C + c;
+    const size_t estep = (size_t)xstep * d.C;        // elements per pixel step
+    const size_t lo_off = rows * d.C;                // element distance of the lo planes
+    const float* praw = d.raw + e_first;
+    const __half* pres = ADD_KIND == 1 ? d.res + e_first : nullptr;
+    const size_t res_lo = (size_t)d.res_lo_rows * d.C;
+    const float* praw2 = ADD_KIND == 2 ? d.raw2 + e_first : nullptr;
+    // the first batch of loads does not depend on the statistics: issue it before the fp64 mean / 1/sigma arithmetic
+    RowsBatch<ADD_KIND> cur, nxt;
+    rows_load<ADD_KIND>(cur, d, praw, pres, praw2, estep, res_lo, xw, xstep);
     float ga[8], be[8], mean = 0.f;
     float ga2[8], be2[8], mean2 = 0.f;
     {
@@ -313,44 +358,22 @@ __global__ void __launch_bounds__(256, 2) gn_apply_rows_kernel(GnApplyDesc d)
             }
         }
     }
-    // running pointers of the warp's current pixel; one pixel step = xstep rows of the padded-flat matrices
-    const int xw = warp / kgroups;
-    const size_t row_first = ((size_t)b * (d.H + 2) + (y + 1)) * Wp + 1 + xw;
-    const size_t e_first = row_first * d.C + c;
-    const size_t estep = (size_t)xstep * d.C;        // elements per pixel step
-    const size_t lo_off = rows * d.C;                // element distance of the lo planes
-    const float* praw = d.raw + e_first;
-    const __half* pres = ADD_KIND == 1 ? d.res + e_first : nullptr;
-    const size_t res_lo = (size_t)d.res_lo_rows * d.C;
-    const float* praw2 = ADD_KIND == 2 ? d.raw2 + e_first : nullptr;
     __half* pout = d.out + e_first;
     uint8_t* pout8 = (PLANES & 1) ? d.out8 + e_first : nullptr;
     uint8_t* pout4 = (PLANES & 2) ? d.out4 + e_first / 2 : nullptr;
     uint32_t* psf = (PLANES & 2) ? d.out_sf + (size_t)kg * rows + row_first : nullptr;
     const bool write_lo = d.out_terms == 2;
     for (int x0 = xw; x0 < d.W; x0 += xstep * U) {
-        float4 r0[U], r1[U];
-        uint4 a0[U], a1[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (x0 + u * xstep < d.W) {
-                const float4* r4 = reinterpret_cast<const float4*>(praw + u * estep);
-                r0[u] = __ldg(r4);
-                r1[u] = __ldg(r4 + 1);
-                if (ADD_KIND == 1) {
-                    a0[u] = __ldg(reinterpret_cast<const uint4*>(pres + u * estep));
-                    a1[u] = d.res_lo_rows > 0 ? __ldg(reinterpret_cast<const uint4*>(pres + u * estep + res_lo)) : make_uint4(0, 0, 0, 0);
-                } else if (ADD_KIND == 2) {
-                    const uint4* q4 = reinterpret_cast<const uint4*>(praw2 + u * estep);
-                    a0[u] = __ldg(q4);
-                    a1[u] = __ldg(q4 + 1);
-                }
-            }
-        }
+        // (plain variant) the next batch is in flight while this one is normalised and stored
+        praw += U * estep;
+        if (ADD_KIND == 1) pres += U * estep;
+        if (ADD_KIND == 2) praw2 += U * estep;
+        const bool more = x0 + xstep * U < d.W;
+        if (kPrefetch && more) rows_load<ADD_KIND>(nxt, d, praw, pres, praw2, estep, res_lo, x0 + xstep * U, xstep);
 #pragma unroll
         for (int u = 0; u < U; u++) {
             if (x0 + u * xstep >= d.W) break;   // warp-uniform
-            float v[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+            float v[8] = {cur.r0[u].x, cur.r0[u].y, cur.r0[u].z, cur.r0[u].w, cur.r1[u].x, cur.r1[u].y, cur.r1[u].z, cur.r1[u].w};
             if (d.group_ch) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) v[j] = (v[j] - mean) * ga[j] + be[j];
@@ -360,8 +383,8 @@ __global__ void __launch_bounds__(256, 2) gn_apply_rows_kernel(GnApplyDesc d)
                 for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
             }
             if (ADD_KIND == 1) {
-                const __half2* hh = reinterpret_cast<const __half2*>(&a0[u]);
-                const __half2* ll = reinterpret_cast<const __half2*>(&a1[u]);
+                const __half2* hh = reinterpret_cast<const __half2*>(&cur.a0[u]);
+                const __half2* ll = reinterpret_cast<const __half2*>(&cur.a1[u]);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const float2 a = __half22float2(hh[j]), bq = __half22float2(ll[j]);
@@ -369,8 +392,8 @@ __global__ void __launch_bounds__(256, 2) gn_apply_rows_kernel(GnApplyDesc d)
                     v[2 * j + 1] += a.y + bq.y;
                 }
             } else if (ADD_KIND == 2) {
-                const float w[8] = {__uint_as_float(a0[u].x), __uint_as_float(a0[u].y), __uint_as_float(a0[u].z), __uint_as_float(a0[u].w),
-                                    __uint_as_float(a1[u].x), __uint_as_float(a1[u].y), __uint_as_float(a1[u].z), __uint_as_float(a1[u].w)};
+                const float w[8] = {__uint_as_float(cur.a0[u].x), __uint_as_float(cur.a0[u].y), __uint_as_float(cur.a0[u].z), __uint_as_float(cur.a0[u].w),
+                                    __uint_as_float(cur.a1[u].x), __uint_as_float(cur.a1[u].y), __uint_as_float(cur.a1[u].z), __uint_as_float(cur.a1[u].w)};
 #pragma unroll
                 for (int j = 0; j < 8; j++) v[j] += (w[j] - mean2) * ga2[j] + be2[j];
             }
@@ -387,12 +410,11 @@ __global__ void __launch_bounds__(256, 2) gn_apply_rows_kernel(GnApplyDesc d)
                 if (lane == 0) psf[u * xstep] = word;
             }
         }
-        praw += U * estep;
-        if (ADD_KIND == 1) pres += U * estep;
-        if (ADD_KIND == 2) praw2 += U * estep;
         pout += U * estep;
         if (PLANES & 1) pout8 += U * estep;
         if (PLANES & 2) { pout4 += U * (estep / 2); psf += U * xstep; }
+        if (kPrefetch) cur = nxt;
+        else if (more) rows_load<ADD_KIND>(cur, d, praw, pres, praw2, estep, res_lo, x0 + xstep * U, xstep);
     }
 }
 

@@ -892,14 +892,19 @@ Plan* plan_for(Net& n, int B, int Cin, int H, int W, std::string& err)
     return out;
 }
 
-// Forwards of ALL handles on one device are chained by an event: a fused-epilogue convolution spins on publications of
-// its own grid, so two such launches from different streams, each holding part of the SMs, could wait for each other
-// forever.  Every forward saturates the chip on its own; nothing is lost by running them one after the other.
+// With the (opt-in) fused GroupNorm epilogue, forwards of ALL handles on one device are chained by an event: a
+// fused-epilogue convolution spins on publications of its own grid, so two such launches from different streams, each
+// holding part of the SMs, could wait for each other forever.  Without it forwards on different streams may overlap:
+// the memory-bound passes of one (GroupNorm apply, stem, head) then share the SMs with the tensor-bound convolutions
+// of the other (two-lane mode of crossloc_b200.pipeline).
 std::mutex g_chain_mutex;
 cudaEvent_t g_chain_event[64] = {};
 
+bool g_chain_enabled = false;   // set once a handle uses the fused GroupNorm epilogue (cl_net_create); never cleared
+
 const char* chain_begin(cudaStream_t stream, int dev)
 {
+    if (!g_chain_enabled) return nullptr;
     std::lock_guard<std::mutex> lock(g_chain_mutex);
     cudaEvent_t& ev = g_chain_event[dev & 63];
     if (!ev) {
@@ -912,6 +917,7 @@ const char* chain_begin(cudaStream_t stream, int dev)
 
 const char* chain_end(cudaStream_t stream, int dev)
 {
+    if (!g_chain_enabled) return nullptr;
     std::lock_guard<std::mutex> lock(g_chain_mutex);
     cudaError_t e = cudaEventRecord(g_chain_event[dev & 63], stream);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
@@ -1020,6 +1026,7 @@ extern "C" int cl_net_create(const cl_net_desc* desc, cl_net** out)
     n->use_graph = !(env && env[0] == '0');
     env = getenv("CROSSLOC_B200_FUSE_GN");
     n->fuse_gn = env && env[0] == '1';   // opt-in: measured slower than conv + gn_apply (26.5 vs 23.2 ms per 32 frames)
+    if (n->fuse_gn) g_chain_enabled = true;
     env = getenv("CROSSLOC_B200_DYNAMIC_TILES");
     n->dynamic_tiles = !(env && env[0] == '0');
     auto idx_ok = [&](int i) { return i >= 0 && i < desc->n_layers; };
