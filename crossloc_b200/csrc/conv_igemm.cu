@@ -1044,9 +1044,13 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 __device__ unsigned long long g_conv_dbg[16];   // wait cycles by site (debug builds only): see cl_debug_counters
 #define CL_DBG_T0() const long long _t0 = clock64()
 #define CL_DBG_ADD(i) do { if (lane == 0) atomicAdd(&g_conv_dbg[i], (unsigned long long)(clock64() - _t0)); } while (0)
+#define CL_DBG_MARK(name) const long long name = clock64()
+#define CL_DBG_SINCE(i, name) do { if (lane == 0) atomicAdd(&g_conv_dbg[i], (unsigned long long)(clock64() - name)); } while (0)
 #else
 #define CL_DBG_T0() do {} while (0)
 #define CL_DBG_ADD(i) do {} while (0)
+#define CL_DBG_MARK(name) do {} while (0)
+#define CL_DBG_SINCE(i, name) do {} while (0)
 #endif
 constexpr uint32_t kSfStageBytes = 4096;   // shared memory reserved per pipeline stage for the scale ring below
 constexpr int kSfSlots = 8;                // the scales have their own ring (only pass 0 uses them): a slot = 512 B activation
@@ -1383,8 +1387,9 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 // shares) go first, one per warp group
                 const int c0 = as ? idx * 16 : (idx < 2 ? (nchunks - 2 + idx) * 16 : (idx - 2) * 16);
                 uint32_t u[16];
-                ptx::tmem_ld_32x16(taddr + (uint32_t)c0, u);
-                ptx::tmem_ld_wait();
+                { CL_DBG_T0(); ptx::tmem_ld_32x16(taddr + (uint32_t)c0, u);
+                ptx::tmem_ld_wait(); if (warp == 4) CL_DBG_ADD(8); }
+                CL_DBG_MARK(t_store);
                 if (idx < 2) {
                     // this warp is done with the previous tile and with the shared columns of this one
                     ptx::tc_fence_before();
@@ -1419,6 +1424,12 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     ptx::tma_store_2d(&tmO, sbuf, n0 + c0, m0 + q * 32);
                     ptx::tma_store_commit();
                 }
+                // Measured with the debug counters (1x1 512->512, cycles per 16-column chunk and warp): tensor-memory load
+                // 35, scale / bias / staging / TMA store 700, GroupNorm sums 810.  Tried and dropped: one reduce-scatter of
+                // the sums per tile instead of per chunk (sums 810 -> 300, 1x1 layers 0.22 -> 0.20 ms, but 123 instead of 86
+                // registers and no gain on the whole step); staged coalesced st.global instead of the TMA store (920 cycles).
+                if (warp == 4) CL_DBG_SINCE(9, t_store);
+                CL_DBG_MARK(t_stats);
                 if (p.group_ch) {
                     const int first_group = (n0 + c0) / p.group_ch;
                     switch (p.group_ch) {
@@ -1429,6 +1440,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                         default: break;
                     }
                 }
+                if (warp == 4) CL_DBG_SINCE(10, t_stats);
             }
             ptx::tc_fence_before();
         }
