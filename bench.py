@@ -367,6 +367,7 @@ def train_workload(dev, steps=5, warmup=2):
     grid = torch.stack([xs[None, :].expand(135, 135), xs[:, None].expand(135, 135)]).to(dev)
     out = {'batch': batch, 'steps': steps}
     variants = (('native_fused', lambda t: train_plan.forward_train(net, t)),
+                ('native_fused_tf32_grade', lambda t: train_plan.forward_train(net, t, backward='fp16x1')),
                 ('stock_autograd_cudnn_tf32', net.forward_reference))
     for name, fwd in variants:
         ms = []
@@ -385,6 +386,14 @@ def train_workload(dev, steps=5, warmup=2):
                 ms.append(e0.elapsed_time(e1))
         out[name] = {'ms_per_step': sum(ms) / len(ms), 'images_per_s': batch * 1e3 * len(ms) / sum(ms), 'loss': float(loss)}
     out['speedup_vs_stock'] = out['stock_autograd_cudnn_tf32']['ms_per_step'] / out['native_fused']['ms_per_step']
+    out['speedup_vs_stock_tf32_grade'] = out['stock_autograd_cudnn_tf32']['ms_per_step'] / out['native_fused_tf32_grade']['ms_per_step']
+    out['arithmetic'] = {
+        'native_fused': 'forward %s, data gradients fp16x3 (three fp16 MMAs per product, fp32 accumulate), weight gradients %s '
+                        '(one pass: all gradients within 3.1e-5 relative L2 of the three-term result, tools/dbg_wgrad_precision.py)'
+                        % (train_plan.FORWARD, train_plan.WGRAD),
+        'native_fused_tf32_grade': 'both gradient GEMMs in one fp16 pass (10-bit mantissa operands like the TF32 kernels stock '
+                                   'PyTorch trains with; gradients within 3.0e-4 of the three-term result)',
+        'stock_autograd_cudnn_tf32': 'torch defaults: cuDNN convolutions with TF32 allowed'}
     out['peak_mem_gb'] = torch.cuda.max_memory_allocated() / 1e9
     del net, opt
     torch.cuda.empty_cache()

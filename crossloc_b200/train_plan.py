@@ -33,6 +33,12 @@ BACKWARD = os.environ.get('CROSSLOC_B200_TRAIN_BACKWARD', 'fp16x3')
 # arithmetic of the forward convolutions: the inference default ('fp16+fp8': e4m3 correction terms on the large layers,
 # 3e-5 relative on the coordinate map) or 'fp16x3'
 FORWARD = os.environ.get('CROSSLOC_B200_TRAIN_FORWARD', 'fp16+fp8')
+# arithmetic of the weight gradient GEMMs alone: one fp16 pass by default.  A weight gradient is one sum over every pixel of
+# the batch (5,400 x batch terms per entry at 60 x 90 cells): the operand rounding averages out and, unlike in the data gradient,
+# does not travel on through the layers below.  Measured on the BASELINE config-4 step (tools/dbg_wgrad_precision.py, batch
+# 12, same forward and data gradients): all gradients move by 3.1e-5 relative L2 (worst convolution weight 8.1e-5, median
+# 1.3e-5) against fp16x3 weight gradients, for 4.7 ms less per step.  'fp16x3' restores the three-term products.
+WGRAD = os.environ.get('CROSSLOC_B200_TRAIN_WGRAD', 'fp16x1')
 _RESCALE_EVERY = 64   # steps between host-side refreshes of the filters' power-of-two scales
 
 
@@ -69,13 +75,15 @@ def supported(net):
 
 
 class TrainPlan:
-    def __init__(self, net, backward=None, forward=None):
+    def __init__(self, net, backward=None, forward=None, wgrad=None):
         self.net = net
         forward = forward or FORWARD
         backward = backward or BACKWARD
-        if backward not in ('fp16x3', 'fp16x1'):
-            raise ValueError('unknown backward arithmetic %r (fp16x3 | fp16x1)' % (backward,))
+        wgrad = wgrad or ('fp16x1' if backward == 'fp16x1' else WGRAD)
+        if backward not in ('fp16x3', 'fp16x1') or wgrad not in ('fp16x3', 'fp16x1'):
+            raise ValueError('unknown backward arithmetic %r / %r (fp16x3 | fp16x1)' % (backward, wgrad))
         self.bwd_terms = 3 if backward == 'fp16x3' else 1
+        self.wgrad_terms = 3 if wgrad == 'fp16x3' else 1
         self._zero_bias = {}
         self.engine = CoordNetEngine(precision=forward)
         self.engine.packer = self._packer
@@ -170,7 +178,7 @@ class TrainPlan:
             tphase.append(ph)
             shifts.append(t - ph * geo.Mp)
         _lib.check(lib.cl_conv_wgrad_pf(d_raw.data_ptr(), geo.Mp, act.h16.data_ptr(), geo.Mp, geo.Mp, cout, cin, act.phases,
-                                        k * k, _i32(shifts), _i32(tphase), self.bwd_terms, 1.0, scale_out[1:2].data_ptr(), 1,
+                                        k * k, _i32(shifts), _i32(tphase), self.wgrad_terms, 1.0, scale_out[1:2].data_ptr(), 1,
                                         gw.data_ptr(), stream))
         if not need_dgrad:
             return None
@@ -333,12 +341,13 @@ class _FusedStep(torch.autograd.Function):
         return (None, None) + tuple(grads.get(id(p)) if ctx.needs_input_grad[2 + i] else None for i, p in enumerate(ctx.params))
 
 
-def forward_train(net, image, backward=None, forward=None):
+def forward_train(net, image, backward=None, forward=None, wgrad=None):
     """Differentiable forward of `net` through the fused plan (one autograd node for the whole network)."""
     plan = getattr(net, '_train_plan', None)
     if (plan is None or (backward is not None and plan.bwd_terms != (3 if backward == 'fp16x3' else 1))
+            or (wgrad is not None and plan.wgrad_terms != (3 if wgrad == 'fp16x3' else 1))
             or (forward is not None and plan.engine.precision != forward)):
-        plan = TrainPlan(net, backward, forward)
+        plan = TrainPlan(net, backward, forward, wgrad)
         object.__setattr__(net, '_train_plan', plan)
     params = tuple(p for p in net.parameters())
     return _FusedStep.apply(plan, image.contiguous().to(torch.float32), *params)
