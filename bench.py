@@ -388,9 +388,10 @@ def train_workload(dev, steps=5, warmup=2):
     out['speedup_vs_stock'] = out['stock_autograd_cudnn_tf32']['ms_per_step'] / out['native_fused']['ms_per_step']
     out['speedup_vs_stock_tf32_grade'] = out['stock_autograd_cudnn_tf32']['ms_per_step'] / out['native_fused_tf32_grade']['ms_per_step']
     out['arithmetic'] = {
-        'native_fused': 'forward %s, data gradients fp16x3 (three fp16 MMAs per product, fp32 accumulate), weight gradients %s '
-                        '(one pass: all gradients within 3.1e-5 relative L2 of the three-term result, tools/dbg_wgrad_precision.py)'
-                        % (train_plan.FORWARD, train_plan.WGRAD),
+        'native_fused': 'forward %s, data gradients %s (fp16 + block-scaled e2m1 correction products on the 256/512-channel '
+                        'layers, fp16x3 elsewhere), weight gradients %s (one fp16 pass); all gradients within 5.3e-5 relative L2 '
+                        'of the all-fp16x3 backward (worst convolution weight 1.4e-4; tools/dbg_wgrad_precision.py)'
+                        % (train_plan.FORWARD, train_plan.BACKWARD, train_plan.WGRAD),
         'native_fused_tf32_grade': 'both gradient GEMMs in one fp16 pass (10-bit mantissa operands like the TF32 kernels stock '
                                    'PyTorch trains with; gradients within 3.0e-4 of the three-term result)',
         'stock_autograd_cudnn_tf32': 'torch defaults: cuDNN convolutions with TF32 allowed'}

@@ -47,6 +47,11 @@ SIGNATURES = {
         _c.c_float, _c.c_int, _c.c_int, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _i32p,
         _i32p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p,
         _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'cl_gn_backward_fp4': (_c.c_int, [
+        _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+        _c.c_float, _c.c_int, _c.c_int, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _i32p,
+        _i32p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p,
+        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p]),
     'cl_head_backward': (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
                                     _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     'cl_nchw_to_pf': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,

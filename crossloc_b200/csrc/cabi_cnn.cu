@@ -253,12 +253,13 @@ extern "C" int cl_conv_wgrad_pf(const void* grad, int64_t g_plane_rows, const vo
     return finish(kFn, cl::conv_wgrad_pf_launch(d, static_cast<cudaStream_t>(cuda_stream)));
 }
 
-extern "C" int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch, const float* raw, const double* stats,
-                              const float* gamma, const float* beta, float eps, int relu_inner, int num_src,
-                              const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
-                              const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out,
-                              double* ab, int ab_C, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows,
-                              float* scale_out, double* dbias, float* d_raw_f32, void* cuda_stream)
+extern "C" int cl_gn_backward_fp4(int pass, int B, int H, int W, int C, int group_ch, const float* raw, const double* stats,
+                                  const float* gamma, const float* beta, float eps, int relu_inner, int num_src,
+                                  const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
+                                  const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out,
+                                  double* ab, int ab_C, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows,
+                                  float* scale_out, double* dbias, float* d_raw_f32, void* d_raw4, int64_t d_raw4_lo_rows,
+                                  void* d_raw_sf, void* cuda_stream)
 {
     static const char* kFn = "cl_gn_backward";
     NEED_DEV(raw); NEED_DEV(ab); NEED_DEV(gmax_bits);
@@ -279,10 +280,24 @@ extern "C" int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch
     d.gmax_bits = static_cast<unsigned*>(gmax_bits); d.d_raw = static_cast<__half*>(d_raw); d.d_raw_lo_rows = d_raw_lo_rows;
     d.scale_out = scale_out; d.dbias = dbias; d.d_raw_f32 = d_raw_f32;
     if (d_raw_f32) NEED_DEV(d_raw_f32);
+    if (d_raw4) { NEED_DEV(d_raw4); NEED_DEV(d_raw_sf); }
+    d.d_raw4 = static_cast<uint8_t*>(d_raw4); d.d_raw4_lo_rows = d_raw4_lo_rows; d.d_raw_sf = static_cast<uint32_t*>(d_raw_sf);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (pass == 0) return finish(kFn, cl::gn_bwd_reduce_launch(d, s));
     NEED_DEV(d_raw); NEED_DEV(scale_out);
     return finish(kFn, cl::gn_bwd_apply_launch(d, s));
+}
+
+extern "C" int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch, const float* raw, const double* stats,
+                              const float* gamma, const float* beta, float eps, int relu_inner, int num_src,
+                              const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
+                              const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out,
+                              double* ab, int ab_C, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows,
+                              float* scale_out, double* dbias, float* d_raw_f32, void* cuda_stream)
+{
+    return cl_gn_backward_fp4(pass, B, H, W, C, group_ch, raw, stats, gamma, beta, eps, relu_inner, num_src, src, src_scale_a,
+                              src_scale_b, src_stride, src_phased, mask_out, g_out, ab, ab_C, gmax_bits, d_raw, d_raw_lo_rows,
+                              scale_out, dbias, d_raw_f32, nullptr, 0, nullptr, cuda_stream);
 }
 
 extern "C" int cl_frames_to_nchw(const uint8_t* frames, int B, int H, int W, int C, const float* mean, const float* stdv,

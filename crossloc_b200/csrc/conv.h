@@ -235,6 +235,11 @@ struct GnBwdDesc {
     float* scale_out;       // pass 2: {2^k, 2^-k}
     double* dbias;          // pass 2, nullable: [C] += sum d_raw (gradient of the convolution bias)
     float* d_raw_f32;       // pass 2, nullable: the same gradient unscaled in fp32 PF [rows][C] (stem: weight gradient in torch)
+    // pass 2, nullable (C % 256 == 0): block-scaled e2m1 planes of the scaled gradient for a data gradient in fp16 + fp4 mode,
+    // in the layout cl_gn_apply_fp4 writes for the forward: [2][d_raw4_lo_rows][C/2] and scale words [C/256][d_raw4_lo_rows]
+    uint8_t* d_raw4;
+    int64_t d_raw4_lo_rows;
+    uint32_t* d_raw_sf;
 };
 const char* gn_bwd_reduce_launch(const GnBwdDesc& d, cudaStream_t stream);
 

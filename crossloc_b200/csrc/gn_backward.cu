@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "conv.h"
+#include "fp4_planes.cuh"
 
 namespace cl {
 
@@ -210,6 +211,16 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 4 : 3) gn_bwd_kernel(GnBwdDe
             }
             *reinterpret_cast<uint4*>(d.d_raw + row * d.C + c) = *reinterpret_cast<const uint4*>(h);
             *reinterpret_cast<uint4*>(d.d_raw + (row + (size_t)d.d_raw_lo_rows) * d.C + c) = *reinterpret_cast<const uint4*>(l);
+            if (d.d_raw4) {
+                // C % 256 == 0: the 32 lanes of a warp hold the 256 channels of one pixel and walk the pixels together
+                float sv8[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) sv8[j] = dr[j] * out_scale;
+                const size_t half_c = (size_t)d.C / 2;
+                const uint32_t word = fp4_store8(d.d_raw4 + row * half_c + c / 2,
+                                                 d.d_raw4 + (row + (size_t)d.d_raw4_lo_rows) * half_c + c / 2, sv8);
+                if ((c & 255) == 0) d.d_raw_sf[(size_t)(c >> 8) * (size_t)d.d_raw4_lo_rows + row] = word;
+            }
         }
     }
 
@@ -383,6 +394,8 @@ const char* gn_bwd_apply_launch(const GnBwdDesc& d, cudaStream_t stream)
 {
     if (const char* e = check(d)) return e;
     if (!d.ab || !d.gmax_bits || !d.d_raw || !d.scale_out) return "gn_backward: the apply pass needs ab, gmax, d_raw and scale_out";
+    if (d.d_raw4 && (d.C % 256 != 0 || !d.d_raw_sf || d.d_raw4_lo_rows <= 0))
+        return "gn_backward: e2m1 gradient planes need C % 256 == 0, the scale table and the plane distance";
     if (d.group_ch % 8 == 0) gn_bwd_kernel<true, true><<<dim3(grid_x(d, 4), d.B), kThreads, 0, stream>>>(d);
     else gn_bwd_kernel<true, false><<<dim3(grid_x(d, 4), d.B), kThreads, 0, stream>>>(d);
     cudaError_t e = cudaGetLastError();

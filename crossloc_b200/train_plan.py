@@ -27,9 +27,11 @@ from .cnn import CoordNetEngine, _nterms_for, _W8_LO_SCALE
 from .train import _i32, _pack
 
 _NTERMS = 3
-# arithmetic of the data / weight gradient GEMMs: 'fp16x3' (default, fp32-grade like the forward) or 'fp16x1' (one
-# fp16 pass with fp32 accumulation: the 10-bit mantissa of the TF32 kernels stock PyTorch trains with by default)
-BACKWARD = os.environ.get('CROSSLOC_B200_TRAIN_BACKWARD', 'fp16x3')
+# arithmetic of the data gradient GEMMs: 'fp16+fp4' (default: a_hi*w_hi in fp16 plus the two correction products as
+# block-scaled e2m1 MMAs, the inference scheme, on the layers whose channel counts are multiples of 256; the others stay
+# fp16x3), 'fp16x3' (three fp16 MMAs per product) or 'fp16x1' (one fp16 pass with fp32 accumulation: the 10-bit mantissa
+# of the TF32 kernels stock PyTorch trains with by default)
+BACKWARD = os.environ.get('CROSSLOC_B200_TRAIN_BACKWARD', 'fp16+fp4')
 # arithmetic of the forward convolutions: the inference default ('fp16+fp8': e4m3 correction terms on the large layers,
 # 3e-5 relative on the coordinate map) or 'fp16x3'
 FORWARD = os.environ.get('CROSSLOC_B200_TRAIN_FORWARD', 'fp16+fp8')
@@ -80,9 +82,11 @@ class TrainPlan:
         forward = forward or FORWARD
         backward = backward or BACKWARD
         wgrad = wgrad or ('fp16x1' if backward == 'fp16x1' else WGRAD)
-        if backward not in ('fp16x3', 'fp16x1') or wgrad not in ('fp16x3', 'fp16x1'):
-            raise ValueError('unknown backward arithmetic %r / %r (fp16x3 | fp16x1)' % (backward, wgrad))
-        self.bwd_terms = 3 if backward == 'fp16x3' else 1
+        if backward not in ('fp16+fp4', 'fp16x3', 'fp16x1') or wgrad not in ('fp16x3', 'fp16x1'):
+            raise ValueError('unknown backward arithmetic %r / %r (fp16+fp4 | fp16x3 | fp16x1)' % (backward, wgrad))
+        self.backward_mode = backward
+        self.bwd_terms = 1 if backward == 'fp16x1' else 3      # layers outside the fp4 scheme
+        self.bwd_fp4 = backward == 'fp16+fp4'
         self.wgrad_terms = 3 if wgrad == 'fp16x3' else 1
         self._zero_bias = {}
         self.engine = CoordNetEngine(precision=forward)
@@ -126,6 +130,19 @@ class TrainPlan:
             buf = self._pool[key] = torch.zeros(2 * geo.Mp, channels, dtype=torch.float16, device=device)
         return buf
 
+    def _fp4_planes(self, geo, channels, device):
+        """e2m1 planes + scale words of a scaled gradient (zero borders, written once), recycled like `_zeros_pf`."""
+        key = ('fp4', geo.B, geo.H, geo.W, channels, str(device))
+        buf = self._pool.get(key)
+        if buf is None:
+            buf = self._pool[key] = (torch.zeros(2 * geo.Mp, channels // 2, dtype=torch.uint8, device=device),
+                                     torch.zeros(channels // 256 * geo.Mp, dtype=torch.int32, device=device))
+        return buf
+
+    def _fp4_dgrad(self, pack):
+        """The data gradient of this convolution runs in fp16 + fp4 mode: stride 1, both channel counts multiples of 256."""
+        return self.bwd_fp4 and pack.stride == 1 and pack.cin % 256 == 0 and pack.cout % 256 == 0
+
     def _gn_backward(self, lib, stream, geo, channels, rec, norm, relu_inner, srcs, mask, want_g, d_raw_f32=None, acc=None):
         """Both passes of cl_gn_backward for one stage; returns (d_raw, scale_out, ab, dbias, g_buf).
         `acc` = (ab pointer, channels per image of the shared ab buffer, dbias view, two-double scratch view) places the
@@ -144,6 +161,8 @@ class TrainPlan:
         scale_out = misc[1:2].view(torch.float32)
         g_buf = torch.empty(geo.Mp, channels, dtype=torch.float32, device=dev) if want_g else None
         d_raw = self._zeros_pf(geo, channels, dev)
+        fp4 = self._fp4_planes(geo, channels, dev) if ('pack' in rec and self._fp4_dgrad(rec['pack'])) else None
+        rec['d_raw4'] = fp4
         group_ch = 0 if norm is None else channels // norm.num_groups
 
         def call(pass_id, sources):
@@ -151,7 +170,7 @@ class TrainPlan:
             ptrs = (ctypes.c_void_p * 3)(*[s.g.data_ptr() for s in sources] + [None] * (3 - n))
             sa = (ctypes.c_void_p * 3)(*[None if s.scale_a is None else s.scale_a.data_ptr() for s in sources] + [None] * (3 - n))
             sb = (ctypes.c_void_p * 3)(*[None if s.scale_b is None else s.scale_b.data_ptr() for s in sources] + [None] * (3 - n))
-            _lib.check(lib.cl_gn_backward(
+            _lib.check(lib.cl_gn_backward_fp4(
                 pass_id, geo.B, geo.H, geo.W, channels, group_ch, rec['raw'].data_ptr(),
                 None if norm is None else rec['stats'].data_ptr(), None if norm is None else norm.weight.data_ptr(),
                 None if norm is None else norm.bias.data_ptr(), 1e-5 if norm is None else float(norm.eps),
@@ -160,7 +179,8 @@ class TrainPlan:
                 None if (mask is None or pass_id == 1) else mask.data_ptr(),
                 None if (g_buf is None or pass_id == 1) else g_buf.data_ptr(), ab_ptr, ab_C, gmax.data_ptr(),
                 d_raw.data_ptr(), geo.Mp, scale_out.data_ptr(), dbias.data_ptr(),
-                None if (d_raw_f32 is None or pass_id == 0) else d_raw_f32.data_ptr(), stream))
+                None if (d_raw_f32 is None or pass_id == 0) else d_raw_f32.data_ptr(),
+                None if fp4 is None else fp4[0].data_ptr(), geo.Mp, None if fp4 is None else fp4[1].data_ptr(), stream))
 
         call(0, srcs)
         call(1, [_Src(g_buf, channels)] if want_g else srcs[:1])
@@ -190,6 +210,19 @@ class TrainPlan:
 
         def igemm(pairs, shifts, raw):
             packed = _pack(pack.weight, pack.scale, pairs, True, n_out, cout)
+            fp4 = rec.get('d_raw4')
+            if fp4 is not None and stride == 1 and len(pairs) == k * k:
+                # fp16 + fp4: e2m1 planes of the transposed filter, packed on the device from its OIHW view
+                w_t = pack.weight.permute(1, 0, 2, 3).contiguous()
+                w4 = torch.empty(2 * len(pairs) * n_out, cout // 2, dtype=torch.uint8, device=dev)
+                w_sf = torch.empty(len(pairs) * (cout // 256) * n_out, dtype=torch.int32, device=dev)
+                _lib.check(lib.cl_pack_conv_fp4(w_t.data_ptr(), n_out, cout, len(pairs), 1.0 / pack.out_scale, w4.data_ptr(),
+                                                w_sf.data_ptr(), stream))
+                _lib.check(lib.cl_conv_igemm_fp4(d_raw.data_ptr(), d_raw.size(0), geo.Mp, cout, packed.data_ptr(), n_out,
+                                                 len(shifts), _i32(shifts), geo.Mp, geo.Hp, geo.Wp, 0, 1.0, raw.data_ptr(),
+                                                 zero_bias.data_ptr(), None, fp4[0].data_ptr(), fp4[0].size(0), geo.Mp,
+                                                 fp4[1].data_ptr(), w4.data_ptr(), w_sf.data_ptr(), stream))
+                return
             _lib.check(lib.cl_conv_igemm(d_raw.data_ptr(), d_raw.size(0), geo.Mp, cout, packed.data_ptr(), n_out,
                                          len(shifts), _i32(shifts), self.bwd_terms, geo.Mp, geo.Hp, geo.Wp, 0, 1.0,
                                          raw.data_ptr(), zero_bias.data_ptr(), 0, 0, 0, 0, 0, stream))
@@ -344,7 +377,7 @@ class _FusedStep(torch.autograd.Function):
 def forward_train(net, image, backward=None, forward=None, wgrad=None):
     """Differentiable forward of `net` through the fused plan (one autograd node for the whole network)."""
     plan = getattr(net, '_train_plan', None)
-    if (plan is None or (backward is not None and plan.bwd_terms != (3 if backward == 'fp16x3' else 1))
+    if (plan is None or (backward is not None and plan.backward_mode != backward)
             or (wgrad is not None and plan.wgrad_terms != (3 if wgrad == 'fp16x3' else 1))
             or (forward is not None and plan.engine.precision != forward)):
         plan = TrainPlan(net, backward, forward, wgrad)

@@ -196,6 +196,15 @@ int cl_gn_backward(int pass, int B, int H, int W, int C, int group_ch, const flo
                    const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out, double* ab,
                    int ab_C, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows, float* scale_out, double* dbias,
                    float* d_raw_f32, void* cuda_stream);
+/* The same with, in pass 1, block-scaled e2m1 planes of the scaled gradient next to the fp16 ones (C % 256 == 0), in the
+ * layout cl_gn_apply_fp4 writes for the forward: d_raw4 [2][d_raw4_lo_rows][C/2], d_raw_sf uint32 [C/256][d_raw4_lo_rows].
+ * They feed cl_conv_igemm_fp4 with the transposed filter = the data gradient at 1.5 fp16-MMA equivalents per product. */
+int cl_gn_backward_fp4(int pass, int B, int H, int W, int C, int group_ch, const float* raw, const double* stats,
+                       const float* gamma, const float* beta, float eps, int relu_inner, int num_src,
+                       const float* const* src, const float* const* src_scale_a, const float* const* src_scale_b,
+                       const int32_t* src_stride, const int32_t* src_phased, const void* mask_out, float* g_out, double* ab,
+                       int ab_C, void* gmax_bits, void* d_raw, int64_t d_raw_lo_rows, float* scale_out, double* dbias,
+                       float* d_raw_f32, void* d_raw4, int64_t d_raw4_lo_rows, void* d_raw_sf, void* cuda_stream);
 
 /*
  * Backward of the 1x1 output head (fc3, networks.py:349) on the padded-flat activation it read (training step):

@@ -65,6 +65,8 @@ def report(tag, g):
 
 report('repeat (atomics order)', again)
 report('wgrad fp16x1', step('fp16x3', 'fp16x1'))
+report('dgrad fp16+fp4, wgrad fp16x3', step('fp16+fp4', 'fp16x3'))
+report('dgrad fp16+fp4, wgrad fp16x1', step('fp16+fp4', 'fp16x1'))
 report('dgrad + wgrad fp16x1', step('fp16x1', 'fp16x1'))
-for bw, wg in (('fp16x3', 'fp16x3'), ('fp16x3', 'fp16x1'), ('fp16x1', 'fp16x1')):
+for bw, wg in (('fp16x3', 'fp16x3'), ('fp16x3', 'fp16x1'), ('fp16+fp4', 'fp16x1'), ('fp16x1', 'fp16x1')):
     print('fwd+loss+bwd  dgrad %s wgrad %s: %.2f ms' % (bw, wg, timed(bw, wg)), flush=True)
