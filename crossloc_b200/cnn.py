@@ -26,11 +26,15 @@ _W8_LO_SCALE = 4096.0   # csrc/conv.h kW8LoScale
 _FP8_1X1 = os.environ.get('CROSSLOC_B200_FP8_1X1', '1') != '0'   # 1x1 512->512 layers in the fp16 + fp8 scheme too
 
 
-def _nterms_for(precision, cin, ksize, stride):
-    """MMA scheme of one convolution: 1 = fp16, 2 = fp16 + e4m3 corrections, 3 = fp16x3."""
+def _nterms_for(precision, cin, ksize, stride, cout=None):
+    """MMA scheme of one convolution: 1 = fp16, 2 = fp16 + e4m3 corrections, 3 = fp16x3, 4 = fp16 + block-scaled e2m1
+    corrections (only with `cout`: both channel counts must be multiples of 256)."""
     if precision == 'fp16x1':
         return 1
-    if precision == 'fp16+fp8' and stride == 1 and cin % 128 == 0 and cin >= 256 and (ksize == 3 or (_FP8_1X1 and cin >= 512)):
+    wide = stride == 1 and cin % 128 == 0 and cin >= 256 and (ksize == 3 or (_FP8_1X1 and cin >= 512))
+    if precision == 'fp16+fp4' and wide:
+        return 4 if (cout is not None and cin % 256 == 0 and cout % 256 == 0) else 2
+    if precision == 'fp16+fp8' and wide:
         return 2
     return 3
 
@@ -59,8 +63,22 @@ class PackedConv:
         if nterms == 2:
             self.weights8 = torch.stack([hi.to(torch.float32).to(torch.float8_e4m3fn),
                                          (lo * _W8_LO_SCALE).to(torch.float8_e4m3fn)], 0).contiguous()
+        self.weights4 = self.w_sf = None
+        if nterms == 4:
+            self.weights4, self.w_sf = pack_fp4(weight.detach().to(torch.float32).contiguous(), 2.0 ** exp)
         self.bias = (bias.detach().to(torch.float32) if bias is not None
                      else torch.zeros(cout, dtype=torch.float32, device=weight.device)).contiguous()
+
+
+def pack_fp4(weight, scale):
+    """OIHW fp32 filter (x scale, a power of two) -> (e2m1 planes [2 * taps * Cout][Cin / 2], scale words) of cl_pack_conv_fp4."""
+    cout, cin, kh, kw = weight.shape
+    taps = kh * kw
+    w4 = torch.empty(2 * taps * cout, cin // 2, dtype=torch.uint8, device=weight.device)
+    w_sf = torch.empty(taps * (cin // 256) * cout, dtype=torch.int32, device=weight.device)
+    _lib.check(_lib.load().cl_pack_conv_fp4(weight.data_ptr(), cout, cin, taps, float(scale), w4.data_ptr(), w_sf.data_ptr(),
+                                            torch.cuda.current_stream(weight.device).cuda_stream))
+    return w4, w_sf
 
 
 class _Geometry:
@@ -81,6 +99,7 @@ class _PF:
         # zero-initialised once: kernels only ever write interior pixels, so the borders stay zero
         self.h16 = torch.zeros(terms * phases * geo.Mp, channels, dtype=torch.float16, device=device)
         self._f8 = None
+        self._f4 = None
         self._device = device
 
     @property
@@ -88,6 +107,15 @@ class _PF:
         if self._f8 is None:
             self._f8 = torch.zeros(2 * self.phases * self.geo.Mp, self.channels, dtype=torch.uint8, device=self._device)
         return self._f8
+
+    @property
+    def f4(self):
+        """(e2m1 planes [2 * Mp][C / 2], scale words [C / 256 * Mp]) of the fp16 + fp4 mode (same-resolution activations)."""
+        if self._f4 is None:
+            assert self.phases == 1 and self.channels % 256 == 0
+            self._f4 = (torch.zeros(2 * self.geo.Mp, self.channels // 2, dtype=torch.uint8, device=self._device),
+                        torch.zeros(self.channels // 256 * self.geo.Mp, dtype=torch.int32, device=self._device))
+        return self._f4
 
 
 def _taps(pack, geo):
@@ -109,14 +137,16 @@ def _taps(pack, geo):
 class CoordNetEngine:
     """Runs the coordinate network of an nn.Module twin (networks.networks.TransPoseNet / Network)."""
 
-    def __init__(self, precision=None):
+    def __init__(self, precision=None, fp4=False):
         self.precision = precision or PRECISION
-        if self.precision == 'fp16+fp4':
-            self.precision = 'fp16+fp8'   # the e2m1 corrections exist in the C++ runtime (csrc/net.cu) only; this plan keeps e4m3
-        if self.precision not in _PRECISIONS:
+        if self.precision == 'fp16+fp4' and not fp4:
+            # inference runs the e2m1 corrections in the C++ runtime (csrc/net.cu); this plan keeps e4m3 unless asked
+            # (fp4=True: the training forward of crossloc_b200.train_plan, plans without MLR merge / full-size head)
+            self.precision = 'fp16+fp8'
+        if self.precision not in _PRECISIONS and self.precision != 'fp16+fp4':
             raise ValueError('unknown conv precision %r (%s)' % (self.precision, ' | '.join(_PRECISIONS)))
         self.terms = 1 if self.precision == 'fp16x1' else 2
-        self.nterms = {'fp16x1': 1, 'fp16x3': 3, 'fp16+fp8': 2}[self.precision]   # scheme of the dominant 3x3 layers
+        self.nterms = {'fp16x1': 1, 'fp16x3': 3, 'fp16+fp8': 2, 'fp16+fp4': 1.5}[self.precision]   # scheme of the dominant 3x3 layers
         self._packs = {}
         self._pack_versions = {}
         self._ws = {}
@@ -137,9 +167,9 @@ class CoordNetEngine:
             return self.packer(name, conv)
         ver = (conv.weight._version, conv.weight.data_ptr(), None if conv.bias is None else conv.bias._version, force_split)
         if self._pack_versions.get(name) != ver:
-            nterms = _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0])
-            if force_split and nterms == 2:
-                nterms = 3   # the operand comes from outside the plan and has no e4m3 planes
+            nterms = _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0], conv.out_channels)
+            if force_split and nterms in (2, 4):
+                nterms = 3   # the operand comes from outside the plan and has no e4m3 / e2m1 planes
             self._packs[name] = PackedConv(conv.weight, conv.bias, conv.stride[0], nterms)
             self._pack_versions[name] = ver
         return self._packs[name]
@@ -201,12 +231,20 @@ class CoordNetEngine:
         lo_rows = act.phases * geo.Mp
         use8 = pack.nterms == 2
         e0 = self._tick()
-        _lib.check(self._lib.cl_conv_igemm(
-            act.h16.data_ptr(), act.h16.size(0), lo_rows, pack.cin, pack.weights.data_ptr(), pack.cout, len(taps),
-            tap_arr, pack.nterms, geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale, raw.data_ptr(),
-            pack.bias.data_ptr(), 0 if stats is None else stats.data_ptr(),
-            act.f8.data_ptr() if use8 else 0, act.f8.size(0) if use8 else 0, lo_rows if use8 else 0,
-            pack.weights8.data_ptr() if use8 else 0, stream))
+        if pack.nterms == 4:
+            f4, sf = act.f4
+            _lib.check(self._lib.cl_conv_igemm_fp4(
+                act.h16.data_ptr(), act.h16.size(0), lo_rows, pack.cin, pack.weights.data_ptr(), pack.cout, len(taps),
+                tap_arr, geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale, raw.data_ptr(), pack.bias.data_ptr(),
+                0 if stats is None else stats.data_ptr(), f4.data_ptr(), f4.size(0), geo.Mp, sf.data_ptr(),
+                pack.weights4.data_ptr(), pack.w_sf.data_ptr(), stream))
+        else:
+            _lib.check(self._lib.cl_conv_igemm(
+                act.h16.data_ptr(), act.h16.size(0), lo_rows, pack.cin, pack.weights.data_ptr(), pack.cout, len(taps),
+                tap_arr, pack.nterms, geo.Mp, geo.Hp, geo.Wp, group_ch, pack.out_scale, raw.data_ptr(),
+                pack.bias.data_ptr(), 0 if stats is None else stats.data_ptr(),
+                act.f8.data_ptr() if use8 else 0, act.f8.size(0) if use8 else 0, lo_rows if use8 else 0,
+                pack.weights8.data_ptr() if use8 else 0, stream))
         # algorithmic FLOPs: 2 * (real output pixels) * Cout * Cin * taps (borders and split terms excluded)
         self._tock(e0, name, (pack.cin, pack.cout, pack.ksize, pack.stride),
                    2.0 * geo.B * geo.H * geo.W * pack.cout * pack.cin * len(taps))
@@ -220,7 +258,9 @@ class CoordNetEngine:
         group_ch = 0 if norm is None else channels // norm.num_groups
         add_kind = 1 if res is not None else (2 if raw2 is not None else 0)
         e0 = self._tick()
-        _lib.check(self._lib.cl_gn_apply(
+        want4 = bool(want8 & 2) if not isinstance(want8, bool) else False
+        want8 = bool(want8 & 1) if not isinstance(want8, bool) else want8
+        _lib.check(self._lib.cl_gn_apply_fp4(
             raw.data_ptr(), geo.B, geo.H, geo.W, channels, group_ch,
             0 if stats is None else stats.data_ptr(),
             0 if norm is None else norm.weight.data_ptr(), 0 if norm is None else norm.bias.data_ptr(),
@@ -229,7 +269,8 @@ class CoordNetEngine:
             0 if raw2 is None else raw2.data_ptr(), 0 if stats2 is None else stats2.data_ptr(),
             0 if norm2 is None else norm2.weight.data_ptr(), 0 if norm2 is None else norm2.bias.data_ptr(),
             1 if relu_outer else 0, out.h16.data_ptr(), out.phases, 2 if (want_lo and self.terms == 2) else 1,
-            out.f8.data_ptr() if want8 else 0, out.channels if out_c0 is not None else 0, out_c0 or 0, stream))
+            out.f8.data_ptr() if want8 else 0, out.channels if out_c0 is not None else 0, out_c0 or 0,
+            out.f4[0].data_ptr() if want4 else 0, out.f4[1].data_ptr() if want4 else 0, stream))
         self._tock(e0, 'gn_apply', ('gn_apply', channels, out.phases, add_kind), 0.0)
         self.launches += 1
         if self.tape is not None:
@@ -251,7 +292,7 @@ class CoordNetEngine:
         return buf
 
     def nterms_of(self, conv):
-        return _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0])
+        return _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0], conv.out_channels)
 
     # ------------------------------------------------------------------ plans
     def forward(self, spec, image):
@@ -314,7 +355,8 @@ class CoordNetEngine:
 
         def planes_for(consumers, also_lo=False):
             """Which operand planes the consumers of an activation need: (fp16 lo plane, e4m3 planes)."""
-            want8 = any(packs[c].nterms == 2 for c in consumers)
+            # bit 0: e4m3 planes, bit 1: block-scaled e2m1 planes (an int, so that `if want8` keeps its meaning)
+            want8 = (1 if any(packs[c].nterms == 2 for c in consumers) else 0) | (2 if any(packs[c].nterms == 4 for c in consumers) else 0)
             # training: the weight gradient reads the fp16 lo plane of every operand, whatever the forward scheme
             want_lo = also_lo or self.tape is not None or any(packs[c].nterms == 3 for c in consumers)
             return want_lo, want8
@@ -442,6 +484,7 @@ class CoordNetEngine:
                 nin = block['norm_in']
                 normed = self._act(ws, 'mlr_normed', 3, res.channels, 1)
                 want_lo, want8 = planes_for([block['convs'][0]])
+                assert not (want8 & 2), 'the MLR merge has no e2m1 planes (fp16 + fp4 is limited to plans without it)'
                 st_n = ws.get('pfgn_stats')
                 if st_n is None or st_n.shape != (batch, nin.num_groups, 2):
                     st_n = ws['pfgn_stats'] = torch.zeros(batch, nin.num_groups, 2, dtype=torch.float64, device=dev)

@@ -23,7 +23,7 @@ import os
 import torch
 
 from . import _lib
-from .cnn import CoordNetEngine, _nterms_for, _W8_LO_SCALE
+from .cnn import CoordNetEngine, _nterms_for, _W8_LO_SCALE, pack_fp4
 from .train import _i32, _pack
 
 _NTERMS = 3
@@ -32,9 +32,9 @@ _NTERMS = 3
 # fp16x3), 'fp16x3' (three fp16 MMAs per product) or 'fp16x1' (one fp16 pass with fp32 accumulation: the 10-bit mantissa
 # of the TF32 kernels stock PyTorch trains with by default)
 BACKWARD = os.environ.get('CROSSLOC_B200_TRAIN_BACKWARD', 'fp16+fp4')
-# arithmetic of the forward convolutions: the inference default ('fp16+fp8': e4m3 correction terms on the large layers,
-# 3e-5 relative on the coordinate map) or 'fp16x3'
-FORWARD = os.environ.get('CROSSLOC_B200_TRAIN_FORWARD', 'fp16+fp8')
+# arithmetic of the forward convolutions: the inference default ('fp16+fp4': block-scaled e2m1 correction terms on the
+# 256/512-channel layers, 1.7e-4 relative on the coordinate map), 'fp16+fp8' (e4m3 correction terms, 3e-5) or 'fp16x3'
+FORWARD = os.environ.get('CROSSLOC_B200_TRAIN_FORWARD', 'fp16+fp4')
 # arithmetic of the weight gradient GEMMs alone: one fp16 pass by default.  A weight gradient is one sum over every pixel of
 # the batch (5,400 x batch terms per entry at 60 x 90 cells): the operand rounding averages out and, unlike in the data gradient,
 # does not travel on through the layers below.  Measured on the BASELINE config-4 step (tools/dbg_wgrad_precision.py, batch
@@ -68,6 +68,9 @@ class _TrainPack:
         if nterms == 2:   # forward in the fp16 + fp8 scheme: e4m3 planes fp8(w_hi), fp8(w_lo * 2^12)
             self.weights8 = torch.stack([self.weights[0].to(torch.float32).to(torch.float8_e4m3fn),
                                          (self.weights[1].to(torch.float32) * _W8_LO_SCALE).to(torch.float8_e4m3fn)], 0).contiguous()
+        self.weights4 = self.w_sf = None
+        if nterms == 4:   # forward in the fp16 + fp4 scheme: block-scaled e2m1 planes of the scaled filter
+            self.weights4, self.w_sf = pack_fp4(w.to(torch.float32), 2.0 ** exp)
         self.bias = (conv.bias.detach().to(torch.float32) if conv.bias is not None
                      else torch.zeros(cout, dtype=torch.float32, device=w.device)).contiguous()
 
@@ -89,7 +92,7 @@ class TrainPlan:
         self.bwd_fp4 = backward == 'fp16+fp4'
         self.wgrad_terms = 3 if wgrad == 'fp16x3' else 1
         self._zero_bias = {}
-        self.engine = CoordNetEngine(precision=forward)
+        self.engine = CoordNetEngine(precision=forward, fp4=forward == 'fp16+fp4')
         self.engine.packer = self._packer
         self._exps = {}
         self._step = 0
@@ -102,7 +105,7 @@ class TrainPlan:
             import math
             exp = 0 if amax == 0.0 or not math.isfinite(amax) else int(math.floor(math.log2(128.0 / amax)))
             self._exps[name] = max(-24, min(24, exp))
-        nterms = _nterms_for(self.engine.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0])
+        nterms = _nterms_for(self.engine.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0], conv.out_channels)
         return _TrainPack(conv, self._exps[name], nterms)
 
     # ------------------------------------------------------------------ forward

@@ -118,10 +118,16 @@ def test_gn_backward_stage_matches_autograd(case):
 
 
 @pytest.mark.parametrize('fused', [True, False])
-def test_training_step_matches_reference_autograd(fused):
+def test_training_step_matches_reference_autograd(fused, monkeypatch):
     """One TransPoseNet training step (coord MLE loss): loss and every gradient vs the stock-torch definition, through the
-    fused plan (crossloc_b200.train_plan) and through the per-layer path (crossloc_b200.train)."""
+    fused plan (crossloc_b200.train_plan) and through the per-layer path (crossloc_b200.train).  The strict comparison runs
+    the plan in its most accurate arithmetic (e4m3 forward corrections, fp16x3 gradients); the default arithmetic (block-scaled
+    e2m1 corrections in the forward and in the data gradient) is compared at the end with the bounds of that scheme."""
     import networks.networks as nets
+    from crossloc_b200 import train_plan
+    monkeypatch.setattr(train_plan, 'FORWARD', 'fp16+fp8')
+    monkeypatch.setattr(train_plan, 'BACKWARD', 'fp16x3')
+    monkeypatch.setattr(train_plan, 'WGRAD', 'fp16x3')
     from loss.coord import scene_coords_regression_loss
     from tests.test_loss_cpu import pixel_grid
     torch.manual_seed(3)
@@ -177,6 +183,17 @@ def test_training_step_matches_reference_autograd(fused):
     # and it is what forward() itself runs when autograd is on
     out = net(x)
     assert out.requires_grad
+    if fused:
+        # default arithmetic of the plan: fp16 + fp4 forward and data gradients, one-pass weight gradients
+        monkeypatch.undo()
+        object.__setattr__(net, '_train_plan', None)
+        loss_ref, g_ref = grads(net.forward_reference, 'probe')
+        loss_nat, g_nat = grads(lambda t: net.forward_train(t, fused=True), 'probe')
+        assert net._train_plan.engine.precision == train_plan.FORWARD and net._train_plan.backward_mode == train_plan.BACKWARD
+        assert abs(float(loss_nat) - float(loss_ref)) < 1e-3 * abs(float(loss_ref))
+        name, err = worst_error(g_nat, g_ref)
+        assert err < 1e-1, (name, err)
+        assert max(float((g_nat[n] - g_ref[n]).norm() / g_ref[n].norm()) for n in tail if g_ref[n].dim() == 4) < 5e-3
 
 
 def test_fused_plan_refuses_stale_backward():
@@ -198,6 +215,7 @@ def test_fused_plan_refuses_stale_backward():
     (False, 'TransPoseNet', 64, 96, 0, 'fp16x3'),
     (True, 'TransPoseNet', 41, 59, 1, 'fp16+fp8'),    # odd sizes at every level of the strided ladder
     (False, 'Network', 48, 64, 0, 'fp16+fp8'),        # vanilla DSAC* network: no GroupNorm, 1-channel input
+    (False, 'TransPoseNet', 50, 70, 1, 'fp16+fp4'),   # block-scaled e2m1 corrections in the forward and the data gradient
 ])
 def test_fused_plan_gradients_on_more_shapes(case):
     """Fused training plan vs stock autograd on a smooth objective: loss value, and every parameter gradient measured
@@ -223,18 +241,21 @@ def test_fused_plan_gradients_on_more_shapes(case):
         return loss.detach(), {n: p.grad.detach().clone() for n, p in net.named_parameters()}
 
     loss_ref, g_ref = grads(net.forward_reference)
-    loss_nat, g_nat = grads(lambda t: train_plan.forward_train(net, t, backward='fp16x3', forward=fwd))
-    assert abs(float(loss_nat) - float(loss_ref)) < 2e-4 * max(1.0, abs(float(loss_ref)))
+    fp4 = fwd == 'fp16+fp4'
+    loss_nat, g_nat = grads(lambda t: train_plan.forward_train(net, t, backward='fp16+fp4' if fp4 else 'fp16x3', forward=fwd,
+                                                              wgrad='fp16x1' if fp4 else 'fp16x3'))
+    assert abs(float(loss_nat) - float(loss_ref)) < (1e-3 if fp4 else 2e-4) * max(1.0, abs(float(loss_ref)))
     scale = max(float(g.double().norm()) for g in g_ref.values())
     errs = {n: float((g_nat[n].double() - g_ref[n].double()).norm()) / max(float(g_ref[n].double().norm()), 1e-4 * scale)
             for n in g_ref}
     worst = max(errs, key=errs.get)
-    assert errs[worst] < 5e-2, (worst, errs[worst])
+    assert errs[worst] < (1e-1 if fp4 else 5e-2), (worst, errs[worst])
     # the typical parameter agrees much better than the worst one; with e4m3 forward terms the forward differs by 3e-5
-    # instead of 1e-5 from fp32, more pre-activations change sign and the toy-sized maps (63 cells) feel every flip
-    assert sorted(errs.values())[len(errs) // 2] < (2e-2 if (fwd == 'fp16+fp8' and not tiny) else 5e-3)
+    # instead of 1e-5 from fp32 (e2m1 terms: 1.7e-4), more pre-activations change sign and the toy-sized maps (63 cells)
+    # feel every flip
+    assert sorted(errs.values())[len(errs) // 2] < (5e-2 if fp4 else (2e-2 if (fwd == 'fp16+fp8' and not tiny) else 5e-3))
     # TF32-grade gradient GEMMs (one fp16 pass): same gradients to 10-bit operand precision
     _, g_fast = grads(lambda t: train_plan.forward_train(net, t, backward='fp16x1', forward=fwd))
     errs = {n: float((g_fast[n].double() - g_ref[n].double()).norm()) / max(float(g_ref[n].double().norm()), 1e-4 * scale)
             for n in g_ref}
-    assert max(errs.values()) < 1e-1 and sorted(errs.values())[len(errs) // 2] < 2e-2
+    assert max(errs.values()) < 1e-1 and sorted(errs.values())[len(errs) // 2] < (5e-2 if fp4 else 2e-2)

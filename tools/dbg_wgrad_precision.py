@@ -17,6 +17,7 @@ from loss.coord import scene_coords_regression_loss  # noqa: E402
 from tests.test_loss_cpu import pixel_grid  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+FWD = sys.argv[2] if len(sys.argv) > 2 else 'fp16+fp4'
 dev = torch.device('cuda', 0)
 torch.manual_seed(2021)
 net = nets.TransPoseNet(torch.tensor(synth.NATURESCAPE_MEAN, dtype=torch.float32), False, False, 2, 2, 3, 1).to(dev).train()
@@ -32,7 +33,7 @@ grid = pixel_grid().to(dev)
 
 def step(backward, wgrad):
     net.zero_grad()
-    pred = train_plan.forward_train(net, images, backward=backward, forward='fp16+fp8', wgrad=wgrad)
+    pred = train_plan.forward_train(net, images, backward=backward, forward=FWD, wgrad=wgrad)
     c, u = torch.split(pred, [3, 1], dim=1)
     loss, _ = scene_coords_regression_loss(0.1, 100.0, 1000.0, 50.0, 'MLE', grid, -1, cam, c, u, poses, gt)
     loss.backward()
