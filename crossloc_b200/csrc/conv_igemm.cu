@@ -50,6 +50,20 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kStageChunkBytes = 32 * 32 * 4;   // one epilogue staging chunk: 32 rows x 32 fp32
 constexpr uint32_t kEpilogueStagingBytes = 4 * 2 * kStageChunkBytes;
 
+// wait / busy cycles by site (debug builds only, CL_DEBUG_TRAP=1): read with cl_debug_counters, tools/dbg_conv_waits.py
+#ifdef CL_DEBUG_TRAP
+__device__ unsigned long long g_conv_dbg[16];   // wait cycles by site (debug builds only): see cl_debug_counters
+#define CL_DBG_T0() const long long _t0 = clock64()
+#define CL_DBG_ADD(i) do { if (lane == 0) atomicAdd(&g_conv_dbg[i], (unsigned long long)(clock64() - _t0)); } while (0)
+#define CL_DBG_MARK(name) const long long name = clock64()
+#define CL_DBG_SINCE(i, name) do { if (lane == 0) atomicAdd(&g_conv_dbg[i], (unsigned long long)(clock64() - name)); } while (0)
+#else
+#define CL_DBG_T0() do {} while (0)
+#define CL_DBG_ADD(i) do {} while (0)
+#define CL_DBG_MARK(name) do {} while (0)
+#define CL_DBG_SINCE(i, name) do {} while (0)
+#endif
+
 // Sums NV per-lane values across the warp with a recursive-halving butterfly (NV - 1 + log2(32 / NV)
 // shuffles per value set).  On return v[0] of lane l holds the total of value index
 // scatter_index<NV>(l); lanes sharing that index hold copies.
@@ -324,7 +338,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int kbi = 0; kbi < kblocks; kbi++) {
                 ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (ptx::elect_one()) {   // elect.sync: the compiler keeps the descriptors in uniform registers
                     const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                     const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
                     if (f8c) {
@@ -807,7 +821,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         const int a_row = p.tap_a_row[tap] + m0;
                         const int w_row = tap * p.w_tap_rows + n0 + (int)crank * w_rows;
                         for (int kb = 0; kb < p.kblocks_per_tap; kb += kstep) {
-                            ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                            { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u); if (leader && warp == 0) CL_DBG_ADD(2); }
                             const uint32_t bar = ptx::smem_u32(&full_bar[stage]);   // resolved to the leader's copy by the load
                             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                             const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
@@ -844,14 +858,21 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint32_t idesc = ptx::make_idesc_f16(2 * kBlockM, p.BN);
             int stage = 0, local = 0;
             uint32_t phase = 0;
+            CL_DBG_MARK(t_mma_loop);
             for (;; local++) {
                 int tile = 0;
                 if (lane == 0) tile = feed_next(feed, num_tiles);
                 tile = __shfl_sync(0xffffffffu, tile, 0);
-                if (tile < 0) break;
+                if (tile < 0) {
+                    CL_DBG_SINCE(6, t_mma_loop);
+#ifdef CL_DEBUG_TRAP
+                    if (lane == 0) atomicAdd(&g_conv_dbg[7], (unsigned long long)local);
+#endif
+                    break;
+                }
                 const int as = local % p.accum_stages;
                 const uint32_t aphase = (uint32_t)(local / p.accum_stages) & 1u;
-                ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aphase ^ 1u);
+                { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aphase ^ 1u); CL_DBG_ADD(0); }
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.BN);
                 const int nstages_tile = f8c ? kblocks / 2 : kblocks;
@@ -860,7 +881,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     for (int kbi = 0; kbi < nstages_tile; kbi++) {
                         ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
                         ptx::tc_fence_after();
-                        if (lane == 0) {
+                        if (ptx::elect_one()) {   // elect.sync: the compiler keeps the descriptors in uniform registers
                             const uint32_t a8lo = smem_base + (uint32_t)stage * p.stage_bytes, a8hi = a8lo + p.a_bytes;
                             const uint32_t w8hi = a8lo + 2u * p.a_bytes, w8lo = w8hi + w_half;
 #pragma unroll
@@ -882,9 +903,9 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     }
                 }
                 for (int kbi = 0; kbi < nstages_tile; kbi++) {
-                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                    { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase); CL_DBG_ADD(1); }
                     ptx::tc_fence_after();
-                    if (lane == 0) {
+                    if (ptx::elect_one()) {   // elect.sync: the compiler keeps the descriptors in uniform registers
                         const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                         const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
                         if (f8c) {
@@ -982,7 +1003,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     else __nanosleep(200);
                 }
             }
-            ptx::mbar_wait(tfull, aphase);
+            { CL_DBG_T0(); ptx::mbar_wait(tfull, aphase); if (leader && warp == 4) CL_DBG_ADD(4); }
+            CL_DBG_MARK(t_epi);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
             if (FUSED) {
@@ -1004,6 +1026,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 epilogue_tile(p, &tmO, taddr, m0, n0, q, lane, stage_base, chunk_no, false, valid, image);   // corrections already folded
                 release(as);
             }
+            if (leader && warp == 4) CL_DBG_SINCE(5, t_epi);
         }
         if (FUSED && pend_tile >= 0) {
             const int pm0 = ((pend_tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
@@ -1040,18 +1063,6 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 //   * Tensor memory: the scale columns do not fit next to two 256-column accumulators, so the second accumulator starts
 //     at column 224 and the scales live in columns 480..511.  The epilogue drains the 32 shared columns first and then
 //     lets the MMA warp start the next tile; the rest of the drain overlaps that tile's MMAs as before.
-#ifdef CL_DEBUG_TRAP
-__device__ unsigned long long g_conv_dbg[16];   // wait cycles by site (debug builds only): see cl_debug_counters
-#define CL_DBG_T0() const long long _t0 = clock64()
-#define CL_DBG_ADD(i) do { if (lane == 0) atomicAdd(&g_conv_dbg[i], (unsigned long long)(clock64() - _t0)); } while (0)
-#define CL_DBG_MARK(name) const long long name = clock64()
-#define CL_DBG_SINCE(i, name) do { if (lane == 0) atomicAdd(&g_conv_dbg[i], (unsigned long long)(clock64() - name)); } while (0)
-#else
-#define CL_DBG_T0() do {} while (0)
-#define CL_DBG_ADD(i) do {} while (0)
-#define CL_DBG_MARK(name) do {} while (0)
-#define CL_DBG_SINCE(i, name) do {} while (0)
-#endif
 constexpr uint32_t kSfStageBytes = 4096;   // shared memory reserved per pipeline stage for the scale ring below
 constexpr int kSfSlots = 8;                // the scales have their own ring (only pass 0 uses them): a slot = 512 B activation
 constexpr uint32_t kSfSlotBytes = 1536;    // scales + 2 x 512 B weight scales; kSfSlots * kSfSlotBytes <= 3 * kSfStageBytes
@@ -1298,7 +1309,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     // read there by its own tensor core; a cluster-scope acquire here costs ~350 cycles per stage)
                     { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&sf_full[slot]), sphase, 7); CL_DBG_ADD(2); }
                     ptx::tc_fence_after();
-                    if (lane == 0) {
+                    if (ptx::elect_one()) {   // elect.sync: the compiler keeps the descriptors in uniform registers
                         const uint32_t a4lo = smem_base + (uint32_t)stage * p.stage_bytes, a4hi = a4lo + p.a_bytes;
                         const uint32_t w4hi = a4lo + 2u * p.a_bytes, w4lo = w4hi + w_half;
                         const uint32_t sfs = sf_base + (uint32_t)slot * kSfSlotBytes;
@@ -1328,7 +1339,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 for (int i = 0; i < n16; i++) {
                     { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, 8); CL_DBG_ADD(3); }
                     ptx::tc_fence_after();
-                    if (lane == 0) {
+                    if (ptx::elect_one()) {   // elect.sync: the compiler keeps the descriptors in uniform registers
                         const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                         const uint32_t sw = sa + 2u * p.a_bytes;
 #pragma unroll

@@ -159,7 +159,7 @@ conv_wgrad_pf_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
             for (int kbi = 0; kbi < kblocks; kbi++) {
                 ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (ptx::elect_one()) {   // elect.sync keeps the MMA operands in uniform registers
                     const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                     const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
                     for (int term = 0; term < p.nterms; term++) {
@@ -333,7 +333,7 @@ conv_wgrad_pf_pair_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_
                 for (int kbi = 0; kbi < kblocks; kbi++) {
                     ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
                     ptx::tc_fence_after();
-                    if (lane == 0) {
+                    if (ptx::elect_one()) {   // elect.sync keeps the MMA operands in uniform registers
                         const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                         const uint32_t sw = sa + (uint32_t)nA * p.a_bytes;
                         for (int term = 0; term < p.nterms; term++) {

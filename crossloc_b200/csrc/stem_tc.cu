@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_tc_kernel(StemDesc d)
             ptx::mbar_wait(ptx::smem_u32(&d_empty[s]), par ^ 1u);
             ptx::mbar_wait(ptx::smem_u32(&a_full[s]), par);
             ptx::tc_fence_after();
-            if (lane == 0) {
+            if (ptx::elect_one()) {   // elect.sync keeps the MMA operands in uniform registers
                 const uint32_t a_hi = smem_base + (uint32_t)s * kABytes, a_lo = a_hi + kPlaneBytes;
                 const uint32_t tmem_d = tmem_base + (uint32_t)(s * kCo);
 #pragma unroll
