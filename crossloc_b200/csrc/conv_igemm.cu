@@ -118,11 +118,27 @@ __device__ __forceinline__ bool scatter_owner(int lane)
     return (lane & mask) == 0;
 }
 
+// Which of the warp's 32 accumulator rows are interior pixels and whether they all belong to one image: the same for every
+// chunk of a tile, so the three warp collectives are paid once per tile.
+struct StatsRows {
+    unsigned vmask;
+    int ref_image;
+    bool uniform;
+};
+__device__ __forceinline__ StatsRows stats_rows(bool valid, int image)
+{
+    StatsRows r;
+    r.vmask = __ballot_sync(0xffffffffu, valid);
+    r.ref_image = r.vmask ? __shfl_sync(0xffffffffu, image, __ffs(r.vmask) - 1) : 0;
+    r.uniform = __all_sync(0xffffffffu, !valid || image == r.ref_image);
+    return r;
+}
+
 // GroupNorm partial sums of one 32-column chunk held by the warp (one row per lane).
 // GC = channels per group; the chunk covers 32 / GC whole groups.
 template <int GC, int NC = 32>
 __device__ __forceinline__ void stats_chunk(const float (&f)[NC], bool valid, int image, int lane, double* stats,
-                                            int groups, int first_group)
+                                            int groups, int first_group, const StatsRows* rows = nullptr)
 {
     constexpr int NG = NC / GC, NV = 2 * NG;
     float v[NV];
@@ -138,11 +154,10 @@ __device__ __forceinline__ void stats_chunk(const float (&f)[NC], bool valid, in
         v[2 * g] = s;
         v[2 * g + 1] = ss;
     }
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    if (vmask == 0) return;
-    const int ref_image = __shfl_sync(0xffffffffu, image, __ffs(vmask) - 1);
-    const bool uniform = __all_sync(0xffffffffu, !valid || image == ref_image);
-    if (uniform) {
+    const StatsRows rr = rows ? *rows : stats_rows(valid, image);
+    if (rr.vmask == 0) return;
+    const int ref_image = rr.ref_image;
+    if (rr.uniform) {
         warp_reduce_scatter<NV>(v, lane);
         if (scatter_owner<NV>(lane)) {
             const int idx = scatter_index<NV>(lane);
@@ -1393,6 +1408,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as ? kAcc1Col : 0u);
             const int nchunks = p.BN / 16;
+            const StatsRows srows = stats_rows(valid, image);
             for (int idx = grp; idx < nchunks; idx += 2) {
                 // drain order: the two chunks in tensor-memory columns 224..255 (the only ones the other accumulator
                 // shares) go first, one per warp group
@@ -1444,10 +1460,10 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 if (p.group_ch) {
                     const int first_group = (n0 + c0) / p.group_ch;
                     switch (p.group_ch) {
-                        case 2: stats_chunk<2, 16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        case 4: stats_chunk<4, 16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        case 8: stats_chunk<8, 16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
-                        case 16: stats_chunk<16, 16>(f, valid, image, lane, p.stats, p.groups, first_group); break;
+                        case 2: stats_chunk<2, 16>(f, valid, image, lane, p.stats, p.groups, first_group, &srows); break;
+                        case 4: stats_chunk<4, 16>(f, valid, image, lane, p.stats, p.groups, first_group, &srows); break;
+                        case 8: stats_chunk<8, 16>(f, valid, image, lane, p.stats, p.groups, first_group, &srows); break;
+                        case 16: stats_chunk<16, 16>(f, valid, image, lane, p.stats, p.groups, first_group, &srows); break;
                         default: break;
                     }
                 }
