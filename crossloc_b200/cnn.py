@@ -329,8 +329,11 @@ class CoordNetEngine:
         layers = spec['layers']          # ordered list of (name, conv, norm or None)
         n_stat = len(layers) + 1
         stats_all = ws.get('stats')
-        if stats_all is None or stats_all.size(0) < n_stat:
-            stats_all = torch.zeros(n_stat, batch, 32, 2, dtype=torch.float64, device=dev)
+        # one [batch][groups][2] slice per layer, sized for the widest grouping in the plan (the convolution epilogue
+        # indexes its slice by image * groups + group)
+        max_groups = max([32] + [norm.num_groups for _, _, norm in layers if norm is not None])
+        if stats_all is None or stats_all.size(0) < n_stat or stats_all.size(2) < max_groups:
+            stats_all = torch.zeros(n_stat, batch, max_groups, 2, dtype=torch.float64, device=dev)
             ws['stats'] = stats_all
         else:
             stats_all.zero_()

@@ -117,3 +117,27 @@ def test_backward_batch_equals_single_images():
                                      1., 1., 100., 50., 100., 8, seed=5, image_base=30 + i)
         assert float(li[0]) == float(loss[i])
         assert torch.equal(gi[0], g[i])
+
+
+def test_backward_single_hypothesis_and_degenerate_map():
+    """Edge cases of the path: one hypothesis (probability 1: the score path vanishes, only the refinement path is left) against
+    the live oracle; a constant map (every P3P fails until max_tries: zero poses, dsacstar_util.h:114-116) must stay finite."""
+    from oracle import dsac_backward_py as tier1
+    mod = backward_module()
+    s = synth.make_scene(40, height=240, width=368)
+    gt = mod.gt_pose_for(s, 40)
+    p = dict(mod.PARAMS)
+    r = tier1.backward_rgb(s['coords'], gt, 1, p['thr'], s['focal'], 184., 120., 1., 1., 100., p['alpha'], p['max_reproj'], 8,
+                           seed=p['seed'], image=40)
+    ref = dict(r)
+    ref['tries'], ref['cells'] = np.asarray(r['tries']), np.asarray(r['cells'])
+    loss, grad, dbg = _run(s, gt, 1, (184., 120.), p, 40)
+    assert dbg['probs'][0] == 1.0
+    _compare(ref, loss, grad, dbg)
+
+    flat = torch.full((1, 3, 30, 46), 2.0, device='cuda')
+    g = torch.zeros_like(flat)
+    out = dsac.backward_rgb_batch(flat, g, torch.eye(4).reshape(1, 4, 4), 8, 10., 480., 184., 120., 1., 1., 100., 100., 100., 8,
+                                  seed=1, image_base=0, max_tries=20)
+    torch.cuda.synchronize()
+    assert np.isfinite(float(out[0])) and torch.isfinite(g).all()
