@@ -236,6 +236,8 @@ struct Net {
     uint64_t tick = 0;
     cudaStream_t capture_stream = nullptr;
     cudaEvent_t fork_event = nullptr;   // recorded by every forward when it enters the residual blocks (cl_net_wait_fork)
+    cudaEvent_t done_event = nullptr;   // end of the last forward of THIS handle: its plans share workspaces, so forwards of
+    bool done_recorded = false;         // one handle issued on different streams are ordered by it
     std::mutex mu;
     std::string err;
 
@@ -244,6 +246,7 @@ struct Net {
         plans.clear();
         if (capture_stream) cudaStreamDestroy(capture_stream);
         if (fork_event) cudaEventDestroy(fork_event);
+        if (done_event) cudaEventDestroy(done_event);
     }
 };
 
@@ -935,6 +938,9 @@ int forward_impl(Net& n, const void* image, bool frames_u8, const float* mean, c
     std::string err;
     Plan* P = plan_for(n, B, Cin, H, W, err);
     if (!P) return fail(-2, "cl_net_forward: %s", err.c_str());
+    // the plans of a handle share input / activation / output buffers: order this forward behind the previous one of the
+    // handle, whatever stream that was issued on (forwards of different handles may overlap)
+    if (n.done_recorded) CL_CUDA(cudaStreamWaitEvent(stream, n.done_event, 0));
     // ---- stage the frames
     if (frames_u8) {
         const size_t bytes = (size_t)B * H * W * Cin;
@@ -999,6 +1005,8 @@ int forward_impl(Net& n, const void* image, bool frames_u8, const float* mean, c
         CL_CUDA(cudaMemcpyAsync(out, P->out.p, out_bytes, cudaMemcpyDefault, stream));
         if (!is_device_ptr(out)) CL_CUDA(cudaStreamSynchronize(stream));
     }
+    CL_CUDA(cudaEventRecord(n.done_event, stream));
+    n.done_recorded = true;
     return 0;
 }
 
@@ -1089,6 +1097,7 @@ extern "C" int cl_net_create(const cl_net_desc* desc, cl_net** out)
     }
     if (const char* e = load_params(*n)) return fail(-2, "cl_net_create: %s", e);
     CL_CUDA(cudaEventCreateWithFlags(&n->fork_event, cudaEventDisableTiming));
+    CL_CUDA(cudaEventCreateWithFlags(&n->done_event, cudaEventDisableTiming));
     *out = reinterpret_cast<cl_net*>(n.release());
     return 0;
 }

@@ -252,3 +252,26 @@ def test_fused_epilogue_vanilla_network_and_many_small_images():
     with torch.no_grad():
         ref = net2.forward_reference(y)
     assert rel_l2(fused, plain) < 5e-6 and rel_l2(fused[:, :3], ref[:, :3]) < 3.3e-4
+
+
+def test_forwards_of_one_handle_on_two_streams_are_ordered():
+    """The plans of a handle share their input / activation / output buffers: forwards issued on different streams are ordered
+    by the handle's own event (forwards of different handles may overlap), so alternating streams gives the single-stream maps."""
+    torch.manual_seed(8)
+    net = nets.TransPoseNet(torch.zeros(3), False, False, 1, 1, 3, 1).eval().to(DEV)
+    xs = [torch.rand(2, 3, 96, 144, device=DEV) for _ in range(4)]
+    with torch.no_grad():
+        want = [net(x).clone() for x in xs]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        got = []
+        for rounds in range(3):
+            got = []
+            for i, x in enumerate(xs):
+                s = streams[i % 2]
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    got.append(net(x).clone())
+        torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert rel_l2(a, b) < 2e-6
