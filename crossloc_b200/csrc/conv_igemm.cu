@@ -1090,7 +1090,8 @@ constexpr uint32_t kFp4StagingBytes = 8 * kFp4ChunkBytes;      // one staging ch
 __global__ void __launch_bounds__(kFp4Threads, 1)
 conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA4,
-                           const __grid_constant__ CUtensorMap tmW4, const ConvIgemmParams p)
+                           const __grid_constant__ CUtensorMap tmW4, const __grid_constant__ CUtensorMap tmA136,
+                           const ConvIgemmParams p)
 {
     constexpr int BK = 64;
     constexpr int kSwizzle = 128;
@@ -1117,7 +1118,11 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const uint32_t w_half = p.w_bytes / 2;
     const bool dynamic = p.tile_counter != nullptr;
     const int n4 = p.num_taps * p.kgroups;                    // stages of pass 0 (256 channels of the e2m1 planes each)
-    const int n16 = p.num_taps * p.kblocks_per_tap / 2;       // stages of pass 1 (128 channels of the fp16 planes each)
+    // stages of pass 1: 128 channels of the fp16 planes of one tap each, or (kw_share) 64 channels of the three kw taps of a
+    // filter row: ONE 136-row activation tile read at row shifts 0, 1, 2 plus the three weight tiles -- a third of the
+    // activation bytes the L2 has to deliver for this pass
+    constexpr uint32_t kA136Bytes = 136 * 128;
+    const int n16 = p.kw_share ? 3 * p.kblocks_per_tap : p.num_taps * p.kblocks_per_tap / 2;
     static_assert(kSfSlots * kSfSlotBytes <= 3 * kSfStageBytes, "scale ring exceeds the shared memory reserved for it");
 
     if (warp == 0 && lane == 0) {
@@ -1126,6 +1131,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         ptx::prefetch_tensormap(&tmO);
         ptx::prefetch_tensormap(&tmA4);
         ptx::prefetch_tensormap(&tmW4);
+        if (p.kw_share) ptx::prefetch_tensormap(&tmA136);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.num_stages; s++) {
@@ -1197,6 +1203,25 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
                 const int n0 = (tile % p.tiles_n) * p.BN;
                 for (int pass = 0; pass < 2; pass++) {
+                    if (pass == 1 && p.kw_share) {
+                        const uint32_t tx_kw = 2u * (kA136Bytes + 3u * w_half);
+                        for (int kh = 0; kh < 3; kh++) {
+                            const int a_row = p.tap_a_row[3 * kh] + m0;   // kw = 0; kw = 1, 2 are the next rows
+                            for (int kb = 0; kb < p.kblocks_per_tap; kb++) {
+                                ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u, 2);
+                                const uint32_t bar = ptx::smem_u32(&full_bar[stage]);
+                                const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                                if (leader) ptx::mbar_expect_tx(bar, tx_kw);
+                                ptx::tma_load_2d_pair(sa, &tmA136, bar, kb * BK, a_row);
+#pragma unroll
+                                for (int kw = 0; kw < 3; kw++)
+                                    ptx::tma_load_2d_pair(sa + kA136Bytes + (uint32_t)kw * w_half, &tmW, bar, kb * BK,
+                                                          (3 * kh + kw) * p.w_tap_rows + n0 + (int)crank * w_rows);
+                                if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                            }
+                        }
+                        continue;
+                    }
                     for (int tap = 0; tap < p.num_taps; tap++) {
                         const int a_row = p.tap_a_row[tap] + m0;
                         const int w_row = tap * p.w_tap_rows + n0 + (int)crank * w_rows;
@@ -1356,6 +1381,19 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     ptx::tc_fence_after();
                     if (ptx::elect_one()) {   // elect.sync: the compiler keeps the descriptors in uniform registers
                         const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        if (p.kw_share) {
+                            const uint32_t sw = sa + kA136Bytes;
+#pragma unroll
+                            for (int kw = 0; kw < 3; kw++) {
+#pragma unroll
+                                for (int k = 0; k < BK / 16; k++) {
+                                    // row shift kw of the shared tile: plain start-address offset (ptx_sm100.cuh, note on swizzles)
+                                    const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(sa + kw * 128 + k * 32);
+                                    const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(sw + kw * w_half + k * 32);
+                                    ptx::mma_f16_ss_pair(tmem_d, da, db, idesc, 1u);
+                                }
+                            }
+                        } else {
                         const uint32_t sw = sa + 2u * p.a_bytes;
 #pragma unroll
                         for (int half = 0; half < 2; half++) {
@@ -1365,6 +1403,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                                 const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(sw + half * w_half + k * 32);
                                 ptx::mma_f16_ss_pair(tmem_d, da, db, idesc, 1u);
                             }
+                        }
                         }
                         ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 0x3);
                         if (i == n16 - 1) ptx::mma_commit_pair(ptx::smem_u32(&tfull_bar[as]), 0x3);
@@ -1581,7 +1620,19 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
     if (d.nterms == 4 && !pair) return "conv_igemm: the fp16 + fp4 mode exists in the CTA-pair kernel only";
     p.accum_stages = (d.nterms == 2 && !pair ? 4 : 2) * BN <= (int)kTmemCols ? 2 : 1;
     plan->smem = (size_t)p.num_stages * p.stage_bytes + kEpilogueStagingBytes + 1024;
+    p.kw_share = 0;
     if (d.nterms == 4) {
+        // filter rows whose three taps are consecutive activation rows (3x3, stride 1): pass 1 shares one activation tile
+        // between them (stage = 136-row activation tile + three weight half-tiles = 65 KB instead of 64 KB)
+        // (CROSSLOC_B200_KW_SHARE=0 restores one tile per tap; same-box A/B: 3x3 512->512 0.881 -> 0.862 ms, step 19.26 -> 18.95 ms)
+        static const int kw_env = [] { const char* e = getenv("CROSSLOC_B200_KW_SHARE"); return e ? atoi(e) : 1; }();
+        bool rows3 = kw_env != 0 && d.num_taps == 9 && BK == 64 && BN == 256;
+        for (int kh = 0; kh < 3 && rows3; kh++)
+            rows3 = d.tap_a_row[3 * kh + 1] == d.tap_a_row[3 * kh] + 1 && d.tap_a_row[3 * kh + 2] == d.tap_a_row[3 * kh] + 2;
+        if (rows3) {
+            p.kw_share = 1;
+            p.stage_bytes = 136u * 128u + 3u * (p.w_bytes / 2);
+        }
         const int budget4 = 227 * 1024 - 2048 - (int)kFp4StagingBytes;
         p.num_stages = budget4 / (int)(p.stage_bytes + kSfStageBytes);
         if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
@@ -1644,6 +1695,9 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
             return "conv_igemm: cuTensorMapEncodeTiled failed for the e2m1 activation matrix";
         if (!make_tensor_map(&plan->tmW8, d.weights4, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin / 2, BN / 2, 128, 1))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the e2m1 weight matrix";
+        plan->out.hi = plan->tmA;
+        if (p.kw_share && !make_tensor_map(&plan->out.hi, d.act, (uint64_t)d.a_total_rows, (uint64_t)d.Cin, 136, BK, 2))
+            return "conv_igemm: cuTensorMapEncodeTiled failed for the 136-row activation box";
     }
     if (d.nterms == 2) {
         // the pair kernel streams the e4m3 planes in 128-byte rows (2 * BK channels per box)
@@ -1692,7 +1746,7 @@ const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream)
         if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, KERNEL, __VA_ARGS__);                            \
     } while (0)
     switch (plan.variant) {
-        case 8: CL_LAUNCH(conv_igemm_pair_fp4_kernel, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.p); break;
+        case 8: CL_LAUNCH(conv_igemm_pair_fp4_kernel, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out.hi, plan.p); break;
         case 7: CL_LAUNCH((conv_igemm_pair_kernel<64, true>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
         case 6: CL_LAUNCH((conv_igemm_pair_kernel<32, true>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
         case 3: CL_LAUNCH((conv_igemm_pair_kernel<64, false>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;

@@ -372,6 +372,12 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr)
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | (sbo << 32) | ((uint64_t)1 << 46) | (layout << 61);
 }
 
+// Measured (tools/dbg_kw_share.py): the XOR pattern of a swizzled K-major tile is a function of the shared-memory ADDRESS
+// bits, for the TMA unit that writes it and for the tensor core that reads it alike.  A descriptor may therefore start at any
+// 128-byte row of a loaded tile with the matrix-base-offset field (bits 49-51) left at 0 -- setting it to (address >> 7) & 7,
+// as the field's description suggests for unaligned starts, reads the wrong rows.  The fp4 convolution uses this to read ONE
+// activation tile at three row shifts (the kw taps of a 3x3 filter row).
+
 // Instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M x N tile.
 __device__ __host__ __forceinline__ uint32_t make_idesc_f16(int M, int N)
 {
