@@ -84,7 +84,8 @@ struct ConvIgemmParams {
     int* tile_counter;
     // fp16 + fp4 mode
     int a4_lo_rows, kgroups;
-    int kw_share;           // 3x3 stride 1: pass 1 loads one 136-row activation tile per (kh, k-block) and reads it at three row shifts
+    int kw_share;           // 3x3 stride 1 (+1 / -1 = rows ascend / descend with kw, 0 = off): pass 1 loads one 136-row activation
+                            // tile per (kh, k-block) and reads it at three row shifts
     const uint32_t* act_sf;
     const uint32_t* w_sf;
     // fused GroupNorm epilogue

@@ -1206,7 +1206,8 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     if (pass == 1 && p.kw_share) {
                         const uint32_t tx_kw = 2u * (kA136Bytes + 3u * w_half);
                         for (int kh = 0; kh < 3; kh++) {
-                            const int a_row = p.tap_a_row[3 * kh] + m0;   // kw = 0; kw = 1, 2 are the next rows
+                            // first of the three consecutive rows (kw = 0 for a forward filter, kw = 2 for a transposed one)
+                            const int a_row = min(p.tap_a_row[3 * kh], p.tap_a_row[3 * kh + 2]) + m0;
                             for (int kb = 0; kb < p.kblocks_per_tap; kb++) {
                                 ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u, 2);
                                 const uint32_t bar = ptx::smem_u32(&full_bar[stage]);
@@ -1383,12 +1384,14 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                         const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                         if (p.kw_share) {
                             const uint32_t sw = sa + kA136Bytes;
+                            const int kw_dir = p.kw_share;   // +1: rows ascend with kw, -1: they descend (transposed filter)
 #pragma unroll
                             for (int kw = 0; kw < 3; kw++) {
+                                const uint32_t shift = (uint32_t)(kw_dir > 0 ? kw : 2 - kw) * 128u;
 #pragma unroll
                                 for (int k = 0; k < BK / 16; k++) {
-                                    // row shift kw of the shared tile: plain start-address offset (ptx_sm100.cuh, note on swizzles)
-                                    const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(sa + kw * 128 + k * 32);
+                                    // row shift of the shared tile: plain start-address offset (ptx_sm100.cuh, note on swizzles)
+                                    const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(sa + shift + k * 32);
                                     const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(sw + kw * w_half + k * 32);
                                     ptx::mma_f16_ss_pair(tmem_d, da, db, idesc, 1u);
                                 }
@@ -1626,11 +1629,12 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
         // between them (stage = 136-row activation tile + three weight half-tiles = 65 KB instead of 64 KB)
         // (CROSSLOC_B200_KW_SHARE=0 restores one tile per tap; same-box A/B: 3x3 512->512 0.881 -> 0.862 ms, step 19.26 -> 18.95 ms)
         static const int kw_env = [] { const char* e = getenv("CROSSLOC_B200_KW_SHARE"); return e ? atoi(e) : 1; }();
-        bool rows3 = kw_env != 0 && d.num_taps == 9 && BK == 64 && BN == 256;
+        int dir = d.num_taps == 9 ? d.tap_a_row[1] - d.tap_a_row[0] : 0;   // +1 forward filter, -1 transposed (data gradient)
+        bool rows3 = kw_env != 0 && (dir == 1 || dir == -1) && BK == 64 && BN == 256;
         for (int kh = 0; kh < 3 && rows3; kh++)
-            rows3 = d.tap_a_row[3 * kh + 1] == d.tap_a_row[3 * kh] + 1 && d.tap_a_row[3 * kh + 2] == d.tap_a_row[3 * kh] + 2;
+            rows3 = d.tap_a_row[3 * kh + 1] == d.tap_a_row[3 * kh] + dir && d.tap_a_row[3 * kh + 2] == d.tap_a_row[3 * kh] + 2 * dir;
         if (rows3) {
-            p.kw_share = 1;
+            p.kw_share = dir;
             p.stage_bytes = 136u * 128u + 3u * (p.w_bytes / 2);
         }
         const int budget4 = 227 * 1024 - 2048 - (int)kFp4StagingBytes;
