@@ -86,6 +86,7 @@ struct ConvIgemmParams {
     int a4_lo_rows, kgroups;
     int kw_share;           // 3x3 stride 1 (+1 / -1 = rows ascend / descend with kw, 0 = off): pass 1 loads one 136-row activation
                             // tile per (kh, k-block) and reads it at three row shifts
+    int kw_share0;          // the same for pass 0 (e2m1 planes): a stage holds one plane's 136-row tile and three weight half-tiles
     const uint32_t* act_sf;
     const uint32_t* w_sf;
     // fused GroupNorm epilogue

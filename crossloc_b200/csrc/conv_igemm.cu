@@ -1091,7 +1091,7 @@ __global__ void __launch_bounds__(kFp4Threads, 1)
 conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA4,
                            const __grid_constant__ CUtensorMap tmW4, const __grid_constant__ CUtensorMap tmA136,
-                           const ConvIgemmParams p)
+                           const __grid_constant__ CUtensorMap tmA4x136, const ConvIgemmParams p)
 {
     constexpr int BK = 64;
     constexpr int kSwizzle = 128;
@@ -1117,7 +1117,9 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const int num_tiles = p.super_m * p.tiles_n;
     const uint32_t w_half = p.w_bytes / 2;
     const bool dynamic = p.tile_counter != nullptr;
-    const int n4 = p.num_taps * p.kgroups;                    // stages of pass 0 (256 channels of the e2m1 planes each)
+    // stages of pass 0: 256 channels of the four e2m1 planes of one tap each, or (kw_share0) of ONE activation plane shared by
+    // the three kw taps of a filter row plus the matching weight plane of the three taps (two stages per filter row and group)
+    const int n4 = p.kw_share0 ? 6 * p.kgroups : p.num_taps * p.kgroups;
     // stages of pass 1: 128 channels of the fp16 planes of one tap each, or (kw_share) 64 channels of the three kw taps of a
     // filter row: ONE 136-row activation tile read at row shifts 0, 1, 2 plus the three weight tiles -- a third of the
     // activation bytes the L2 has to deliver for this pass
@@ -1132,6 +1134,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         ptx::prefetch_tensormap(&tmA4);
         ptx::prefetch_tensormap(&tmW4);
         if (p.kw_share) ptx::prefetch_tensormap(&tmA136);
+        if (p.kw_share0) ptx::prefetch_tensormap(&tmA4x136);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.num_stages; s++) {
@@ -1203,6 +1206,28 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 const int m0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
                 const int n0 = (tile % p.tiles_n) * p.BN;
                 for (int pass = 0; pass < 2; pass++) {
+                    if (pass == 0 && p.kw_share0) {
+                        const uint32_t tx_kw = 2u * (kA136Bytes + 3u * w_half);
+                        for (int kh = 0; kh < 3; kh++) {
+                            const int a_row = min(p.tap_a_row[3 * kh], p.tap_a_row[3 * kh + 2]) + m0;
+                            for (int kg = 0; kg < p.kgroups; kg++) {
+                                for (int half = 0; half < 2; half++) {   // a_lo4 with w_hi4, then a_hi4 with w_lo4
+                                    ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u, 2);
+                                    const uint32_t bar = ptx::smem_u32(&full_bar[stage]);
+                                    const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                                    if (leader) ptx::mbar_expect_tx(bar, tx_kw);
+                                    ptx::tma_load_2d_pair(sa, &tmA4x136, bar, kg * 128, (half == 0 ? p.a4_lo_rows : 0) + a_row);
+#pragma unroll
+                                    for (int kw = 0; kw < 3; kw++)
+                                        ptx::tma_load_2d_pair(sa + kA136Bytes + (uint32_t)kw * w_half, &tmW4, bar, kg * 128,
+                                                              (half == 0 ? 0 : p.w_lo_rows) + (3 * kh + kw) * p.w_tap_rows + n0 +
+                                                                  (int)crank * w_rows);
+                                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     if (pass == 1 && p.kw_share) {
                         const uint32_t tx_kw = 2u * (kA136Bytes + 3u * w_half);
                         for (int kh = 0; kh < 3; kh++) {
@@ -1265,6 +1290,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         const int sf_rows = p.a4_lo_rows;
         const int nblocks = p.Cout / 128;
         int ltap = p.num_taps, lkg = 0, lm0 = 0, ln0 = 0;
+        int lkh = 0, lkw = 0;   // kw_share0: slots in the order (kh, group, kw) the shared-tile stages consume them
         bool ldone = false;
         auto load_item = [&](uint4& wa, uint4& b0, uint4& b1) -> bool {
             if (ldone) return false;
@@ -1277,6 +1303,8 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 ln0 = (tile % p.tiles_n) * p.BN;
                 ltap = 0;
                 lkg = 0;
+                lkh = 0;
+                lkw = 0;
             }
             // lane l collects the words of rows l, l + 32, l + 64, l + 96 of the tile: one 16-byte row of the
             // 32 x 128-bit block tcgen05.cp broadcasts to the four lane quarters
@@ -1291,7 +1319,13 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             const uint4* wb = reinterpret_cast<const uint4*>(p.w_sf + ((size_t)(ltap * p.kgroups + lkg) * nblocks + ln0 / 128) * 128);
             b0 = __ldg(wb + lane);
             b1 = __ldg(wb + 32 + lane);
-            if (++lkg == p.kgroups) { lkg = 0; ++ltap; }
+            if (p.kw_share0) {
+                if (++lkw == 3) {
+                    lkw = 0;
+                    if (++lkg == p.kgroups) { lkg = 0; ++lkh; }
+                }
+                ltap = lkh == 3 ? p.num_taps : 3 * lkh + lkw;
+            } else if (++lkg == p.kgroups) { lkg = 0; ++ltap; }
             return true;
         };
 #pragma unroll
@@ -1344,7 +1378,53 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     ptx::tc_fence_after();
                 }
                 const uint32_t tmem_d = tmem_base + (as ? kAcc1Col : 0u);
-                for (int i = 0; i < n4; i++) {
+                if (p.kw_share0) {
+                    // shared-tile stages: (filter row, channel group) x (a_lo4 * w_hi4 | a_hi4 * w_lo4); the three scale slots of
+                    // the row's taps are copied into tensor memory for both products and released after the second one
+                    for (int j = 0; j < 3 * p.kgroups; j++) {
+                        const int slot0 = slot;
+                        const uint32_t sph0 = sphase;
+                        for (int half = 0; half < 2; half++) {
+                            { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, 6); CL_DBG_ADD(1); }
+                            if (half == 0) {
+                                CL_DBG_T0();
+                                for (int kw = 0; kw < 3; kw++) {
+                                    const int sl = slot0 + kw;
+                                    ptx::mbar_wait(ptx::smem_u32(&sf_full[sl % kSfSlots]), sl >= kSfSlots ? sph0 ^ 1u : sph0, 7);
+                                }
+                                CL_DBG_ADD(2);
+                            }
+                            ptx::tc_fence_after();
+                            if (ptx::elect_one()) {
+                                const uint32_t a4 = smem_base + (uint32_t)stage * p.stage_bytes, w4 = a4 + kA136Bytes;
+#pragma unroll
+                                for (int kw = 0; kw < 3; kw++) {
+                                    const uint32_t sfs = sf_base + (uint32_t)((slot0 + kw) % kSfSlots) * kSfSlotBytes;
+                                    const uint32_t sfa = tmem_base + kSfCol + (uint32_t)((half * 3 + kw) & 1) * 16u, sfb = sfa + 4u;
+                                    ptx::tmem_cp_sf_pair(sfa, ptx::make_sf_desc(sfs));
+                                    ptx::tmem_cp_sf_pair(sfb, ptx::make_sf_desc(sfs + 512u));
+                                    ptx::tmem_cp_sf_pair(sfb + 4u, ptx::make_sf_desc(sfs + 1024u));
+                                    const uint32_t shift = (uint32_t)(p.kw_share > 0 ? kw : 2 - kw) * 128u;
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) {
+                                        const uint64_t da = ptx::make_kmajor_desc<kSwizzle>(a4 + shift + k * 32);
+                                        const uint64_t db = ptx::make_kmajor_desc<kSwizzle>(w4 + kw * w_half + k * 32);
+                                        ptx::mma_mxf4_ss_pair(tmem_d, da, db, half ? idesc4b : idesc4a, (j | half | kw | k) != 0 ? 1u : 0u, sfa, sfb);
+                                    }
+                                }
+                                ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 0x3);
+                                if (half == 1)
+                                    for (int kw = 0; kw < 3; kw++)
+                                        ptx::mma_commit_pair(ptx::smem_u32(&sf_empty[(slot0 + kw) % kSfSlots]), 0x3);
+                            }
+                            __syncwarp();
+                            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                        }
+                        slot = slot0 + 3;
+                        if (slot >= kSfSlots) { slot -= kSfSlots; sphase ^= 1u; }
+                    }
+                }
+                for (int i = 0; i < (p.kw_share0 ? 0 : n4); i++) {
                     { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, 6); CL_DBG_ADD(1); }
                     // (CTA-scope wait, as for the operand barrier: the peer's scales stay in the peer's shared memory and are
                     // read there by its own tensor core; a cluster-scope acquire here costs ~350 cycles per stage)
@@ -1627,13 +1707,16 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
     if (d.nterms == 4) {
         // filter rows whose three taps are consecutive activation rows (3x3, stride 1): pass 1 shares one activation tile
         // between them (stage = 136-row activation tile + three weight half-tiles = 65 KB instead of 64 KB)
-        // (CROSSLOC_B200_KW_SHARE=0 restores one tile per tap; same-box A/B: 3x3 512->512 0.881 -> 0.862 ms, step 19.26 -> 18.95 ms)
+        // (CROSSLOC_B200_KW_SHARE=0 restores one tile per tap; same-box A/B: 3x3 512->512 0.881 -> 0.862 ms, step 19.26 -> 18.95 ms.
+        //  =2 also shares the e2m1 planes of pass 0 -- identical results, but no measurable gain: 0.905 vs 0.902 ms, opt-in only)
         static const int kw_env = [] { const char* e = getenv("CROSSLOC_B200_KW_SHARE"); return e ? atoi(e) : 1; }();
         int dir = d.num_taps == 9 ? d.tap_a_row[1] - d.tap_a_row[0] : 0;   // +1 forward filter, -1 transposed (data gradient)
         bool rows3 = kw_env != 0 && (dir == 1 || dir == -1) && BK == 64 && BN == 256;
         for (int kh = 0; kh < 3 && rows3; kh++)
             rows3 = d.tap_a_row[3 * kh + 1] == d.tap_a_row[3 * kh] + dir && d.tap_a_row[3 * kh + 2] == d.tap_a_row[3 * kh] + 2 * dir;
+        p.kw_share0 = 0;
         if (rows3) {
+            p.kw_share0 = kw_env == 2 ? 1 : 0;
             p.kw_share = dir;
             p.stage_bytes = 136u * 128u + 3u * (p.w_bytes / 2);
         }
@@ -1700,8 +1783,11 @@ const char* conv_igemm_prepare(const ConvIgemmDesc& d, ConvIgemmPlan* plan)
         if (!make_tensor_map(&plan->tmW8, d.weights4, (uint64_t)2 * d.num_taps * d.Cout, (uint64_t)d.Cin / 2, BN / 2, 128, 1))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the e2m1 weight matrix";
         plan->out.hi = plan->tmA;
+        plan->out.lo = plan->tmA8;
         if (p.kw_share && !make_tensor_map(&plan->out.hi, d.act, (uint64_t)d.a_total_rows, (uint64_t)d.Cin, 136, BK, 2))
             return "conv_igemm: cuTensorMapEncodeTiled failed for the 136-row activation box";
+        if (p.kw_share0 && !make_tensor_map(&plan->out.lo, d.act4, (uint64_t)d.a4_total_rows, (uint64_t)d.Cin / 2, 136, 128, 1))
+            return "conv_igemm: cuTensorMapEncodeTiled failed for the 136-row e2m1 activation box";
     }
     if (d.nterms == 2) {
         // the pair kernel streams the e4m3 planes in 128-byte rows (2 * BK channels per box)
@@ -1750,7 +1836,7 @@ const char* conv_igemm_run(const ConvIgemmPlan& plan, cudaStream_t stream)
         if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, KERNEL, __VA_ARGS__);                            \
     } while (0)
     switch (plan.variant) {
-        case 8: CL_LAUNCH(conv_igemm_pair_fp4_kernel, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out.hi, plan.p); break;
+        case 8: CL_LAUNCH(conv_igemm_pair_fp4_kernel, plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out.hi, plan.out.lo, plan.p); break;
         case 7: CL_LAUNCH((conv_igemm_pair_kernel<64, true>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
         case 6: CL_LAUNCH((conv_igemm_pair_kernel<32, true>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
         case 3: CL_LAUNCH((conv_igemm_pair_kernel<64, false>), plan.tmA, plan.tmW, plan.tmO, plan.tmA8, plan.tmW8, plan.out, plan.p); break;
