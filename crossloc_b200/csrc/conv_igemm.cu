@@ -1296,7 +1296,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             if (ldone) return false;
             if (ltap == p.num_taps) {
                 int tile = 0;
-                if (lane == 0) tile = feed_next(feed, num_tiles);
+                { CL_DBG_T0(); if (lane == 0) tile = feed_next(feed, num_tiles); if (leader) CL_DBG_ADD(12); }
                 tile = __shfl_sync(0xffffffffu, tile, 0);
                 if (tile < 0) { ldone = true; return false; }
                 lm0 = ((tile / p.tiles_n) * 2 + (int)crank) * kBlockM;
@@ -1338,7 +1338,7 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 #pragma unroll
             for (int u = 0; u < kSfAhead; u++) {
                 if (!qv[u]) { more = false; break; }
-                ptx::mbar_wait(ptx::smem_u32(&sf_empty[slot]), sphase ^ 1u, 3);
+                { CL_DBG_T0(); ptx::mbar_wait(ptx::smem_u32(&sf_empty[slot]), sphase ^ 1u, 3); if (leader) CL_DBG_ADD(11); }
                 const uint32_t dst = sf_base + (uint32_t)slot * kSfSlotBytes + (uint32_t)lane * 16u;
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(qa[u].x), "r"(qa[u].y), "r"(qa[u].z), "r"(qa[u].w) : "memory");
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 512u), "r"(qb0[u].x), "r"(qb0[u].y), "r"(qb0[u].z), "r"(qb0[u].w) : "memory");
