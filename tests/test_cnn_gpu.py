@@ -411,3 +411,34 @@ def test_mlr_fused_plan_matches_reference_math():
     with torch.no_grad():
         out2 = net(x)
     assert torch.equal(out, out2) and net._engine.launches > launches
+
+
+def test_kw_shared_tiles_equal_per_tap_tiles(tmp_path):
+    """The fp16 + fp4 convolution reads ONE 136-row activation tile at three row shifts for the kw taps of a filter row
+    (CROSSLOC_B200_KW_SHARE: 0 = one tile per tap, 1 = shared in the fp16 pass [default], 2 = also in the e2m1 pass).  The mode is
+    latched per process, so each runs in its own interpreter; the raw outputs agree up to the order of the fp32 accumulation."""
+    import subprocess
+    import sys
+    script = tmp_path / 'kw.py'
+    script.write_text('''
+import sys, torch
+sys.path.insert(0, %r)
+from tests import test_cnn_gpu as T
+torch.manual_seed(11)
+out = []
+for cin, cout, b, h, w in ((512, 512, 2, 17, 23), (256, 512, 1, 60, 90)):
+    conv = torch.nn.Conv2d(cin, cout, 3, 1, 1).cuda()
+    x = (torch.randn(b, cin, h, w, device='cuda') * 1.5).relu()
+    raw, stats = T.run_conv_fp4(x, conv, 32)
+    out += [raw.cpu(), stats.cpu()]
+torch.save(out, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    results = []
+    for mode in ('0', '1', '2'):
+        dst = tmp_path / ('out%s.pt' % mode)
+        env = dict(os.environ, CROSSLOC_B200_KW_SHARE=mode)
+        subprocess.check_call([sys.executable, str(script), str(dst)], env=env)
+        results.append(torch.load(dst))
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert rel_l2(a.double(), b.double()) < 2e-6
