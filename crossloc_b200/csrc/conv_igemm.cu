@@ -1531,10 +1531,21 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as ? kAcc1Col : 0u);
             const int nchunks = p.BN / 16;
             const StatsRows srows = stats_rows(valid, image);
-            for (int idx = grp; idx < nchunks; idx += 2) {
-                // drain order: the two chunks in tensor-memory columns 224..255 (the only ones the other accumulator
-                // shares) go first, one per warp group
-                const int c0 = as ? idx * 16 : (idx < 2 ? (nchunks - 2 + idx) * 16 : (idx - 2) * 16);
+            // drain order: the two chunks in tensor-memory columns 224..255 (the only ones the other accumulator
+            // shares) go first, one per warp group
+            auto chunk_col = [&](int idx) { return as ? idx * 16 : (idx < 2 ? (nchunks - 2 + idx) * 16 : (idx - 2) * 16); };
+            // groups of 16 channels (the 512-channel layers): the (sum, sum of squares) of the warp's up to eight chunks wait in
+            // registers for ONE reduce-scatter per tile -- the chain of dependent shuffles per chunk was the longest part of the
+            // 1x1 layers' drain (810 of ~1650 cycles per chunk, debug counters)
+            const bool defer16 = p.group_ch == 16;
+            float gsum[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) gsum[i] = 0.f;
+#pragma unroll 1
+            for (int k = 0; k < 8; k++) {
+                const int idx = grp + 2 * k;
+                if (idx >= nchunks) break;
+                const int c0 = chunk_col(idx);
                 uint32_t u[16];
                 { CL_DBG_T0(); ptx::tmem_ld_32x16(taddr + (uint32_t)c0, u);
                 ptx::tmem_ld_wait(); if (warp == 4) CL_DBG_ADD(8); }
@@ -1574,12 +1585,25 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     ptx::tma_store_commit();
                 }
                 // Measured with the debug counters (1x1 512->512, cycles per 16-column chunk and warp): tensor-memory load
-                // 35, scale / bias / staging / TMA store 700, GroupNorm sums 810.  Tried and dropped: one reduce-scatter of
-                // the sums per tile instead of per chunk (sums 810 -> 300, 1x1 layers 0.22 -> 0.20 ms, but 123 instead of 86
-                // registers and no gain on the whole step); staged coalesced st.global instead of the TMA store (920 cycles).
+                // 35, scale / bias / staging / TMA store 700, GroupNorm sums 810 -> 300 with one reduce-scatter per tile (below;
+                // same-box A/B: 1x1 layers 0.212 -> 0.199 ms).  Tried and dropped: staged coalesced st.global instead of the
+                // TMA store (920 cycles).
                 if (warp == 4) CL_DBG_SINCE(9, t_store);
                 CL_DBG_MARK(t_stats);
-                if (p.group_ch) {
+                if (defer16) {
+                    float sm = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const float xv = valid ? f[j] : 0.f;
+                        sm += xv;
+                        sq += xv * xv;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {   // static register indices: select instead of gsum[2 * k]
+                        gsum[2 * i] = i == k ? sm : gsum[2 * i];
+                        gsum[2 * i + 1] = i == k ? sq : gsum[2 * i + 1];
+                    }
+                } else if (p.group_ch) {
                     const int first_group = (n0 + c0) / p.group_ch;
                     switch (p.group_ch) {
                         case 2: stats_chunk<2, 16>(f, valid, image, lane, p.stats, p.groups, first_group, &srows); break;
@@ -1590,6 +1614,27 @@ conv_igemm_pair_fp4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     }
                 }
                 if (warp == 4) CL_DBG_SINCE(10, t_stats);
+            }
+            if (defer16 && srows.vmask != 0) {
+                CL_DBG_MARK(t_flush);
+                if (srows.uniform) {
+                    warp_reduce_scatter<16>(gsum, lane);
+                    if (scatter_owner<16>(lane)) {
+                        const int vi = scatter_index<16>(lane);
+                        const int idx = grp + 2 * (vi >> 1);
+                        if (idx < nchunks)
+                            atomicAdd(p.stats + ((size_t)srows.ref_image * p.groups + (n0 + chunk_col(idx)) / 16) * 2 + (vi & 1), (double)gsum[0]);
+                    }
+                } else if (valid) {
+                    // the warp's rows straddle two images (once per image boundary): every lane publishes its own sums
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int idx = grp + 2 * (i >> 1);
+                        if (idx < nchunks)
+                            atomicAdd(p.stats + ((size_t)image * p.groups + (n0 + chunk_col(idx)) / 16) * 2 + (i & 1), (double)gsum[i]);
+                    }
+                }
+                if (warp == 4) CL_DBG_SINCE(10, t_flush);
             }
             ptx::tc_fence_before();
         }
