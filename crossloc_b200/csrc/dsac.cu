@@ -14,6 +14,8 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "dsac.h"
 #include "dsac_common.cuh"
 #include "dsac_refine.cuh"
@@ -253,10 +255,14 @@ cudaError_t dsac_forward_launch(const DsacArgs& a, cudaStream_t stream, cudaEven
     dsac_score_kernel<<<dim3(a.hyps, a.B), kScoreThreads, 0, stream>>>(a);
     if (ev) cudaEventRecord(ev[2], stream);
     {
-        // cells per thread stay around four or fewer up to 8 CTAs (the portable cluster limit)
         const int n = a.Hc * a.Wc;
+        // measured at 60 x 90 cells (tools/dbg_refine_cluster.py, 32 frames): 1 / 2 / 4 / 8 CTAs per image = 0.80 / 0.74 / 0.58 /
+        // 0.76 ms -- beyond four CTAs the cluster barriers of the ~300 reductions cost more than the shorter passes save; in
+        // the live step (solve of batch k next to the stem of batch k + 1) four instead of eight: 19.48 -> 18.89 ms per step
         int cs = 1;
-        while (cs < 8 && n > cs * kRefineThreads * 3) cs *= 2;
+        while (cs < 8 && n > cs * kRefineThreads * 6) cs *= 2;
+        static const int cs_env = [] { const char* e = getenv("CROSSLOC_B200_REFINE_CLUSTER"); return e ? atoi(e) : 0; }();
+        if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8) cs = cs_env;   // tuning knob
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(a.B * cs));
         cfg.blockDim = dim3(kRefineThreads);
