@@ -160,6 +160,7 @@ class CoordNetEngine:
         self._conv_rec = {}
         self._keep_i = 0
         self._shared = {}
+        self.no_fp4 = set()   # ids of convolutions that must not use the fp16 + fp4 scheme (see nterms_of)
 
     # ------------------------------------------------------------------ parameters
     def _pack(self, name, conv, force_split=False):
@@ -167,7 +168,7 @@ class CoordNetEngine:
             return self.packer(name, conv)
         ver = (conv.weight._version, conv.weight.data_ptr(), None if conv.bias is None else conv.bias._version, force_split)
         if self._pack_versions.get(name) != ver:
-            nterms = _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0], conv.out_channels)
+            nterms = self.nterms_of(conv)
             if force_split and nterms in (2, 4):
                 nterms = 3   # the operand comes from outside the plan and has no e4m3 / e2m1 planes
             self._packs[name] = PackedConv(conv.weight, conv.bias, conv.stride[0], nterms)
@@ -292,7 +293,10 @@ class CoordNetEngine:
         return buf
 
     def nterms_of(self, conv):
-        return _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0], conv.out_channels)
+        n = _nterms_for(self.precision, conv.in_channels, conv.kernel_size[0], conv.stride[0], conv.out_channels)
+        if n == 4 and id(conv) in self.no_fp4:
+            n = 2   # its operand is written by a pass without e2m1 planes (MLR: encoder slices, cl_pf_groupnorm)
+        return n
 
     # ------------------------------------------------------------------ plans
     def forward(self, spec, image):

@@ -502,7 +502,10 @@ class TransPoseNet(nn.Module):
             return self.forward_train(inputs)
         if self.num_mlr != 0:
             if self._engine is None:
-                self._engine = CoordNetEngine()
+                # fp16 + fp4 inside the encoders and the decoder; the merge convolutions that read the concatenated encoder
+                # outputs / the mlr_norm result keep e4m3 corrections (those passes write no e2m1 planes)
+                self._engine = CoordNetEngine(fp4=True)
+                self._engine.no_fp4 = {id(self.mlr_skip[0]), id(self.mlr_forward[0])}
             return self._forward_mlr(inputs)
         return _run_native(self, self._spec(inputs), inputs)
 

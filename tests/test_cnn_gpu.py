@@ -401,12 +401,13 @@ def test_mlr_fused_plan_matches_reference_math():
         ref = net.forward_reference(x)
         via_train = net.forward_train(x)
     assert out.shape == ref.shape == (2, 4, 15, 17)
-    assert rel_l2(out[:, :3], ref[:, :3]) < 2e-4
-    assert rel_l2(out[:, 3:], ref[:, 3:]) < 1e-3
-    assert rel_l2(out[:, :3], via_train[:, :3]) < 2e-4
+    # encoders and decoder run the fp16 + fp4 scheme (1.7e-4 on the single-encoder network), the merge e4m3 corrections
+    assert rel_l2(out[:, :3], ref[:, :3]) < 5e-4
+    assert rel_l2(out[:, 3:], ref[:, 3:]) < 2e-3
+    assert rel_l2(out[:, :3], via_train[:, :3]) < 5e-4
     with torch.no_grad():
         unfused = net._forward_mlr_unfused(x)
-    assert rel_l2(out, unfused) < 2e-4   # fused merge (cl_pf_groupnorm, sliced encoder outputs) vs stock GroupNorm + torch.cat
+    assert rel_l2(out, unfused) < 5e-4   # fused merge (cl_pf_groupnorm, sliced encoder outputs) vs stock GroupNorm + torch.cat
     launches = net._engine.launches
     with torch.no_grad():
         out2 = net(x)
