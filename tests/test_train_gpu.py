@@ -259,3 +259,48 @@ def test_fused_plan_gradients_on_more_shapes(case):
     errs = {n: float((g_fast[n].double() - g_ref[n].double()).norm()) / max(float(g_ref[n].double().norm()), 1e-4 * scale)
             for n in g_ref}
     assert max(errs.values()) < 1e-1 and sorted(errs.values())[len(errs) // 2] < (5e-2 if fp4 else 2e-2)
+
+
+def test_default_plan_gradients_are_closer_to_fp32_than_stock_tf32():
+    """Whole-network gradients on frames large enough that single ReLU flips no longer dominate (2 x 480 x 720, full-width
+    TransPoseNet, the reference's coord MLE loss): the default arithmetic of the fused plan (fp16 + fp4 forward and data
+    gradients, one-pass weight gradients) against stock autograd in fp32 (TF32 off) -- within 1e-3 relative L2 over all
+    parameters, and closer than stock autograd with TF32 on, i.e. than what `train_single_task.py` runs by default."""
+    import networks.networks as nets
+    from crossloc_b200 import synth, train_plan
+    from loss.coord import scene_coords_regression_loss
+    from tests.test_loss_cpu import pixel_grid
+    torch.manual_seed(2021)
+    net = nets.TransPoseNet(torch.tensor(synth.NATURESCAPE_MEAN, dtype=torch.float32), False, False, 1, 1, 3, 1).to(DEV).train()
+    batch, h, w = 2, 480, 720
+    _, gt, poses, _ = synth.make_batch(0, batch, height=h, width=w)
+    images = torch.rand(batch, 3, h, w, device=DEV)
+    gt = torch.from_numpy(gt).to(DEV)
+    poses = torch.from_numpy(poses).float().to(DEV)
+    cam = torch.eye(3, device=DEV)
+    cam[0, 0] = cam[1, 1] = 480.0
+    cam[0, 2], cam[1, 2] = w / 2, h / 2
+    grid = pixel_grid().to(DEV)
+
+    def grads(forward):
+        net.zero_grad()
+        c, u = torch.split(forward(images), [3, 1], dim=1)
+        loss, _ = scene_coords_regression_loss(0.1, 100.0, 1000.0, 50.0, 'MLE', grid, -1, cam, c, u, poses, gt)
+        loss.backward()
+        return {n: p.grad.detach().double().clone() for n, p in net.named_parameters()}
+
+    def err(g, ref):
+        return (sum(float((g[n] - ref[n]).norm()) ** 2 for n in ref) ** 0.5) / (sum(float(ref[n].norm()) ** 2 for n in ref) ** 0.5)
+
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        ref = grads(net.forward_reference)
+        torch.backends.cudnn.allow_tf32 = True
+        stock_tf32 = err(grads(net.forward_reference), ref)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    object.__setattr__(net, '_train_plan', None)
+    native = err(grads(lambda t: train_plan.forward_train(net, t)), ref)
+    assert native < 1e-3, native
+    assert native < stock_tf32, (native, stock_tf32)
